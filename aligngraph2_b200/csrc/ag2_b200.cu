@@ -1,0 +1,638 @@
+// ag2_b200.cu -- kernels and the C ABI (include/ag2_b200.h) of the B200-native mecat2ref+ hot path.
+//
+// Built for sm_100a only (see __graft_entry__.build()).  No CPU fallback: every entry point needs a
+// live CUDA context and returns AG2_ENODEV / AG2_ECUDA otherwise.
+#include "../../include/ag2_b200.h"
+#include "xdrop_device.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ag2;
+
+static_assert(sizeof(ag2_candidate) == sizeof(Candidate), "ag2_candidate layout");
+static_assert(sizeof(ag2_record) == sizeof(Record), "ag2_record layout");
+
+namespace {
+
+constexpr int kChainWarps = 8;    // warps per CTA of the chain kernel
+constexpr int kFastK = 4;         // columns per lane on the fast path: 128-column band window
+constexpr int kWideK = 23;        // 736 columns: covers every possible block (N <= 718)
+constexpr int kWideWarps = 2;
+
+// ---------------------------------------------------------------------------------------------
+// packing kernels (A8: get_dna_encode_table + ">3 -> 0", MC/defs.cpp:3-36, mecat2ref_aux.cpp:195-197)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned encode_ascii(unsigned c, unsigned &irregular)
+{
+    unsigned code = 0;
+    irregular = 1;
+    switch (c) {
+    case 'A': code = 0; irregular = 0; break;
+    case 'C': code = 1; irregular = 0; break;
+    case 'G': code = 2; irregular = 0; break;
+    case 'T': code = 3; irregular = 0; break;
+    case 'a': code = 0; break;
+    case 'c': code = 1; break;
+    case 'g': code = 2; break;
+    case 't': code = 3; break;
+    default: break;
+    }
+    return code;
+}
+
+// one thread = 16 bases = one output word
+__global__ void pack_ref_kernel(const char *__restrict__ ascii, int64_t n, uint32_t *__restrict__ out)
+{
+    const int64_t nw = (n + 15) >> 4;
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        const int64_t base = w << 4;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (base + i < n) {
+                unsigned irr;
+                v |= encode_ascii((unsigned char)ascii[base + i], irr) << (2 * i);
+            }
+        }
+        out[w] = v;
+    }
+}
+
+// one thread = 32 bases of one read = two 2-bit words + one "irregular" word.
+// poff[r] = packed base offset of read r (multiple of 32); offs[r] = ASCII offset.
+__global__ void pack_reads_kernel(const char *__restrict__ ascii, const int64_t *__restrict__ offs,
+                                  const int64_t *__restrict__ poff, int64_t n_reads, int64_t n_groups,
+                                  uint32_t *__restrict__ out2, uint32_t *__restrict__ irr_out)
+{
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pb = g << 5;
+        int64_t lo = 0, hi = n_reads - 1; // last read with poff[r] <= pb
+        while (lo < hi) {
+            const int64_t mid = (lo + hi + 1) >> 1;
+            if (poff[mid] <= pb) lo = mid;
+            else hi = mid - 1;
+        }
+        const int64_t len = offs[lo + 1] - offs[lo];
+        const int64_t local = pb - poff[lo];
+        const char *src = ascii + offs[lo] + local;
+        uint32_t w0 = 0, w1 = 0, ir = 0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (local + i < len) {
+                unsigned irregular;
+                const unsigned code = encode_ascii((unsigned char)src[i], irregular);
+                if (i < 16) w0 |= code << (2 * i);
+                else w1 |= code << (2 * (i - 16));
+                ir |= irregular << i;
+            }
+        }
+        out2[2 * g] = w0;
+        out2[2 * g + 1] = w1;
+        irr_out[g] = ir;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// extension kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void extend_setup_kernel(const Candidate *cand, int64_t n, PackedSeqs sq, int64_t n_reads, ExtGeom *geom,
+                                    int64_t *caps)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        ExtGeom g;
+        caps[i] = setup_one(cand[i], sq, n_reads, g);
+        geom[i] = g;
+    }
+}
+
+// single-CTA exclusive scan of int64 (n up to a few million; plumbing, not a hot kernel).
+// out[i] = sum in[0..i), out[n] = total.
+__global__ void exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out)
+{
+    __shared__ int64_t part[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (n + blockDim.x - 1) / blockDim.x;
+    const int64_t lo = min(n, t * per), hi = min(n, lo + per);
+    int64_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += in[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int64_t acc = 0;
+        for (unsigned i = 0; i < blockDim.x; ++i) {
+            const int64_t v = part[i];
+            part[i] = acc;
+            acc += v;
+        }
+        out[n] = acc;
+    }
+    __syncthreads();
+    s = part[t];
+    for (int64_t i = lo; i < hi; ++i) {
+        const int64_t v = in[i];
+        out[i] = s;
+        s += v;
+    }
+}
+
+__global__ void set_slots_kernel(ExtGeom *geom, const int64_t *prefix, int64_t first, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        geom[first + i].slot = prefix[first + i] - prefix[first];
+}
+
+// Persistent warps pull chains (extension directions) from a global counter.
+template <int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
+{
+    __shared__ WarpSmem smem[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem &sm = smem[warp];
+    uint8_t *tb = g.tb + ((size_t)blockIdx.x * WARPS + warp) * g.tb_stride;
+    ChainCounters ctr = {0, 0, 0, 0, 0};
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(g.next, 1ull);
+        t = __shfl_sync(kFull, t, 0);
+        if ((int64_t)t >= g.n_chains) break;
+        const int64_t chain = g.queue ? (int64_t)g.queue[t] : (int64_t)t;
+        const bool done = run_chain<K>(g, chain, sm, tb, lane, ctr);
+        if (!done) {
+            ctr.wide += 1;
+            if (lane == 0 && g.wide_count) g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)chain;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&g.counters->cells, ctr.cells);
+        atomicAdd(&g.counters->rows, ctr.rows);
+        atomicAdd(&g.counters->blocks, ctr.blocks);
+        atomicAdd(&g.counters->interior, ctr.interior);
+        atomicAdd(&g.counters->wide, ctr.wide);
+    }
+}
+
+__global__ void extend_finalize_kernel(const Candidate *cand, const ExtGeom *geom, const ChainResult *res,
+                                       const int32_t *read_len, int64_t first, int64_t n, Record *rec,
+                                       int64_t *str_begin, int64_t *ok_len)
+{
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = first + k;
+        const Candidate c = cand[i];
+        const ExtGeom g = geom[i];
+        Record o;
+        int64_t sb;
+        const int rlen = g.valid ? read_len[c.read] : 0;
+        finalize_one(c, g, res[2 * i], res[2 * i + 1], rlen, o, sb);
+        rec[i] = o;
+        str_begin[i] = sb;
+        ok_len[i] = o.ok ? o.aln_len : 0;
+    }
+}
+
+// One CTA per record: workspace columns -> dense output, and fills aln_off.
+__global__ void compact_kernel(Record *rec, const int64_t *str_begin, const int64_t *dense_off, int64_t dense_base,
+                               int64_t first, int64_t n, const char *ws_q, const char *ws_t, char *out_q, char *out_t,
+                               unsigned long long *aligned, unsigned long long *columns)
+{
+    for (int64_t k = blockIdx.x; k < n; k += gridDim.x) {
+        const int64_t i = first + k;
+        const int64_t dst = dense_base + dense_off[i];
+        if (threadIdx.x == 0) rec[i].aln_off = dst;
+        if (!rec[i].ok) continue;
+        const int len = rec[i].aln_len;
+        const char *sq = ws_q + str_begin[i], *st = ws_t + str_begin[i];
+        for (int c = threadIdx.x; c < len; c += blockDim.x) {
+            out_q[dst + c] = sq[c];
+            out_t[dst + c] = st[c];
+        }
+        if (threadIdx.x == 0) {
+            atomicAdd(aligned, (unsigned long long)(rec[i].qe - rec[i].qb));
+            atomicAdd(columns, (unsigned long long)len);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace
+
+struct ag2_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    DevBuf ascii;                       // staging for ASCII uploads
+    DevBuf ref2;
+    int64_t ref_len = 0;
+    DevBuf reads2, reads_irr, read_off, read_len, ascii_offs;
+    int64_t n_reads = 0, read_bases = 0;
+
+    DevBuf cand, geom, caps, prefix, res, rec, str_begin, ok_len, dense_off;
+    int64_t n_cand = 0;
+    std::vector<int64_t> h_prefix;
+    DevBuf ws_q, ws_t;                  // workspace strings (one chunk of candidates)
+    DevBuf out_q, out_t;                // dense output strings
+    int64_t out_total = 0;
+    DevBuf tb, tb_wide;
+    DevBuf wide_queue;
+    DevBuf scalars;                     // ChainCounters + work counters + totals
+    size_t ws_limit = (size_t)6 << 30;  // bytes per workspace string per chunk
+    bool ran = false;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> chain_events;
+    ag2_extend_stats stats = {};
+};
+
+namespace {
+
+struct Scalars {
+    ChainCounters ctr;
+    unsigned long long next_fast, next_wide;
+    unsigned int wide_count, pad;
+    unsigned long long aligned, columns;
+};
+
+int fail(ag2_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? AG2_ENOMEM : AG2_ECUDA, "%s: %s",    \
+                        #call, cudaGetErrorString(e_));                                             \
+    } while (0)
+
+int reserve(ag2_ctx *ctx, DevBuf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return AG2_OK;
+    if (b.p) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t want = bytes + bytes / 16 + 256;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return AG2_OK;
+}
+
+#define RESERVE(buf, bytes)                                   \
+    do {                                                      \
+        int r_ = reserve(ctx, buf, bytes);                    \
+        if (r_ != AG2_OK) return r_;                          \
+    } while (0)
+
+int grid_for(int64_t items, int threads, int sm_count)
+{
+    int64_t g = (items + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+PackedSeqs seqs_of(const ag2_ctx *ctx)
+{
+    PackedSeqs s;
+    s.ref2 = (const uint32_t *)ctx->ref2.p;
+    s.ref_len = ctx->ref_len;
+    s.reads2 = (const uint32_t *)ctx->reads2.p;
+    s.reads_irr = (const uint32_t *)ctx->reads_irr.p;
+    s.read_off = (const int64_t *)ctx->read_off.p;
+    s.read_len = (const int32_t *)ctx->read_len.p;
+    return s;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *ag2_version(void) { return "aligngraph2_b200 0.1 (sm_100a)"; }
+
+const char *ag2_last_error(const ag2_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int ag2_ctx_create(int device, ag2_ctx **out)
+{
+    if (!out) return AG2_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return AG2_ENODEV;
+    if (device < 0 || device >= count) return AG2_EINVAL;
+    ag2_ctx *ctx = new ag2_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return AG2_ENODEV;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaMalloc(&ctx->scalars.p, sizeof(Scalars)) != cudaSuccess) {
+        delete ctx;
+        return AG2_ECUDA;
+    }
+    ctx->scalars.cap = sizeof(Scalars);
+    *out = ctx;
+    return AG2_OK;
+}
+
+void ag2_ctx_destroy(ag2_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *all[] = {&ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
+                     &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->res, &ctx->rec,
+                     &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
+                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->wide_queue, &ctx->scalars};
+    for (DevBuf *b : all)
+        if (b->p) cudaFree(b->p);
+    for (auto &e : ctx->chain_events) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void *ag2_ctx_stream(ag2_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len)
+{
+    if (!ctx || !ref || ref_len <= 0) return fail(ctx, AG2_EINVAL, "ag2_ref_load: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    RESERVE(ctx->ascii, (size_t)ref_len);
+    const int64_t nw = (ref_len + 15) >> 4;
+    RESERVE(ctx->ref2, (size_t)(nw + 4) * 4);
+    CK(cudaMemcpyAsync(ctx->ascii.p, ref, (size_t)ref_len, cudaMemcpyHostToDevice, ctx->stream));
+    pack_ref_kernel<<<grid_for(nw, 256, ctx->sm_count), 256, 0, ctx->stream>>>((const char *)ctx->ascii.p, ref_len,
+                                                                              (uint32_t *)ctx->ref2.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->ref_len = ref_len;
+    return AG2_OK;
+}
+
+int ag2_reads_load(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t n)
+{
+    if (!ctx || !bases || !offs || n <= 0 || offs[0] != 0) return fail(ctx, AG2_EINVAL, "ag2_reads_load: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int64_t> poff((size_t)n + 1);
+    std::vector<int32_t> lens((size_t)n);
+    int64_t p = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t len = offs[r + 1] - offs[r];
+        if (len < 0 || len > 0x7fffffff) return fail(ctx, AG2_EINVAL, "ag2_reads_load: read %ld has bad length", (long)r);
+        poff[r] = p;
+        lens[r] = (int32_t)len;
+        p += (len + 31) & ~(int64_t)31;
+    }
+    poff[n] = p;
+    const int64_t total = offs[n], groups = p >> 5;
+    RESERVE(ctx->ascii, (size_t)total + 64);
+    RESERVE(ctx->ascii_offs, (size_t)(n + 1) * 8);
+    RESERVE(ctx->read_off, (size_t)(n + 1) * 8);
+    RESERVE(ctx->read_len, (size_t)n * 4);
+    RESERVE(ctx->reads2, (size_t)(groups * 2 + 4) * 4);
+    RESERVE(ctx->reads_irr, (size_t)(groups + 4) * 4);
+    CK(cudaMemcpyAsync(ctx->ascii.p, bases, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ascii_offs.p, offs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->read_off.p, poff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->read_len.p, lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (groups > 0) {
+        pack_reads_kernel<<<grid_for(groups, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+            (const char *)ctx->ascii.p, (const int64_t *)ctx->ascii_offs.p, (const int64_t *)ctx->read_off.p, n, groups,
+            (uint32_t *)ctx->reads2.p, (uint32_t *)ctx->reads_irr.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream)); // poff/lens are stack-owned
+    ctx->n_reads = n;
+    ctx->read_bases = total;
+    return AG2_OK;
+}
+
+int ag2_extend_upload(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n)
+{
+    if (!ctx || !cand || n <= 0 || n > 0x3fffffff) return fail(ctx, AG2_EINVAL, "ag2_extend_upload: bad argument");
+    if (!ctx->ref_len || !ctx->n_reads) return fail(ctx, AG2_ESTATE, "ag2_extend_upload: load reference and reads first");
+    CK(cudaSetDevice(ctx->device));
+    RESERVE(ctx->cand, (size_t)n * sizeof(Candidate));
+    CK(cudaMemcpyAsync(ctx->cand.p, cand, (size_t)n * sizeof(Candidate), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_cand = n;
+    ctx->ran = false;
+    return AG2_OK;
+}
+
+int ag2_extend_run(ag2_ctx *ctx)
+{
+    if (!ctx || ctx->n_cand <= 0) return fail(ctx, AG2_ESTATE, "ag2_extend_run: no candidates uploaded");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n_cand;
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
+    RESERVE(ctx->geom, (size_t)n * sizeof(ExtGeom));
+    RESERVE(ctx->caps, (size_t)n * 8);
+    RESERVE(ctx->prefix, (size_t)(n + 1) * 8);
+    RESERVE(ctx->res, (size_t)n * 2 * sizeof(ChainResult));
+    RESERVE(ctx->rec, (size_t)n * sizeof(Record));
+    RESERVE(ctx->str_begin, (size_t)n * 8);
+    RESERVE(ctx->ok_len, (size_t)n * 8);
+    RESERVE(ctx->dense_off, (size_t)(n + 1) * 8);
+    RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
+
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xdrop_chains_kernel<kFastK, kChainWarps>, kChainWarps * 32, 0));
+    if (occ < 1) occ = 1;
+    const int fast_grid = ctx->sm_count * occ;
+    const size_t tb_stride = (size_t)(kMaxBlk + 2) * TbLayout<kFastK>::kRowBytes;
+    RESERVE(ctx->tb, tb_stride * fast_grid * kChainWarps);
+    const int wide_grid = ctx->sm_count;
+    const size_t tbw_stride = (size_t)(kMaxBlk + 2) * TbLayout<kWideK>::kRowBytes;
+    RESERVE(ctx->tb_wide, tbw_stride * wide_grid * kWideWarps);
+
+    const PackedSeqs sq = seqs_of(ctx);
+    Scalars *sc = (Scalars *)ctx->scalars.p;
+    CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+    extend_setup_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const Candidate *)ctx->cand.p, n, sq, ctx->n_reads,
+                                                                         (ExtGeom *)ctx->geom.p, (int64_t *)ctx->caps.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->caps.p, n, (int64_t *)ctx->prefix.p);
+    launches += 2;
+    CK(cudaGetLastError());
+    ctx->h_prefix.resize((size_t)n + 1);
+    CK(cudaMemcpyAsync(ctx->h_prefix.data(), ctx->prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const std::vector<int64_t> &pf = ctx->h_prefix;
+
+    size_t max_chunk = 0;
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    for (int64_t lo = 0; lo < n;) {
+        int64_t hi = lo + 1;
+        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= ctx->ws_limit) ++hi;
+        chunks.push_back({lo, hi});
+        const size_t need = (size_t)(pf[hi] - pf[lo]);
+        if (need > max_chunk) max_chunk = need;
+        lo = hi;
+    }
+    RESERVE(ctx->ws_q, max_chunk + 64);
+    RESERVE(ctx->ws_t, max_chunk + 64);
+    // upper bound of the dense strings: every column consumes a base of the read or the window
+    RESERVE(ctx->out_q, (size_t)pf[n] / 2 + ctx->read_bases + 64);
+    RESERVE(ctx->out_t, (size_t)pf[n] / 2 + ctx->read_bases + 64);
+
+    while (ctx->chain_events.size() < chunks.size()) {
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        ctx->chain_events.push_back({a, b});
+    }
+
+    // per chunk: chains -> (wide rerun) -> finalize -> scan of the ok lengths -> compaction into the
+    // dense output at the running base
+    int64_t dense_base = 0;
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const int64_t lo = chunks[ci].first, cn = chunks[ci].second - chunks[ci].first;
+        set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p, lo, cn);
+        CK(cudaMemsetAsync(&sc->next_fast, 0, 2 * sizeof(unsigned long long) + sizeof(unsigned int), st));
+        ChainArgs a = {};
+        a.seqs = sq;
+        a.cand = (const Candidate *)ctx->cand.p + lo;
+        a.geom = (const ExtGeom *)ctx->geom.p + lo;
+        a.res = (ChainResult *)ctx->res.p + 2 * lo;
+        a.ws_q = (char *)ctx->ws_q.p;
+        a.ws_t = (char *)ctx->ws_t.p;
+        a.tb = (uint8_t *)ctx->tb.p;
+        a.tb_stride = tb_stride;
+        a.n_chains = 2 * cn;
+        a.queue = nullptr;
+        a.next = &sc->next_fast;
+        a.wide_queue = (int32_t *)ctx->wide_queue.p;
+        a.wide_count = &sc->wide_count;
+        a.counters = &sc->ctr;
+        CK(cudaEventRecord(ctx->chain_events[ci].first, st));
+        xdrop_chains_kernel<kFastK, kChainWarps><<<fast_grid, kChainWarps * 32, 0, st>>>(a);
+        CK(cudaEventRecord(ctx->chain_events[ci].second, st));
+        CK(cudaGetLastError());
+        // chains whose band outgrew the fast window: rerun on the wide kernel (usually none)
+        unsigned int n_wide = 0;
+        CK(cudaMemcpyAsync(&n_wide, &sc->wide_count, sizeof n_wide, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        launches += 2;
+        if (n_wide > 0) {
+            ChainArgs w = a;
+            w.tb = (uint8_t *)ctx->tb_wide.p;
+            w.tb_stride = tbw_stride;
+            w.n_chains = n_wide;
+            w.queue = (const int32_t *)ctx->wide_queue.p;
+            w.next = &sc->next_wide;
+            w.wide_queue = nullptr;
+            w.wide_count = nullptr;
+            xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        extend_finalize_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>(
+            (const Candidate *)ctx->cand.p, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p,
+            (const int32_t *)ctx->read_len.p, lo, cn, (Record *)ctx->rec.p, (int64_t *)ctx->str_begin.p,
+            (int64_t *)ctx->ok_len.p);
+        // per-chunk scan, shifted by the running base
+        exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->ok_len.p + lo, cn, (int64_t *)ctx->dense_off.p + lo);
+        launches += 2;
+        int64_t chunk_total = 0;
+        CK(cudaMemcpyAsync(&chunk_total, (int64_t *)ctx->dense_off.p + lo + cn, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        compact_kernel<<<grid_for(cn, 1, ctx->sm_count * 2), 128, 0, st>>>(
+            (Record *)ctx->rec.p, (const int64_t *)ctx->str_begin.p, (const int64_t *)ctx->dense_off.p, dense_base, lo, cn,
+            (const char *)ctx->ws_q.p, (const char *)ctx->ws_t.p, (char *)ctx->out_q.p, (char *)ctx->out_t.p,
+            &sc->aligned, &sc->columns);
+        ++launches;
+        CK(cudaGetLastError());
+        dense_base += chunk_total;
+    }
+    CK(cudaStreamSynchronize(st));
+    ctx->out_total = dense_base;
+
+    // stats
+    Scalars hs;
+    CK(cudaMemcpy(&hs, sc, sizeof hs, cudaMemcpyDeviceToHost));
+    ag2_extend_stats &s = ctx->stats;
+    s.cells = (int64_t)hs.ctr.cells;
+    s.rows = (int64_t)hs.ctr.rows;
+    s.blocks = (int64_t)hs.ctr.blocks;
+    s.interior = (int64_t)hs.ctr.interior;
+    s.wide_chains = (int64_t)hs.ctr.wide;
+    s.aligned = (int64_t)hs.aligned;
+    s.columns = (int64_t)hs.columns;
+    s.launches = launches;
+    s.kernel_ms = 0;
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->chain_events[ci].first, ctx->chain_events[ci].second));
+        s.kernel_ms += ms;
+    }
+    ctx->ran = true;
+    return AG2_OK;
+}
+
+int ag2_extend_get_stats(ag2_ctx *ctx, ag2_extend_stats *out)
+{
+    if (!ctx || !out) return AG2_EINVAL;
+    if (!ctx->ran) return fail(ctx, AG2_ESTATE, "ag2_extend_get_stats: nothing ran");
+    *out = ctx->stats;
+    return AG2_OK;
+}
+
+int ag2_extend_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used)
+{
+    if (!ctx || !rec_out) return fail(ctx, AG2_EINVAL, "ag2_extend_fetch: bad argument");
+    if (!ctx->ran) return fail(ctx, AG2_ESTATE, "ag2_extend_fetch: call ag2_extend_run first");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n_cand;
+    CK(cudaMemcpyAsync(rec_out, ctx->rec.p, (size_t)n * sizeof(Record), cudaMemcpyDeviceToHost, ctx->stream));
+    if (aln_used) *aln_used = ctx->out_total;
+    int rc = AG2_OK;
+    if (qaln_out && saln_out && aln_cap >= ctx->out_total) {
+        CK(cudaMemcpyAsync(qaln_out, ctx->out_q.p, (size_t)ctx->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(saln_out, ctx->out_t.p, (size_t)ctx->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (qaln_out || saln_out) {
+        rc = fail(ctx, AG2_ECAP, "ag2_extend_fetch: need %ld bytes per string, have %ld", (long)ctx->out_total, (long)aln_cap);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out, char *qaln_out,
+                           char *saln_out, int64_t aln_cap, int64_t *aln_used)
+{
+    int r = ag2_extend_upload(ctx, cand, n);
+    if (r != AG2_OK) return r;
+    r = ag2_extend_run(ctx);
+    if (r != AG2_OK) return r;
+    return ag2_extend_fetch(ctx, rec_out, qaln_out, saln_out, aln_cap, aln_used);
+}
+
+} // extern "C"

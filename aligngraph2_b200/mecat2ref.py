@@ -1,0 +1,138 @@
+"""Host-side mirror of the reference's mecat2ref+ extension interface, over the C ABI.
+
+Reference seams (paths under mecat_plus/MECAT-master_1/src/):
+  * ``GapAligner::go`` / ``XdropAligner``      common/gapalign.h:4-25, common/xdrop_gapalign.cpp:359-439
+  * ``extend_candidate``                        mecat2ref/mecat2ref_aux.cpp:210-270
+  * ``candidate_save`` / ``TempResult``         mecat2ref/mecat2ref_defs.h:90-95, mecat2ref/output.h
+
+``Mecat2RefDevice`` owns one GPU context: load the (concatenated, upper-cased) reference once, load a
+batch of reads, then extend any number of candidates.  Results come back as ``TempResult``-like
+records; alignment strings are ASCII ``ACGT-`` exactly as the reference writes them.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import CANDIDATE_DTYPE, RECORD_DTYPE, Ag2Error, ExtendStats
+
+
+def _as_bytes_array(x) -> np.ndarray:
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(x, dtype=np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+class Mecat2RefDevice:
+    """One GPU's resident state for the mecat2ref+ hot path (reference + read batch)."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        self._ctx = C.c_void_p()
+        rc = self._L.ag2_ctx_create(device, C.byref(self._ctx))
+        if rc != 0:
+            raise Ag2Error(f"ag2_ctx_create(device={device}) failed: {_lib.ERRORS.get(rc, rc)} "
+                           "(a CUDA device is required; there is no CPU fallback)")
+        self.device = device
+        self.n_reads = 0
+        self.ref_len = 0
+        self._n_cand = 0
+
+    def close(self) -> None:
+        if self._ctx:
+            self._L.ag2_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            msg = self._L.ag2_last_error(self._ctx).decode(errors="replace")
+            raise Ag2Error(f"{what}: {_lib.ERRORS.get(rc, rc)}: {msg}")
+
+    # -- residency ---------------------------------------------------------------------------
+    def load_reference(self, ref) -> None:
+        """``ref``: ASCII bases of the concatenated reference (creat_ref_index, impl_large.cpp:432-437)."""
+        a = _as_bytes_array(ref)
+        self._check(self._L.ag2_ref_load(self._ctx, a.ctypes.data, a.size), "ag2_ref_load")
+        self.ref_len = int(a.size)
+
+    def load_reads(self, reads: Sequence | None = None, *, bases=None, offsets=None) -> None:
+        """Either a sequence of ASCII reads, or a concatenated ``bases`` buffer with ``offsets`` (n+1)."""
+        if reads is not None:
+            arrs = [_as_bytes_array(r) for r in reads]
+            offsets = np.zeros(len(arrs) + 1, dtype=np.int64)
+            np.cumsum([a.size for a in arrs], out=offsets[1:])
+            bases = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.uint8)
+        bases = _as_bytes_array(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        self._check(self._L.ag2_reads_load(self._ctx, bases.ctypes.data, offsets.ctypes.data, n), "ag2_reads_load")
+        self.n_reads = n
+
+    # -- extension ---------------------------------------------------------------------------
+    @staticmethod
+    def make_candidates(read, strand, loc1, loc2, score=None) -> np.ndarray:
+        n = len(read)
+        c = np.zeros(n, dtype=CANDIDATE_DTYPE)
+        c["read"], c["strand"], c["loc1"], c["loc2"] = read, strand, loc1, loc2
+        c["score"] = 0 if score is None else score
+        return c
+
+    def extend(self, cand: np.ndarray, qaln_out: np.ndarray | None = None, saln_out: np.ndarray | None = None):
+        """extend_candidate over a batch.  Returns (records, qaln, saln): records is a RECORD_DTYPE
+        array (one per candidate, ``ok`` as GapAligner::go returns), strings are uint8 ASCII buffers
+        indexed by ``aln_off``/``aln_len``."""
+        cand = np.ascontiguousarray(cand, dtype=CANDIDATE_DTYPE)
+        n = cand.size
+        rec = np.zeros(n, dtype=RECORD_DTYPE)
+        self.upload_candidates(cand)
+        self.run()
+        used = C.c_int64()
+        self._check(self._L.ag2_extend_fetch(self._ctx, rec.ctypes.data, None, None, 0, C.byref(used)), "ag2_extend_fetch")
+        if qaln_out is None or qaln_out.size < used.value:
+            qaln_out = np.empty(max(used.value, 1), dtype=np.uint8)
+        if saln_out is None or saln_out.size < used.value:
+            saln_out = np.empty(max(used.value, 1), dtype=np.uint8)
+        self._check(self._L.ag2_extend_fetch(self._ctx, rec.ctypes.data, qaln_out.ctypes.data, saln_out.ctypes.data,
+                                             qaln_out.size, C.byref(used)), "ag2_extend_fetch")
+        return rec, qaln_out[:used.value], saln_out[:used.value]
+
+    def extend_batch_into(self, cand: np.ndarray, rec: np.ndarray, qaln_out: np.ndarray, saln_out: np.ndarray) -> int:
+        """The single C-ABI call (ag2_xdrop_extend_batch) with caller-owned host buffers."""
+        used = C.c_int64()
+        self._check(self._L.ag2_xdrop_extend_batch(self._ctx, cand.ctypes.data, cand.size, rec.ctypes.data,
+                                                   qaln_out.ctypes.data, saln_out.ctypes.data, qaln_out.size,
+                                                   C.byref(used)), "ag2_xdrop_extend_batch")
+        return used.value
+
+    def upload_candidates(self, cand: np.ndarray) -> None:
+        cand = np.ascontiguousarray(cand, dtype=CANDIDATE_DTYPE)
+        self._check(self._L.ag2_extend_upload(self._ctx, cand.ctypes.data, cand.size), "ag2_extend_upload")
+        self._n_cand = cand.size
+
+    def run(self) -> None:
+        """Launch the extension kernels on resident data (no host<->device traffic but scalars)."""
+        self._check(self._L.ag2_extend_run(self._ctx), "ag2_extend_run")
+
+    def stats(self) -> dict:
+        s = ExtendStats()
+        self._check(self._L.ag2_extend_get_stats(self._ctx, C.byref(s)), "ag2_extend_get_stats")
+        return {k: getattr(s, k) for k, _ in ExtendStats._fields_}
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.ag2_ctx_stream(self._ctx) or 0)
+
+
+def record_strings(rec, qaln: np.ndarray, saln: np.ndarray):
+    """(qmap, smap) bytes of one record."""
+    o, n = int(rec["aln_off"]), int(rec["aln_len"])
+    return qaln[o:o + n].tobytes(), saln[o:o + n].tobytes()

@@ -1,0 +1,111 @@
+/*
+ * ag2_b200.h -- C ABI of the B200-native mecat2ref+ / PAGraph hot path (libag2_b200.so).
+ *
+ * The reference (Godotcoffee/AlignGraph2) has no FFI layer: its hot path sits behind process
+ * boundaries (AlignGraph2.py:265-277 spawns mecat2ref+).  In-process, the narrowest seams are
+ *   - GapAligner::go            mecat_plus/MECAT-master_1/src/common/gapalign.h:4-25
+ *   - extend_candidate          mecat_plus/MECAT-master_1/src/mecat2ref/mecat2ref_aux.cpp:210-270
+ *   - meap_ref_impl_large       mecat_plus/MECAT-master_1/src/mecat2ref/mecat2ref.cpp:602,995
+ * and the entry points below cut exactly there.  INTEGRATION.md shows the
+ * patch a maintainer would apply to reference_mapping() to call them.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; caller-owned HOST buffers unless a name says
+ * `_dev`; every function returns 0 on success or a negative AG2_E* code (ag2_last_error() gives
+ * the text); no exceptions cross the boundary; one ag2_ctx per GPU, not thread-safe.
+ * There is no CPU fallback: without a CUDA device ag2_ctx_create fails with AG2_ENODEV.
+ */
+#ifndef AG2_B200_H
+#define AG2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AG2_OK 0
+#define AG2_ENODEV (-1)   /* no usable CUDA device */
+#define AG2_ECUDA (-2)    /* CUDA runtime error */
+#define AG2_EINVAL (-3)   /* bad argument */
+#define AG2_ENOMEM (-4)   /* device or host allocation failed */
+#define AG2_ESTATE (-5)   /* call order (e.g. extend before reference/reads are loaded) */
+#define AG2_ECAP (-6)     /* caller buffer too small */
+
+typedef struct ag2_ctx ag2_ctx;
+
+/* One candidate = one call of extend_candidate (mecat2ref_aux.cpp:210): `candidate_save`
+ * (mecat2ref_defs.h:90-95) reduced to the fields the extension reads. */
+typedef struct ag2_candidate {
+    int32_t read;    /* index into the loaded read batch */
+    int32_t strand;  /* 0 = 'F' (read as given), 1 = 'R' (reverse complement, impl_large.cpp:799-833) */
+    int64_t loc1;    /* 1-based reference position of the seed (candidate_save::loc1) */
+    int32_t loc2;    /* 0-based position in the oriented read   (candidate_save::loc2) */
+    int32_t score;   /* candidate_save::score, copied to the record (TempResult::vscore) */
+} ag2_candidate;
+
+/* One extension result = TempResult (output.h) without the strings.  ok mirrors the return of
+ * GapAligner::go (qe - qb >= 1000, mecat2ref_aux.cpp:240).  Fields other than ok are only
+ * meaningful when ok != 0; aln_off/aln_len locate the two alignment strings. */
+typedef struct ag2_record {
+    int32_t ok;
+    int32_t read;
+    int32_t strand;
+    int32_t vscore;
+    int32_t qb, qe, qs;   /* strand-local read coordinates, read length */
+    int32_t aln_len;      /* alignment columns (strings are NOT NUL terminated) */
+    int64_t sb, se;       /* global (concatenated) reference coordinates */
+    int64_t aln_off;      /* offset of this record's columns in qaln_out / saln_out */
+} ag2_record;
+
+/* Device-side work counters of the last extend call (for the roofline: SURVEY.md 8d). */
+typedef struct ag2_extend_stats {
+    int64_t cells;        /* DP cell evaluations == inner-loop iterations of xdrop_align */
+    int64_t rows;         /* DP rows */
+    int64_t blocks;       /* xdrop_align calls */
+    int64_t aligned;      /* sum of (qe - qb) over ok records */
+    int64_t columns;      /* alignment columns emitted over ok records */
+    int64_t wide_chains;  /* extension directions that left the 128-column fast path */
+    int64_t interior;     /* rows that needed the exact interior-pruned-cell fix-up */
+    int64_t launches;     /* kernel launches made by the call */
+    double kernel_ms;     /* CUDA-event time of the dominant kernel (xdrop_chains_kernel) */
+} ag2_extend_stats;
+
+int ag2_ctx_create(int device, ag2_ctx **ctx);
+void ag2_ctx_destroy(ag2_ctx *ctx);
+const char *ag2_last_error(const ag2_ctx *ctx);
+const char *ag2_version(void);
+
+/* Reference: ASCII bases, already concatenated over chromosomes and upper-cased the way
+ * creat_ref_index does (impl_large.cpp:432-437).  Packed 2 bits/base on the device. */
+int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len);
+
+/* Read batch: ASCII bases, reads concatenated; offs has n+1 entries (offs[0] = 0).  Packed 2
+ * bits/base on the device with a side bitmask for bases the reverse strand must not complement
+ * (anything but upper-case ACGT). */
+int ag2_reads_load(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t n_reads);
+
+/* extend_candidate x n.  rec_out[n]; qaln_out/saln_out receive ASCII ACGT- columns of the ok
+ * records back to back (record i at [aln_off, aln_off + aln_len)); aln_cap is the capacity of
+ * each string buffer, *aln_used the bytes written.  AG2_ECAP if too small (rec_out is still
+ * filled, so the caller can size the buffers and call ag2_extend_fetch). */
+int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out,
+                           char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used);
+
+/* Split form of the same call for callers that keep inputs resident in HBM:
+ * _upload copies candidates, _run launches the kernels on resident data (no host traffic),
+ * _fetch copies records and strings back. */
+int ag2_extend_upload(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n);
+int ag2_extend_run(ag2_ctx *ctx);
+int ag2_extend_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_out, int64_t aln_cap,
+                     int64_t *aln_used);
+int ag2_extend_get_stats(ag2_ctx *ctx, ag2_extend_stats *out);
+
+/* The CUDA stream the context launches on (cudaStream_t as void*), for callers that time with
+ * their own events. */
+void *ag2_ctx_stream(ag2_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,174 @@
+"""ctypes bindings for the parity checkers.  TEST INFRASTRUCTURE ONLY.
+
+``Oracle``  -> oracle/libag2_oracle.so (this repo's C restatement; built by oracle/Makefile,
+               travels to the GPU box)
+``RefLib``  -> oracle/_ref/libref_mecat.so (the unmodified reference sources behind
+               oracle/ref_shim.cpp; only exists where /root/reference was available at build time)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package aligngraph2_b200 never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libag2_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libref_mecat.so")
+REF_BIN = os.path.join(HERE, "_ref", "mecat2ref")
+
+MAX_ALN = 500000  # MC/defs.h:202 MAX_SEQ_SIZE
+
+
+def build(ref: bool = True) -> None:
+    """Build the oracle (.so) and, when /root/reference is present, the reference checkers."""
+    subprocess.run(["make", "-s", "-C", HERE, "oracle"], check=True)
+    if ref and os.path.isdir("/root/reference/mecat_plus"):
+        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+
+
+class _Aln(C.Structure):
+    _fields_ = [
+        ("ok", C.c_int), ("qoff", C.c_int), ("qend", C.c_int), ("toff", C.c_int), ("tend", C.c_int),
+        ("aln_size", C.c_int), ("qaln", C.c_void_p), ("taln", C.c_void_p),
+        ("cells", C.c_long), ("rows", C.c_long), ("calls", C.c_long),
+    ]
+
+
+def _u8(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+class Oracle:
+    """The C restatement (oracle/ag2_oracle.c)."""
+
+    def __init__(self) -> None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        self.lib = C.CDLL(ORACLE_SO)
+        L = self.lib
+        L.orc_xdrop_new.restype = C.c_void_p
+        L.orc_xdrop_free.argtypes = [C.c_void_p]
+        L.orc_xdrop_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_long)]
+        L.orc_xdrop_go.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int, C.POINTER(_Aln)]
+        L.orc_extend_candidate.argtypes = [C.c_void_p, C.c_char_p, C.c_long, C.c_char_p, C.c_int,
+                                           C.c_long, C.c_long, C.POINTER(C.c_long), C.POINTER(_Aln)]
+        L.orc_xdrop_counters.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.POINTER(C.c_long),
+                                         C.POINTER(C.c_long)]
+        self.x = C.c_void_p(L.orc_xdrop_new())
+
+    def __del__(self):
+        try:
+            self.lib.orc_xdrop_free(self.x)
+        except Exception:
+            pass
+
+    def block(self, A, M, B, N, forward=True):
+        """One block DP.  A, B: uint8 code arrays in *memory* order; for forward=False the block
+        starts at the LAST element and runs towards index 0.  Returns (score, ae, be, ops, cells)."""
+        A = _u8(A)
+        B = _u8(B)
+        ops = np.zeros(M + N + 8, dtype=np.uint8)
+        ae, be, nops, cells = C.c_int(), C.c_int(), C.c_int(), C.c_long()
+        pa = A.ctypes.data + (0 if forward else len(A) - 1)
+        pb = B.ctypes.data + (0 if forward else len(B) - 1)
+        s = self.lib.orc_xdrop_block(self.x, pa, M, pb, N, int(forward), C.byref(ae), C.byref(be),
+                                     ops.ctypes.data, C.byref(nops), C.byref(cells))
+        return s, ae.value, be.value, ops[:nops.value].copy(), cells.value
+
+    def go(self, q, qstart, t, tstart, min_aln=1000):
+        q = _u8(q)
+        t = _u8(t)
+        a = _Aln()
+        self.lib.orc_xdrop_go(self.x, q.ctypes.data, qstart, len(q), t.ctypes.data, tstart, len(t), min_aln,
+                              C.byref(a))
+        return _aln_dict(a)
+
+    def extend(self, ref: bytes, read: bytes, loc1: int, loc2: int):
+        """extend_candidate on raw ASCII; ``read`` already oriented.  Returns dict with rec."""
+        a = _Aln()
+        rec = (C.c_long * 4)()
+        self.lib.orc_extend_candidate(self.x, ref, len(ref), read, len(read), loc1, loc2, rec, C.byref(a))
+        d = _aln_dict(a)
+        d.update(qb=rec[0], qe=rec[1], sb=rec[2], se=rec[3])
+        return d
+
+    def counters(self):
+        c, r, k = C.c_long(), C.c_long(), C.c_long()
+        self.lib.orc_xdrop_counters(self.x, C.byref(c), C.byref(r), C.byref(k))
+        return c.value, r.value, k.value
+
+
+def _aln_dict(a: _Aln) -> dict:
+    return dict(ok=a.ok, qoff=a.qoff, qend=a.qend, toff=a.toff, tend=a.tend, aln_size=a.aln_size,
+                qaln=C.string_at(a.qaln, a.aln_size), taln=C.string_at(a.taln, a.aln_size),
+                cells=a.cells, rows=a.rows, calls=a.calls)
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_SO)
+
+
+class RefLib:
+    """The unmodified reference GapAligner / extend_candidate (oracle/ref_shim.cpp)."""
+
+    def __init__(self) -> None:
+        self.lib = C.CDLL(REF_SO)
+        L = self.lib
+        L.ref_xdrop_new.restype = C.c_void_p
+        L.ref_xdrop_free.argtypes = [C.c_void_p]
+        L.ref_xdrop_go.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        L.ref_xdrop_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                      C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.POINTER(C.c_int)]
+        L.ref_extend_candidate.argtypes = [C.c_void_p, C.c_char_p, C.c_long, C.c_char_p, C.c_char_p, C.c_int,
+                                           C.c_long, C.c_long, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                           C.POINTER(C.c_long), C.c_void_p, C.c_void_p]
+        self.x = C.c_void_p(L.ref_xdrop_new())
+        self._qa = C.create_string_buffer(MAX_ALN)
+        self._ta = C.create_string_buffer(MAX_ALN)
+
+    def __del__(self):
+        try:
+            self.lib.ref_xdrop_free(self.x)
+        except Exception:
+            pass
+
+    def block(self, A, M, B, N, forward=True):
+        # one guard element on each side: the reference reads B[N] (dead value) at the band end
+        A = np.concatenate(([0], _u8(A), [0])).astype(np.uint8)
+        B = np.concatenate(([0], _u8(B), [0])).astype(np.uint8)
+        ops = np.zeros(M + N + 8, dtype=np.uint8)
+        ae, be, nops = C.c_int(), C.c_int(), C.c_int()
+        pa = A.ctypes.data + (1 if forward else len(A) - 2)
+        pb = B.ctypes.data + (1 if forward else len(B) - 2)
+        s = self.lib.ref_xdrop_block(self.x, pa, M, pb, N, int(forward), C.byref(ae), C.byref(be),
+                                     ops.ctypes.data, C.byref(nops))
+        return s, ae.value, be.value, ops[:nops.value].copy()
+
+    def go(self, q, qstart, t, tstart, min_aln=1000):
+        q = np.concatenate(([0], _u8(q), [0])).astype(np.uint8)
+        t = np.concatenate(([0], _u8(t), [0])).astype(np.uint8)
+        out = (C.c_int * 5)()
+        ok = self.lib.ref_xdrop_go(self.x, q.ctypes.data + 1, qstart, len(q) - 2, t.ctypes.data + 1, tstart,
+                                   len(t) - 2, min_aln, out, self._qa, self._ta)
+        n = out[4]
+        return dict(ok=ok, qoff=out[0], qend=out[1], toff=out[2], tend=out[3], aln_size=n,
+                    qaln=self._qa.raw[:n], taln=self._ta.raw[:n])
+
+    def extend(self, ref: bytes, read: bytes, loc1: int, loc2: int):
+        oi = (C.c_int * 4)()
+        ol = (C.c_long * 2)()
+        ok = self.lib.ref_extend_candidate(self.x, ref, len(ref), read, read, len(read), loc1, loc2, ord("F"), 0,
+                                           oi, ol, self._qa, self._ta)
+        if not ok:
+            return dict(ok=0)
+        qa = self._qa.value
+        return dict(ok=1, qb=oi[0], qe=oi[1], sb=ol[0], se=ol[1], qaln=qa, taln=self._ta.value, aln_size=len(qa))

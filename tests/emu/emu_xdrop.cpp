@@ -1,0 +1,147 @@
+// emu_xdrop.cpp -- runs the product's X-drop device code (xdrop_device.cuh) under the one-warp CPU
+// emulation of warp_emu.h.  TEST INFRASTRUCTURE ONLY: built by tests/emu/build.sh into
+// tests/emu/libemu_xdrop.so and loaded by tests/test_emu_xdrop.py.
+#define AG2_EMU 1
+#include "../../aligngraph2_b200/csrc/xdrop_device.cuh"
+
+#include <vector>
+
+using namespace ag2;
+
+namespace {
+
+template <int K>
+void block_impl(const uint8_t *A, int M, const uint8_t *B, int N, int *ae, int *be, uint8_t *ops, int *nops,
+                long *cells, int *overflow, long *interior)
+{
+    static WarpSmem sm;
+    std::vector<uint8_t> tb((size_t)(kMaxBlk + 2) * TbLayout<K>::kRowBytes);
+    memcpy(sm.A, A, M);
+    memcpy(sm.B, B, N);
+    int r_ae = 0, r_be = 0, r_n = 0, r_over = 0;
+    ChainCounters ctr = {0, 0, 0, 0, 0};
+    warp_emu::run_warp([&]() {
+        const int lane = warp_emu::st().cur;
+        ChainCounters lc = {0, 0, 0, 0, 0};
+        int a = 0, b = 0;
+        const int over = dp_block<K>(sm.A, M, sm.B, N, tb.data(), lane, a, b, lc);
+        __syncwarp();
+        if (lane == 0) {
+            r_over = over;
+            ctr = lc;
+            if (!over) {
+                int q, t, ac, m, w;
+                r_n = walk_block<K>(tb.data(), a, b, sm, q, t, ac, m, w);
+                r_ae = a;
+                r_be = b;
+            }
+        }
+    });
+    *ae = r_ae;
+    *be = r_be;
+    *nops = r_n;
+    *overflow = r_over;
+    *cells = (long)ctr.cells;
+    *interior = (long)ctr.interior;
+    static const uint8_t map[3] = {3, 0, 6}; // kOpSub/kOpGapA/kOpGapB -> reference op codes
+    for (int i = 0; i < r_n; ++i) ops[i] = map[sm.ops[i]];
+}
+
+void pack2(const char *s, int64_t n, std::vector<uint32_t> &w2, std::vector<uint32_t> &irr, int64_t base)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        int code = 0, ir = 1;
+        switch (s[i]) {
+        case 'A': code = 0; ir = 0; break;
+        case 'C': code = 1; ir = 0; break;
+        case 'G': code = 2; ir = 0; break;
+        case 'T': code = 3; ir = 0; break;
+        case 'a': code = 0; break;
+        case 'c': code = 1; break;
+        case 'g': code = 2; break;
+        case 't': code = 3; break;
+        default: code = 0; break;
+        }
+        const int64_t p = base + i;
+        w2[p >> 4] |= (uint32_t)code << (2 * (p & 15));
+        if (ir) irr[p >> 5] |= 1u << (p & 31);
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+void emu_dp_block(int K, const uint8_t *A, int M, const uint8_t *B, int N, int *ae, int *be, uint8_t *ops,
+                  int *nops, long *cells, int *overflow, long *interior)
+{
+    if (K == 2) block_impl<2>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
+    else if (K == 3) block_impl<3>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
+    else if (K == 4) block_impl<4>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
+    else if (K == 8) block_impl<8>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
+    else block_impl<23>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
+}
+
+// extend_candidate on raw ASCII (read as given + strand flag).  Returns ok; rec = qb qe sb se aln_len
+// cells wide; strings into qaln/taln.
+int emu_extend(int K, const char *ref, long ref_len, const char *read, int read_len, int strand, long loc1,
+               int loc2, long *rec, char *qaln, char *taln)
+{
+    std::vector<uint32_t> ref2((ref_len >> 4) + 2, 0), dummy((ref_len >> 5) + 2, 0);
+    pack2(ref, ref_len, ref2, dummy, 0);
+    std::vector<uint32_t> rd2((read_len >> 4) + 2, 0), irr((read_len >> 5) + 2, 0);
+    pack2(read, read_len, rd2, irr, 0);
+    int64_t roff = 0;
+    int32_t rlen = read_len;
+    PackedSeqs sq = {ref2.data(), ref_len, rd2.data(), irr.data(), &roff, &rlen};
+    Candidate c = {0, strand, loc1, loc2, 7};
+    ExtGeom g;
+    const int64_t cap = setup_one(c, sq, 1, g);
+    if (!g.valid) return -1;
+    std::vector<char> wq(cap + 1, '?'), wt(cap + 1, '?');
+    ChainResult res[2];
+    ChainCounters ctr = {0, 0, 0, 0, 0};
+    std::vector<uint8_t> tb((size_t)(kMaxBlk + 2) * TbLayout<23>::kRowBytes);
+    static WarpSmem sm;
+    ChainArgs a = {};
+    a.seqs = sq;
+    a.cand = &c;
+    a.geom = &g;
+    a.res = res;
+    a.ws_q = wq.data();
+    a.ws_t = wt.data();
+    a.n_chains = 2;
+    int wide = 0;
+    warp_emu::run_warp([&]() {
+        const int lane = warp_emu::st().cur;
+        ChainCounters lc = {0, 0, 0, 0, 0};
+        for (int chain = 0; chain < 2; ++chain) {
+            bool ok;
+            if (K == 2) ok = run_chain<2>(a, chain, sm, tb.data(), lane, lc);
+            else if (K == 3) ok = run_chain<3>(a, chain, sm, tb.data(), lane, lc);
+            else if (K == 4) ok = run_chain<4>(a, chain, sm, tb.data(), lane, lc);
+            else ok = run_chain<23>(a, chain, sm, tb.data(), lane, lc);
+            if (!ok) {
+                if (lane == 0) ++wide;
+                run_chain<23>(a, chain, sm, tb.data(), lane, lc);
+            }
+        }
+        if (lane == 0) ctr = lc;
+    });
+    Record o;
+    int64_t sb;
+    finalize_one(c, g, res[0], res[1], rlen, o, sb);
+    rec[0] = o.qb;
+    rec[1] = o.qe;
+    rec[2] = o.sb;
+    rec[3] = o.se;
+    rec[4] = o.aln_len;
+    rec[5] = (long)ctr.cells;
+    rec[6] = wide;
+    rec[7] = (long)ctr.interior;
+    memcpy(qaln, wq.data() + sb, o.aln_len);
+    memcpy(taln, wt.data() + sb, o.aln_len);
+    return o.ok;
+}
+
+} // extern "C"
