@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- aligned Gbp/s of the mecat2ref+ extension hot path on B200 (BASELINE.json metric).
+
+Workload at N=1: BASELINE.json configs[1] -- 500k synthetic PacBio CLR reads (10 kb templates, 15 %
+error) against a 5 Mb reference, X-drop DP-extend stage only (one seed anchor per read).  A "step"
+is one pass of the extension over the whole read batch.
+
+  value : whole-job aligned Gbp/s with reads, reference and candidates already resident in HBM
+  e2e   : the same through the reference-facing C-ABI calls with HOST (pinned) buffers: ASCII reads
+          host->device + pack, candidates up, records and both alignment strings device->host
+  roofline / cpu_baseline : see DESIGN.md "Measurement"
+
+`--impl reference` times the reference's own CPU implementation of the same stage (the unmodified
+XdropAligner behind oracle/_ref/libref_mecat.so when it was built, else the oracle port) on all host
+cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "aligned_gbp_per_s"
+UNIT = "Gbp/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=500_000, help="reads per GPU (configs[1]: 500k)")
+    ap.add_argument("--ref-len", type=int, default=5_000_000)
+    ap.add_argument("--tlen", type=int, default=10_000)
+    ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--cpu-sample-per-core", type=int, default=150, help="reads per host core in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def make_workload(args, rank: int, device: str):
+    from aligngraph2_b200 import synth
+    d = synth.make_batch_torch(args.seed + 1000 * rank, args.ref_len, args.reads, args.tlen, device=device)
+    return d
+
+
+def cpu_worker(job):
+    """One host core: extend_candidate over a slice of the sample with the reference (or the port)."""
+    kind, ref, bases, off, strand, loc1, loc2, lo, hi = job
+    from aligngraph2_b200 import synth
+    from oracle import binding
+    eng = binding.RefLib() if kind == "reference" else binding.Oracle()
+    aligned = 0
+    t0 = time.perf_counter()
+    for i in range(lo, hi):
+        rd = synth.orient(bases[off[i]:off[i + 1]].tobytes(), int(strand[i]))
+        a = eng.extend(ref, rd, int(loc1[i]), int(loc2[i]))
+        if a["ok"]:
+            aligned += a["qe"] - a["qb"]
+    return aligned, time.perf_counter() - t0
+
+
+def cpu_baseline(ref, bases, off, strand, loc1, loc2, n_sample: int, cores: int):
+    """aligned Gbp/s of the CPU implementation on `cores` processes over the first n_sample reads."""
+    import multiprocessing as mp
+    from oracle import binding
+    binding.build(ref=False)
+    kind = "reference" if binding.have_ref() else "port"
+    n_sample = max(cores, min(n_sample, len(off) - 1))
+    cut = int(off[n_sample])
+    refb = ref.tobytes()
+    sub = bases[:cut]
+    bounds = np.linspace(0, n_sample, cores + 1).astype(int)
+    jobs = [(kind, refb, sub, off[:n_sample + 1], strand, loc1, loc2, int(bounds[k]), int(bounds[k + 1])) for k in range(cores)]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    aligned = sum(r[0] for r in res)
+    busy = max(r[1] for r in res)
+    return {"value": aligned / busy / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {n_sample} reads of the workload ({aligned / 1e6:.1f} Mbp aligned), extend stage only, "
+                      f"{cores} processes x 1 thread, slowest worker {busy:.1f} s (pool wall {wall:.1f} s)"}
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU path on this box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    cores = host_cores()
+    n_sample = min(args.reads, cores * args.cpu_sample_per_core)
+    a2 = argparse.Namespace(**vars(args))
+    a2.reads = n_sample
+    d = make_workload(a2, 0, dev)
+    ref, bases, off = d["ref"].cpu().numpy(), d["bases"].cpu().numpy(), d["offsets"].cpu().numpy()
+    strand, loc1, loc2 = d["strand"].cpu().numpy(), d["loc1"].cpu().numpy(), d["loc2"].cpu().numpy()
+    vals, last = [], None
+    for it in range(args.warmup + args.steps):
+        # each step = the same bounded sample; the CPU path has no warm-up effect worth more than one pass
+        if it < args.warmup and it > 0:
+            continue
+        last = cpu_baseline(ref, bases, off, strand, loc1, loc2, n_sample, cores)
+        if it >= args.warmup:
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    last["value"] = v
+    aligned_per_step = float(last["sample"].split("(")[1].split(" Mbp")[0]) * 1e6
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": aligned_per_step / (v * 1e9) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": workload_config(args, sample=n_sample), "cpu_baseline": last,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, sample=None):
+    c = {"workload": f"BASELINE configs[1]: {args.reads} synthetic PacBio CLR reads/GPU ({args.tlen} bp templates, 15% error: "
+                     f"60/25/15 ins/del/sub) vs {args.ref_len} bp uniform reference, X-drop DP-extend stage only, one seed anchor per read",
+         "reads_per_gpu": args.reads, "ref_len": args.ref_len, "seed": args.seed,
+         "l2": "inputs larger than L2 (packed reads + traceback scratch >> 126 MB)"}
+    if sample is not None:
+        c["cpu_sample_reads"] = sample
+    return c
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from aligngraph2_b200.lib import CANDIDATE_DTYPE, RECORD_DTYPE
+    from aligngraph2_b200.mecat2ref import Mecat2RefDevice
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: aligngraph2_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic inputs (generated on the device, then staged in pinned host memory) ----
+    d = make_workload(args, rank, "cuda")
+    n = args.reads
+    h_ref = d["ref"].cpu().numpy()
+    h_bases = torch.empty(d["bases"].numel(), dtype=torch.uint8, pin_memory=True)
+    h_bases.copy_(d["bases"])
+    h_off = d["offsets"].cpu().numpy()
+    cand = np.zeros(n, dtype=CANDIDATE_DTYPE)
+    cand["read"] = np.arange(n)
+    cand["strand"] = d["strand"].cpu().numpy()
+    cand["loc1"] = d["loc1"].cpu().numpy()
+    cand["loc2"] = d["loc2"].cpu().numpy()
+    cand["score"] = 8
+    h_cand_t = torch.from_numpy(cand.view(np.uint8)).pin_memory()
+    h_cand = h_cand_t.numpy().view(CANDIDATE_DTYPE)
+    total_bases = int(h_off[-1])
+    del d
+    torch.cuda.empty_cache()
+
+    dev = Mecat2RefDevice(local)
+    dev.load_reference(h_ref)
+    bases_np = h_bases.numpy()
+    dev.load_reads(bases=bases_np, offsets=h_off)
+    dev.upload_candidates(h_cand)
+    stream = torch.cuda.ExternalStream(dev.stream)
+
+    # ---- device-resident timing: `value` ----
+    for _ in range(args.warmup):
+        dev.run()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    kernel_ms = 0.0
+    for _ in range(args.steps):
+        dev.run()
+        kernel_ms += dev.stats()["kernel_ms"]
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    st = dev.stats()
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    agg = torch.tensor([float(st["aligned"]), float(st["cells"])], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    aligned_all = float(agg[0].item())
+    value = aligned_all * args.steps / (ms_max * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with host buffers: `e2e` ----
+    e2e = None
+    if not args.no_e2e:
+        rec = torch.empty(n * RECORD_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+        cap = int(st["columns"]) + 4096
+        h_q = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        h_s = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        rec_np = rec.numpy().view(RECORD_DTYPE)
+
+        def step():
+            dev.load_reads(bases=bases_np, offsets=h_off)
+            return dev.extend_batch_into(h_cand, rec_np, h_q.numpy(), h_s.numpy())
+
+        step()
+        barrier()
+        e0.record(stream)
+        used = 0
+        for _ in range(args.steps):
+            used = step()
+        e1.record(stream)
+        barrier()
+        t2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        aligned_e2e = float(rec_np["qe"][rec_np["ok"] == 1].astype(np.int64).sum() - rec_np["qb"][rec_np["ok"] == 1].astype(np.int64).sum())
+        a2 = torch.tensor([aligned_e2e], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(a2, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(a2.item()) * args.steps / (float(t2.item()) * 1e-3) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(total_bases + h_off.nbytes + h_cand.nbytes),
+               "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used), "ms_per_step": float(t2.item()) / args.steps}
+
+    # ---- roofline of the dominant kernel (xdrop_chains_kernel) ----
+    peak, peak_src = peaks()
+    cbar = st["cells"] / max(1, st["aligned"])
+    b_alg = 3.0 * cbar + 3.6                      # bytes per aligned base, SURVEY.md 8(d)
+    kern_s = kernel_ms / args.steps * 1e-3
+    achieved = b_alg * st["aligned"] / kern_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "xdrop_chains_kernel<4,8>", "kernel_ms_per_launch": kernel_ms / args.steps,
+                "algorithmic_bytes_per_aligned_base": b_alg, "cells_per_aligned_base": cbar,
+                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        ns = min(n, cores * args.cpu_sample_per_core)
+        cpu = cpu_baseline(h_ref, bases_np, h_off, cand["strand"], cand["loc1"], cand["loc2"], ns, cores)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+                "e2e": e2e, "gpu_launches": int(st["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+                "stats": {k: st[k] for k in ("cells", "rows", "blocks", "aligned", "columns", "wide_chains", "interior")}}
+        print(json.dumps(line))
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
