@@ -4,6 +4,7 @@
 // live CUDA context and returns AG2_ENODEV / AG2_ECUDA otherwise.
 #include "../../include/ag2_b200.h"
 #include "xdrop_device.cuh"
+#include "xdrop_fast.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -19,7 +20,7 @@ static_assert(sizeof(ag2_record) == sizeof(Record), "ag2_record layout");
 namespace {
 
 constexpr int kChainWarps = 8;    // warps per CTA of the chain kernel
-constexpr int kFastK = 4;         // columns per lane on the fast path: 128-column band window
+constexpr int kFastMinCtas = 3;   // resident CTAs per SM the fast kernel is compiled for (24 warps)
 constexpr int kWideK = 23;        // 736 columns: covers every possible block (N <= 718)
 constexpr int kWideWarps = 2;
 
@@ -145,7 +146,38 @@ __global__ void set_slots_kernel(ExtGeom *geom, const int64_t *prefix, int64_t f
         geom[first + i].slot = prefix[first + i] - prefix[first];
 }
 
-// Persistent warps pull chains (extension directions) from a global counter.
+// Fast path: persistent warps pull chains (extension directions) from a global counter; chains whose
+// band outgrows the 128-column window are queued for the wide kernel below.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, kFastMinCtas) xdrop_chains_fast_kernel(ChainArgs g)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FastSmem *smem = reinterpret_cast<FastSmem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    FastSmem &sm = smem[warp];
+    uint8_t *tb = g.tb + ((size_t)blockIdx.x * WARPS + warp) * g.tb_stride;
+    ChainCounters ctr = {0, 0, 0, 0, 0};
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(g.next, 1ull);
+        t = __shfl_sync(kFull, t, 0);
+        if ((int64_t)t >= g.n_chains) break;
+        const bool done = run_chain_fast(g, (int64_t)t, sm, tb, lane, ctr);
+        if (!done) {
+            ctr.wide += 1;
+            if (lane == 0) g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)t;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&g.counters->cells, ctr.cells);
+        atomicAdd(&g.counters->rows, ctr.rows);
+        atomicAdd(&g.counters->blocks, ctr.blocks);
+        atomicAdd(&g.counters->interior, ctr.interior);
+        atomicAdd(&g.counters->wide, ctr.wide);
+    }
+}
+
+// Wide path (any band a block can have): the int32 row kernel with K columns per lane.
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
 {
@@ -466,10 +498,12 @@ int ag2_extend_run(ag2_ctx *ctx)
     RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
 
     int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xdrop_chains_kernel<kFastK, kChainWarps>, kChainWarps * 32, 0));
+    const size_t fast_smem = sizeof(FastSmem) * kChainWarps;
+    CK(cudaFuncSetAttribute(xdrop_chains_fast_kernel<kChainWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xdrop_chains_fast_kernel<kChainWarps>, kChainWarps * 32, fast_smem));
     if (occ < 1) occ = 1;
     const int fast_grid = ctx->sm_count * occ;
-    const size_t tb_stride = (size_t)(kMaxBlk + 2) * TbLayout<kFastK>::kRowBytes;
+    const size_t tb_stride = (size_t)(kMaxBlk + 2) * 64;
     RESERVE(ctx->tb, tb_stride * fast_grid * kChainWarps);
     const int wide_grid = ctx->sm_count;
     const size_t tbw_stride = (size_t)(kMaxBlk + 2) * TbLayout<kWideK>::kRowBytes;
@@ -534,7 +568,7 @@ int ag2_extend_run(ag2_ctx *ctx)
         a.wide_count = &sc->wide_count;
         a.counters = &sc->ctr;
         CK(cudaEventRecord(ctx->chain_events[ci].first, st));
-        xdrop_chains_kernel<kFastK, kChainWarps><<<fast_grid, kChainWarps * 32, 0, st>>>(a);
+        xdrop_chains_fast_kernel<kChainWarps><<<fast_grid, kChainWarps * 32, fast_smem, st>>>(a);
         CK(cudaEventRecord(ctx->chain_events[ci].second, st));
         CK(cudaGetLastError());
         // chains whose band outgrew the fast window: rerun on the wide kernel (usually none)

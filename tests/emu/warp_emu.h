@@ -134,6 +134,16 @@ inline T __shfl_up_sync(unsigned m, T v, unsigned d)
     const T o = __shfl_sync(m, v, lane - (int)d);
     return lane >= (int)d ? o : v;
 }
+template <typename T>
+inline T __shfl_down_sync(unsigned m, T v, unsigned d)
+{
+    const int lane = warp_emu::st().cur;
+    const T o = __shfl_sync(m, v, (lane + (int)d) & 31);
+    return lane + (int)d < 32 ? o : v;
+}
+struct uint4 { unsigned x, y, z, w; };
+template <typename T>
+inline T __ldcg(const T *p) { return *p; }
 inline unsigned __ballot_sync(unsigned, bool p)
 {
     const uint64_t *buf = warp_emu::exchange(p ? 1 : 0);
