@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--ref-len", type=int, default=5_000_000)
     ap.add_argument("--tlen", type=int, default=10_000)
     ap.add_argument("--seed", type=int, default=20261017)
-    ap.add_argument("--cpu-sample-per-core", type=int, default=150, help="reads per host core in the CPU baseline sample")
+    ap.add_argument("--cpu-sample-per-core", type=int, default=1000, help="reads per host core in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
