@@ -5,7 +5,9 @@
 #include "../../include/ag2_b200.h"
 #include "xdrop_device.cuh"
 #include "xdrop_fast.cuh"
+#include "xdrop_lane.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -101,11 +103,13 @@ __global__ void pack_reads_kernel(const char *__restrict__ ascii, const int64_t 
 // extension kernels
 // ---------------------------------------------------------------------------------------------
 __global__ void extend_setup_kernel(const Candidate *cand, int64_t n, PackedSeqs sq, int64_t n_reads, ExtGeom *geom,
-                                    int64_t *caps)
+                                    int64_t *caps, int64_t *nmeta)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         ExtGeom g;
-        caps[i] = setup_one(cand[i], sq, n_reads, g);
+        int64_t m;
+        caps[i] = setup_one(cand[i], sq, n_reads, g, m);
+        nmeta[i] = m;
         geom[i] = g;
     }
 }
@@ -140,10 +144,45 @@ __global__ void exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out)
     }
 }
 
-__global__ void set_slots_kernel(ExtGeom *geom, const int64_t *prefix, int64_t first, int64_t n)
+__global__ void set_slots_kernel(ExtGeom *geom, const int64_t *prefix, const int64_t *meta_prefix, int64_t first, int64_t n)
 {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         geom[first + i].slot = prefix[first + i] - prefix[first];
+        geom[first + i].meta = meta_prefix[first + i] - meta_prefix[first];
+    }
+}
+
+// Lane path (xdrop_lane.cuh): one thread per extension direction, 32 directions in lock step per
+// warp, refilled from a global queue at block boundaries.
+__global__ void __launch_bounds__(kLaneThreads) xdrop_lane_kernel(LaneArgs g)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    LaneSmem &sm = *reinterpret_cast<LaneSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    uint8_t *scratch = g.scratch + ((size_t)blockIdx.x * kLaneThreads + tid) * kLaneScratch;
+    lane_kernel_body(g, sm, tid, scratch);
+}
+
+// One warp per record: the two directions' workspace areas -> dense strings; fills aln_off.
+__global__ void assemble_kernel(Record *rec, const ExtGeom *geom, const ChainResult *res, const uint32_t *meta,
+                                const int64_t *dense_off, int64_t dense_base, int64_t first, int64_t n, const char *ws_q,
+                                const char *ws_t, char *out_q, char *out_t, unsigned long long *aligned,
+                                unsigned long long *columns)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = warp; k < n; k += nwarps) {
+        const int64_t i = first + k;
+        const int64_t dst = dense_base + dense_off[i];
+        if (lane == 0) rec[i].aln_off = dst;
+        if (!rec[i].ok) continue;
+        assemble_record(geom[i], res[2 * i], res[2 * i + 1], meta, ws_q, ws_t, out_q + dst, out_t + dst, lane);
+        if (lane == 0) {
+            atomicAdd(aligned, (unsigned long long)(rec[i].qe - rec[i].qb));
+            atomicAdd(columns, (unsigned long long)rec[i].aln_len);
+        }
+    }
 }
 
 // Fast path: persistent warps pull chains (extension directions) from a global counter; chains whose
@@ -270,9 +309,9 @@ struct ag2_ctx {
     DevBuf reads2, reads_irr, read_off, read_len, ascii_offs;
     int64_t n_reads = 0, read_bases = 0;
 
-    DevBuf cand, geom, caps, prefix, res, rec, str_begin, ok_len, dense_off;
+    DevBuf cand, geom, caps, prefix, nmeta, meta_prefix, meta, res, rec, str_begin, ok_len, dense_off;
     int64_t n_cand = 0;
-    std::vector<int64_t> h_prefix;
+    std::vector<int64_t> h_prefix, h_meta_prefix;
     DevBuf ws_q, ws_t;                  // workspace strings (one chunk of candidates)
     DevBuf out_q, out_t;                // dense output strings
     int64_t out_total = 0;
@@ -397,7 +436,7 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
-                     &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->res, &ctx->rec,
+                     &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
                      &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->wide_queue, &ctx->scalars};
     for (DevBuf *b : all)
@@ -490,6 +529,8 @@ int ag2_extend_run(ag2_ctx *ctx)
     RESERVE(ctx->geom, (size_t)n * sizeof(ExtGeom));
     RESERVE(ctx->caps, (size_t)n * 8);
     RESERVE(ctx->prefix, (size_t)(n + 1) * 8);
+    RESERVE(ctx->nmeta, (size_t)n * 8);
+    RESERVE(ctx->meta_prefix, (size_t)(n + 1) * 8);
     RESERVE(ctx->res, (size_t)n * 2 * sizeof(ChainResult));
     RESERVE(ctx->rec, (size_t)n * sizeof(Record));
     RESERVE(ctx->str_begin, (size_t)n * 8);
@@ -497,14 +538,14 @@ int ag2_extend_run(ag2_ctx *ctx)
     RESERVE(ctx->dense_off, (size_t)(n + 1) * 8);
     RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
 
+    // lane kernel: as many CTAs per SM as shared memory allows (band + target block per thread)
     int occ = 0;
-    const size_t fast_smem = sizeof(FastSmem) * kChainWarps;
-    CK(cudaFuncSetAttribute(xdrop_chains_fast_kernel<kChainWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xdrop_chains_fast_kernel<kChainWarps>, kChainWarps * 32, fast_smem));
+    const size_t lane_smem = sizeof(LaneSmem);
+    CK(cudaFuncSetAttribute(xdrop_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xdrop_lane_kernel, kLaneThreads, lane_smem));
     if (occ < 1) occ = 1;
-    const int fast_grid = ctx->sm_count * occ;
-    const size_t tb_stride = (size_t)(kMaxBlk + 2) * 64;
-    RESERVE(ctx->tb, tb_stride * fast_grid * kChainWarps);
+    const int lane_grid = ctx->sm_count * occ;
+    RESERVE(ctx->tb, (size_t)kLaneScratch * lane_grid * kLaneThreads);
     const int wide_grid = ctx->sm_count;
     const size_t tbw_stride = (size_t)(kMaxBlk + 2) * TbLayout<kWideK>::kRowBytes;
     RESERVE(ctx->tb_wide, tbw_stride * wide_grid * kWideWarps);
@@ -513,31 +554,42 @@ int ag2_extend_run(ag2_ctx *ctx)
     Scalars *sc = (Scalars *)ctx->scalars.p;
     CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
     extend_setup_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const Candidate *)ctx->cand.p, n, sq, ctx->n_reads,
-                                                                         (ExtGeom *)ctx->geom.p, (int64_t *)ctx->caps.p);
+                                                                         (ExtGeom *)ctx->geom.p, (int64_t *)ctx->caps.p,
+                                                                         (int64_t *)ctx->nmeta.p);
     exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->caps.p, n, (int64_t *)ctx->prefix.p);
-    launches += 2;
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->nmeta.p, n, (int64_t *)ctx->meta_prefix.p);
+    launches += 3;
     CK(cudaGetLastError());
     ctx->h_prefix.resize((size_t)n + 1);
+    ctx->h_meta_prefix.resize((size_t)n + 1);
     CK(cudaMemcpyAsync(ctx->h_prefix.data(), ctx->prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_meta_prefix.data(), ctx->meta_prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const std::vector<int64_t> &pf = ctx->h_prefix;
+    const std::vector<int64_t> &pf = ctx->h_prefix, &mf = ctx->h_meta_prefix;
 
-    size_t max_chunk = 0;
+    // candidates are processed in chunks whose workspace strings fit ws_limit
+    size_t max_chunk = 0, max_meta = 0;
     std::vector<std::pair<int64_t, int64_t>> chunks;
     for (int64_t lo = 0; lo < n;) {
         int64_t hi = lo + 1;
         while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= ctx->ws_limit) ++hi;
         chunks.push_back({lo, hi});
-        const size_t need = (size_t)(pf[hi] - pf[lo]);
-        if (need > max_chunk) max_chunk = need;
+        max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
+        max_meta = std::max(max_meta, (size_t)(mf[hi] - mf[lo]));
         lo = hi;
     }
     RESERVE(ctx->ws_q, max_chunk + 64);
     RESERVE(ctx->ws_t, max_chunk + 64);
-    // upper bound of the dense strings: every column consumes a base of the read or the window
-    RESERVE(ctx->out_q, (size_t)pf[n] / 2 + ctx->read_bases + 64);
-    RESERVE(ctx->out_t, (size_t)pf[n] / 2 + ctx->read_bases + 64);
-
+    RESERVE(ctx->meta, (max_meta + 16) * 4);
+    // upper bound of the dense strings: every column consumes a base of the read or of its window
+    {
+        const Candidate *hc = nullptr;
+        (void)hc;
+        size_t bound = 0;
+        for (int64_t i = 0; i < n; ++i) bound += (size_t)(pf[i + 1] - pf[i]);
+        RESERVE(ctx->out_q, bound + 64);
+        RESERVE(ctx->out_t, bound + 64);
+    }
     while (ctx->chain_events.size() < chunks.size()) {
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
@@ -545,39 +597,45 @@ int ag2_extend_run(ag2_ctx *ctx)
         ctx->chain_events.push_back({a, b});
     }
 
-    // per chunk: chains -> (wide rerun) -> finalize -> scan of the ok lengths -> compaction into the
+    // per chunk: lane kernel -> (wide rerun) -> finalize -> scan of the ok lengths -> assemble into the
     // dense output at the running base
     int64_t dense_base = 0;
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const int64_t lo = chunks[ci].first, cn = chunks[ci].second - chunks[ci].first;
-        set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p, lo, cn);
+        set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p,
+                                                                           (const int64_t *)ctx->meta_prefix.p, lo, cn);
         CK(cudaMemsetAsync(&sc->next_fast, 0, 2 * sizeof(unsigned long long) + sizeof(unsigned int), st));
-        ChainArgs a = {};
+        LaneArgs a = {};
         a.seqs = sq;
         a.cand = (const Candidate *)ctx->cand.p + lo;
         a.geom = (const ExtGeom *)ctx->geom.p + lo;
         a.res = (ChainResult *)ctx->res.p + 2 * lo;
+        a.meta = (uint32_t *)ctx->meta.p;
         a.ws_q = (char *)ctx->ws_q.p;
         a.ws_t = (char *)ctx->ws_t.p;
-        a.tb = (uint8_t *)ctx->tb.p;
-        a.tb_stride = tb_stride;
+        a.scratch = (uint8_t *)ctx->tb.p;
         a.n_chains = 2 * cn;
-        a.queue = nullptr;
         a.next = &sc->next_fast;
         a.wide_queue = (int32_t *)ctx->wide_queue.p;
         a.wide_count = &sc->wide_count;
         a.counters = &sc->ctr;
         CK(cudaEventRecord(ctx->chain_events[ci].first, st));
-        xdrop_chains_fast_kernel<kChainWarps><<<fast_grid, kChainWarps * 32, fast_smem, st>>>(a);
+        xdrop_lane_kernel<<<lane_grid, kLaneThreads, lane_smem, st>>>(a);
         CK(cudaEventRecord(ctx->chain_events[ci].second, st));
         CK(cudaGetLastError());
-        // chains whose band outgrew the fast window: rerun on the wide kernel (usually none)
+        // directions that left the lane path (band > 120 columns, or reservation exceeded): wide kernel
         unsigned int n_wide = 0;
         CK(cudaMemcpyAsync(&n_wide, &sc->wide_count, sizeof n_wide, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         launches += 2;
         if (n_wide > 0) {
-            ChainArgs w = a;
+            ChainArgs w = {};
+            w.seqs = sq;
+            w.cand = a.cand;
+            w.geom = a.geom;
+            w.res = a.res;
+            w.ws_q = a.ws_q;
+            w.ws_t = a.ws_t;
             w.tb = (uint8_t *)ctx->tb_wide.p;
             w.tb_stride = tbw_stride;
             w.n_chains = n_wide;
@@ -585,6 +643,7 @@ int ag2_extend_run(ag2_ctx *ctx)
             w.next = &sc->next_wide;
             w.wide_queue = nullptr;
             w.wide_count = nullptr;
+            w.counters = &sc->ctr;
             xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
             CK(cudaGetLastError());
             ++launches;
@@ -593,16 +652,15 @@ int ag2_extend_run(ag2_ctx *ctx)
             (const Candidate *)ctx->cand.p, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p,
             (const int32_t *)ctx->read_len.p, lo, cn, (Record *)ctx->rec.p, (int64_t *)ctx->str_begin.p,
             (int64_t *)ctx->ok_len.p);
-        // per-chunk scan, shifted by the running base
         exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->ok_len.p + lo, cn, (int64_t *)ctx->dense_off.p + lo);
         launches += 2;
         int64_t chunk_total = 0;
         CK(cudaMemcpyAsync(&chunk_total, (int64_t *)ctx->dense_off.p + lo + cn, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        compact_kernel<<<grid_for(cn, 1, ctx->sm_count * 2), 128, 0, st>>>(
-            (Record *)ctx->rec.p, (const int64_t *)ctx->str_begin.p, (const int64_t *)ctx->dense_off.p, dense_base, lo, cn,
-            (const char *)ctx->ws_q.p, (const char *)ctx->ws_t.p, (char *)ctx->out_q.p, (char *)ctx->out_t.p,
-            &sc->aligned, &sc->columns);
+        assemble_kernel<<<grid_for(cn * 32, 256, ctx->sm_count), 256, 0, st>>>(
+            (Record *)ctx->rec.p, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p, (const uint32_t *)ctx->meta.p,
+            (const int64_t *)ctx->dense_off.p, dense_base, lo, cn, (const char *)ctx->ws_q.p, (const char *)ctx->ws_t.p,
+            (char *)ctx->out_q.p, (char *)ctx->out_t.p, &sc->aligned, &sc->columns);
         ++launches;
         CK(cudaGetLastError());
         dense_base += chunk_total;
@@ -610,7 +668,6 @@ int ag2_extend_run(ag2_ctx *ctx)
     CK(cudaStreamSynchronize(st));
     ctx->out_total = dense_base;
 
-    // stats
     Scalars hs;
     CK(cudaMemcpy(&hs, sc, sizeof hs, cudaMemcpyDeviceToHost));
     ag2_extend_stats &s = ctx->stats;

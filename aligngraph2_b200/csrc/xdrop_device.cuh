@@ -61,19 +61,33 @@ struct Candidate { // == ag2_candidate
     int32_t loc2, score;
 };
 
+// Workspace slot of one candidate: [left area: capL columns][right area: capR columns].
+//   lane path : every block of a direction appends its columns in WALK order (end -> origin) to the
+//               direction's area; per-block (n_ops, skip) words go to `meta`; assemble_record() puts
+//               them in final order
+//   wide path : columns are written at their final place, the left direction right-to-left ending
+//               at slot + capL, the right direction left-to-right from there
 struct ExtGeom {      // per candidate, written by extend_setup_kernel
     int64_t slot;     // first column of this candidate's slot in the workspace strings
+    int64_t meta;     // first block-metadata word of this candidate (left blocks, then right blocks)
     int32_t left;     // left_ref_size  (mecat2ref_aux.cpp:186)
     int32_t right;    // right_ref_size (:187)
     int32_t valid;
+    int32_t capL;     // columns reserved for the left direction
+    int32_t capR;
+    int32_t nmetaL;   // block-metadata words reserved for the left direction
+    int32_t nmetaR;
     int32_t pad;
 };
 
 struct ChainResult {
-    int32_t ncols;    // columns written by this direction
+    int32_t ncols;    // columns emitted by this direction
     int32_t qcons;    // query bases consumed by those columns
     int32_t tcons;    // target bases consumed
     int32_t last_op;  // op of the farthest column (for the left direction's dropped column)
+    int32_t nblocks;  // lane path: number of block-metadata words written
+    int32_t mode;     // 0 = lane path (segments + metadata), 1 = wide path (final positions)
+    int32_t pad0, pad1;
 };
 
 struct ChainCounters {
@@ -379,7 +393,7 @@ __device__ bool run_chain(const ChainArgs &g, int64_t chain, WarpSmem &sm, uint8
     const bool forward = (chain & 1) != 0; // 0 = left (backward), 1 = right
     const Candidate c = g.cand[ci];
     const ExtGeom ge = g.geom[ci];
-    ChainResult out = {0, 0, 0, -1};
+    ChainResult out = {0, 0, 0, -1, 0, 1, 0, 0};
     if (!ge.valid) {
         if (lane == 0) g.res[chain] = out;
         return true;
@@ -394,7 +408,7 @@ __device__ bool run_chain(const ChainArgs &g, int64_t chain, WarpSmem &sm, uint8
     const int q0 = forward ? read_start : read_start - 1;      // oriented read position of block-local 0
     const int64_t t0 = forward ? ref_start : ref_start - 1;    // reference position of block-local 0
     const int inc = forward ? 1 : -1;
-    const int64_t mid = ge.slot + read_start + ge.left;         // first column of the right direction
+    const int64_t mid = ge.slot + ge.capL;                      // first column of the right direction
     int qidx = 0, tidx = 0;
     int ncols = 0, qcons = 0, tcons = 0, last_op = -1;
     ChainCounters lc = {0, 0, 0, 0, 0};
@@ -504,13 +518,17 @@ struct Record { // == ag2_record
 };
 
 // extract_sequences (M2R/mecat2ref_aux.cpp:171-208): window sizes around the seed.
-// Returns the number of workspace columns this candidate needs (0 if the candidate is malformed).
-__device__ __forceinline__ int64_t setup_one(const Candidate &c, const PackedSeqs &sq, int64_t n_reads, ExtGeom &g)
+// Returns the number of workspace columns this candidate needs (0 if the candidate is malformed);
+// n_meta receives the number of block-metadata words.
+__device__ __forceinline__ int64_t setup_one(const Candidate &c, const PackedSeqs &sq, int64_t n_reads, ExtGeom &g,
+                                             int64_t &n_meta)
 {
     g.slot = 0;
+    g.meta = 0;
     g.left = g.right = 0;
     g.valid = 0;
-    g.pad = 0;
+    g.capL = g.capR = g.nmetaL = g.nmetaR = g.pad = 0;
+    n_meta = 0;
     if (c.read < 0 || c.read >= n_reads) return 0;
     const int64_t rlen = sq.read_len[c.read];
     const int64_t read_start = c.loc2, ref_start = c.loc1 - 1;
@@ -521,12 +539,19 @@ __device__ __forceinline__ int64_t setup_one(const Candidate &c, const PackedSeq
     g.left = (int32_t)min(L2, mul_1p2(L));
     g.right = (int32_t)min(R2, mul_1p2(R));
     g.valid = 1;
-    return rlen + g.left + g.right;
+    // a block that is not the last one advances by >= ~480 bases on one side; the slack covers the
+    // columns trim_mismatch_end hands back to the next block.  A direction that outgrows either
+    // reservation is rerun on the wide path, so these are performance, not correctness, bounds.
+    g.nmetaL = (int32_t)((L1 + g.left) / 400 + 4);
+    g.nmetaR = (int32_t)((R1 + g.right) / 400 + 4);
+    g.capL = (int32_t)(L1 + g.left + 64 * g.nmetaL);
+    g.capR = (int32_t)(R1 + g.right + 64 * g.nmetaR);
+    n_meta = g.nmetaL + g.nmetaR;
+    return (int64_t)g.capL + g.capR;
 }
 
 // XdropAligner::go's assembly (:398-438) + extend_candidate's record (mecat2ref_aux.cpp:240-251).
-// The farthest left column is dropped (:401-402).  Strings live at [str_begin, str_begin + aln_len)
-// of the workspace.
+// The farthest left column is dropped (:401-402).  assemble_record() copies the columns.
 __device__ __forceinline__ void finalize_one(const Candidate &c, const ExtGeom &g, const ChainResult &l,
                                              const ChainResult &r, int rlen, Record &o, int64_t &str_begin)
 {
@@ -556,7 +581,7 @@ __device__ __forceinline__ void finalize_one(const Candidate &c, const ExtGeom &
     o.se = ref_start - g.left + tend;
     o.aln_len = lcols + r.ncols;
     o.ok = (qend - qoff >= 1000) ? 1 : 0;
-    str_begin = g.slot + read_start + g.left - lcols;
+    str_begin = g.slot + g.capL - lcols; // only meaningful when both directions ran on the wide path
 }
 
 } // namespace ag2

@@ -303,7 +303,7 @@ __device__ bool run_chain_fast(const ChainArgs &g, int64_t chain, FastSmem &sm, 
     const bool forward = (chain & 1) != 0;
     const Candidate c = g.cand[ci];
     const ExtGeom ge = g.geom[ci];
-    ChainResult out = {0, 0, 0, -1};
+    ChainResult out = {0, 0, 0, -1, 0, 1, 0, 0};
     if (!ge.valid) {
         if (lane == 0) g.res[chain] = out;
         return true;
@@ -317,7 +317,7 @@ __device__ bool run_chain_fast(const ChainArgs &g, int64_t chain, FastSmem &sm, 
     const int q0 = forward ? read_start : read_start - 1;
     const int64_t t0 = forward ? ref_start : ref_start - 1;
     const int inc = forward ? 1 : -1;
-    const int64_t mid = ge.slot + read_start + ge.left;
+    const int64_t mid = ge.slot + ge.capL;
     int qidx = 0, tidx = 0;
     int ncols = 0, qcons = 0, tcons = 0, last_op = -1;
     ChainCounters lc = {0, 0, 0, 0, 0};

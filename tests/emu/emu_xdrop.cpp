@@ -4,6 +4,7 @@
 #define AG2_EMU 1
 #include "../../aligngraph2_b200/csrc/xdrop_device.cuh"
 #include "../../aligngraph2_b200/csrc/xdrop_fast.cuh"
+#include "../../aligngraph2_b200/csrc/xdrop_lane.cuh"
 
 #include <vector>
 
@@ -139,7 +140,8 @@ int emu_extend(int K, const char *ref, long ref_len, const char *read, int read_
     PackedSeqs sq = {ref2.data(), ref_len, rd2.data(), irr.data(), &roff, &rlen};
     Candidate c = {0, strand, loc1, loc2, 7};
     ExtGeom g;
-    const int64_t cap = setup_one(c, sq, 1, g);
+    int64_t nm_;
+    const int64_t cap = setup_one(c, sq, 1, g, nm_);
     if (!g.valid) return -1;
     std::vector<char> wq(cap + 1, '?'), wt(cap + 1, '?');
     ChainResult res[2];
@@ -187,6 +189,113 @@ int emu_extend(int K, const char *ref, long ref_len, const char *read, int read_
     memcpy(qaln, wq.data() + sb, o.aln_len);
     memcpy(taln, wt.data() + sb, o.aln_len);
     return o.ok;
+}
+
+
+// The whole lane path for a batch of candidates over one reference, as ONE emulated warp:
+// setup_one -> lane_kernel_body (+ wide rerun of handed-over directions) -> finalize_one -> assemble_record.
+// reads: concatenated ASCII with offs[n+1]; cand: n x (read, strand, loc1, loc2).  Outputs per candidate:
+// rec[8] = ok qb qe sb se aln_len mode_left mode_right; strings concatenated into qaln/taln at aoff[i].
+int emu_lane_batch(const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
+                   int n, long *rec, long *aoff, char *qaln, char *taln, long *stats /* cells wide */)
+{
+    std::vector<uint32_t> ref2((ref_len >> 4) + 8, 0), dummy((ref_len >> 5) + 8, 0);
+    pack2(ref, ref_len, ref2, dummy, 0);
+    std::vector<int64_t> roff(n_reads + 1);
+    std::vector<int32_t> rlen(n_reads);
+    int64_t p = 0;
+    for (int r = 0; r < n_reads; ++r) {
+        roff[r] = p;
+        rlen[r] = (int32_t)(offs[r + 1] - offs[r]);
+        p += (rlen[r] + 31) & ~31;
+    }
+    std::vector<uint32_t> rd2((p >> 4) + 8, 0), irr((p >> 5) + 8, 0);
+    for (int r = 0; r < n_reads; ++r) pack2(reads + offs[r], rlen[r], rd2, irr, roff[r]);
+    PackedSeqs sq = {ref2.data(), ref_len, rd2.data(), irr.data(), roff.data(), rlen.data()};
+    std::vector<Candidate> cs(n);
+    std::vector<ExtGeom> ge(n);
+    int64_t ws = 0, nm = 0;
+    for (int i = 0; i < n; ++i) {
+        cs[i] = Candidate{(int32_t)cand[4 * i], (int32_t)cand[4 * i + 1], cand[4 * i + 2], (int32_t)cand[4 * i + 3], 3};
+        int64_t m;
+        const int64_t cap = setup_one(cs[i], sq, n_reads, ge[i], m);
+        ge[i].slot = ws;
+        ge[i].meta = nm;
+        ws += cap;
+        nm += m;
+    }
+    std::vector<char> wq(ws + 64, '?'), wt(ws + 64, '?');
+    std::vector<uint32_t> meta(nm + 16, 0);
+    std::vector<ChainResult> res(2 * n);
+    std::vector<uint8_t> scratch((size_t)kLaneScratch * 32 + 64);
+    std::vector<int32_t> wide_queue(2 * n + 1);
+    unsigned long long next = 0;
+    unsigned int wide_count = 0;
+    ChainCounters ctr = {0, 0, 0, 0, 0};
+    static LaneSmem lsm;
+    LaneArgs a = {};
+    a.seqs = sq;
+    a.cand = cs.data();
+    a.geom = ge.data();
+    a.res = res.data();
+    a.meta = meta.data();
+    a.ws_q = wq.data();
+    a.ws_t = wt.data();
+    a.scratch = (uint8_t *)(((uintptr_t)scratch.data() + 15) & ~(uintptr_t)15);
+    a.n_chains = 2 * n;
+    a.next = &next;
+    a.wide_queue = wide_queue.data();
+    a.wide_count = &wide_count;
+    a.counters = &ctr;
+    warp_emu::run_warp([&]() {
+        const int lane = warp_emu::st().cur;
+        lane_kernel_body(a, lsm, lane, a.scratch + (size_t)lane * kLaneScratch);
+    });
+    // wide rerun
+    if (wide_count) {
+        static WarpSmem sm;
+        std::vector<uint8_t> tb((size_t)(kMaxBlk + 2) * TbLayout<23>::kRowBytes);
+        ChainArgs w = {};
+        w.seqs = sq;
+        w.cand = cs.data();
+        w.geom = ge.data();
+        w.res = res.data();
+        w.ws_q = wq.data();
+        w.ws_t = wt.data();
+        warp_emu::run_warp([&]() {
+            const int lane = warp_emu::st().cur;
+            ChainCounters lc = {0, 0, 0, 0, 0};
+            for (unsigned k = 0; k < wide_count; ++k) run_chain<23>(w, wide_queue[k], sm, tb.data(), lane, lc);
+            if (lane == 0) {
+                ctr.cells += lc.cells;
+            }
+        });
+    }
+    long o = 0;
+    for (int i = 0; i < n; ++i) {
+        Record r;
+        int64_t sb;
+        finalize_one(cs[i], ge[i], res[2 * i], res[2 * i + 1], ge[i].valid ? rlen[cs[i].read] : 0, r, sb);
+        rec[8 * i + 0] = r.ok;
+        rec[8 * i + 1] = r.qb;
+        rec[8 * i + 2] = r.qe;
+        rec[8 * i + 3] = r.sb;
+        rec[8 * i + 4] = r.se;
+        rec[8 * i + 5] = r.aln_len;
+        rec[8 * i + 6] = res[2 * i].mode;
+        rec[8 * i + 7] = res[2 * i + 1].mode;
+        aoff[i] = o;
+        if (r.ok) {
+            const ExtGeom g2 = ge[i];
+            const ChainResult l = res[2 * i], rr = res[2 * i + 1];
+            char *oq = qaln + o, *ot = taln + o;
+            warp_emu::run_warp([&]() { assemble_record(g2, l, rr, meta.data(), wq.data(), wt.data(), oq, ot, warp_emu::st().cur); });
+            o += r.aln_len;
+        }
+    }
+    stats[0] = (long)ctr.cells;
+    stats[1] = (long)wide_count;
+    return 0;
 }
 
 } // extern "C"

@@ -151,6 +151,8 @@ inline unsigned __ballot_sync(unsigned, bool p)
     for (int l = 0; l < 32; ++l) r |= (unsigned)(buf[l] & 1) << l;
     return r;
 }
+inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
+inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, p) == 0xffffffffu; }
 inline int __reduce_min_sync(unsigned, int v)
 {
     const uint64_t *buf = warp_emu::exchange((uint64_t)(int64_t)v);
