@@ -7,7 +7,7 @@
 //   * 32 chains advance in lock step per warp (SIMT): one DP row at a time, the inner column loop
 //     runs until the widest of the 32 bands is done; chains of different length are refilled from a
 //     global queue at block boundaries so lanes stay busy;
-//   * the band state (h, e as int16 pairs, 128-column circular window) and the block's target codes
+//   * the band state (16 bits per column, 128-column circular window) and the block's target codes
 //     (2 bit) live in shared memory laid out [slot][thread]: lane i always hits bank i -- conflict
 //     free whatever column each lane is at;
 //   * query codes of the block are normalised once per block into a per-thread scratch line and read
@@ -33,10 +33,23 @@ constexpr int kNeg16 = -16000;      // MIN_SCORE on the lane path: same arithmet
 constexpr int kLaneTbBytes = (kMaxBlk + 2) * 64;
 constexpr int kLaneScratch = kLaneTbBytes + 256; // + normalised query codes of the block
 
+// Band state of one column in 16 bits: (x << 1) | dead with x = e + 1.  A live column always has
+// e = h - 1 (every statement that writes both sets them so: :58-59, :122/:135, :148-149), so x = h;
+// a pruned column that stays in the band has h = MIN_SCORE and keeps its e (:111); the sentinel is
+// (MIN_SCORE, MIN_SCORE) (:161-162).  Two consecutive columns of a thread share one 32-bit word
+// so that lane i only ever touches bank i.
 struct LaneSmem {
-    uint32_t band[kBandSlots][kLaneThreads]; // (h & 0xffff) | (e << 16)
+    uint16_t band[kBandSlots / 2][kLaneThreads][2];
     uint32_t tseq[kSeqWords][kLaneThreads];  // target block, 16 codes per word, extension order
 };
+
+__device__ __forceinline__ uint16_t *band_slot(LaneSmem &sm, int tid, int b)
+{
+    const int slot = b & (kBandSlots - 1);
+    return &sm.band[slot >> 1][tid][slot & 1];
+}
+__device__ __forceinline__ uint16_t band_live(int h) { return (uint16_t)(h * 2); }
+constexpr uint16_t kBandSentinel = (uint16_t)(((kNeg16 + 1) * 2) | 1);
 
 struct LaneArgs {
     PackedSeqs seqs;
@@ -129,7 +142,7 @@ __device__ int lane_dp(LaneSmem &sm, int tid, const uint32_t *__restrict__ qcode
     int bsize = min(N, xd) + 1, first = 0, best = 0, ae = 0, be = 0;
     unsigned cells = 0, rows = 0;
     // row 0 (:53-67)
-    for (int i = 0; i < bsize; ++i) sm.band[i][tid] = (uint32_t)((-i) & 0xffff) | ((uint32_t)(-i - 1) << 16);
+    for (int i = 0; i < bsize; ++i) *band_slot(sm, tid, i) = band_live(-i);
 
     uint32_t aw = 0;
     for (int a = 1; a <= M; ++a) {
@@ -142,59 +155,63 @@ __device__ int lane_dp(LaneSmem &sm, int tid, const uint32_t *__restrict__ qcode
         cells += (unsigned)(bsize - first);
         ++rows;
         uint32_t tbw = 0;
+        int sh = 4 * (first & 7);
+        uint32_t bw = sm.tseq[first >> 4][tid] >> (2 * (first & 15));
         int b;
         for (b = first; b < bsize; ++b) { // (:84-140)
-            const uint32_t he = sm.band[b & (kBandSlots - 1)][tid];
-            const uint32_t bwd = sm.tseq[b >> 4][tid];
-            const int bc = (int)((bwd >> (2 * (b & 15))) & 3u);
-            const int h = (int)(short)(he & 0xffffu);
-            const int e = (int)he >> 16;
-            const int next_diag = h + (ac == bc ? 1 : -1);
+            uint16_t *cell = band_slot(sm, tid, b);
+            const int st = (int)(short)*cell;
+            const int x = st >> 1;
+            const int e = x - 1;
+            const int h = (st & 1) ? kNeg16 : x;
+            const int next_diag = h + ((int)(bw & 3u) == ac ? 1 : -1);
+            bw >>= 2;
+            if (((b + 1) & 15) == 0) bw = sm.tseq[(b + 1) >> 4][tid];
             int sc = diag;
             int nib = kOpSub;
             if (sc < e) { sc = e; nib = kOpGapB; }
             if (sc < hgap) { sc = hgap; nib = kOpGapA; }
-            int nh, ne = e;
             if (sc < thr) { // best - sc > x_dropoff (:109)
-                nh = kNeg16;
-                if (first == b) { ++first; nh = h; } // dropped from the band: column state is dead
+                if (first == b) ++first;         // dropped from the band: the column is dead
+                else *cell = (uint16_t)(st | 1); // h = MIN_SCORE, e unchanged (:111)
             } else {
                 last = b;
                 if (sc > best) { best = sc; thr = sc - xd; ae = a; be = b; }
                 if (e >= sc) nib |= kExtA;     // e - ge >= sc - goe (:121-126)
                 if (hgap >= sc) nib |= kExtB;  // (:129-133)
-                ne = sc - 1;
                 hgap = sc - 1;
-                nh = sc;
+                *cell = band_live(sc);         // h = sc, e = sc - 1
             }
-            sm.band[b & (kBandSlots - 1)][tid] = (uint32_t)(nh & 0xffff) | ((uint32_t)ne << 16);
             diag = next_diag;
-            tbw |= (uint32_t)nib << (4 * (b & 7));
-            if ((b & 7) == 7) {
+            tbw |= (uint32_t)nib << sh;
+            sh += 4;
+            if (sh == 32) {
                 trow[(b & (kBandSlots - 1)) >> 3] = tbw;
                 tbw = 0;
+                sh = 0;
             }
         }
         if (first == bsize) break; // (:142)
         if (last < bsize - 1) {
-            // the band shrinks: cells beyond `last` of this row were already stored or are pending in tbw
-            if ((b & 7) != 0) trow[((b - 1) & (kBandSlots - 1)) >> 3] = tbw;
-            bsize = last + 1;
+            if (sh != 0) trow[((b - 1) & (kBandSlots - 1)) >> 3] = tbw;
+            bsize = last + 1; // (:144-145)
         } else {
             while (hgap >= best - xd && bsize < N) { // (:147-153)
-                sm.band[bsize & (kBandSlots - 1)][tid] = (uint32_t)(hgap & 0xffff) | ((uint32_t)(hgap - 1) << 16);
+                *band_slot(sm, tid, bsize) = band_live(hgap);
                 hgap -= 1;
-                tbw |= (uint32_t)kOpGapA << (4 * (bsize & 7));
-                if ((bsize & 7) == 7) {
+                tbw |= (uint32_t)kOpGapA << sh;
+                sh += 4;
+                if (sh == 32) {
                     trow[(bsize & (kBandSlots - 1)) >> 3] = tbw;
                     tbw = 0;
+                    sh = 0;
                 }
                 ++bsize;
             }
-            if ((bsize & 7) != 0) trow[((bsize - 1) & (kBandSlots - 1)) >> 3] = tbw;
+            if (sh != 0) trow[((bsize - 1) & (kBandSlots - 1)) >> 3] = tbw;
         }
         if (bsize < N) { // (:160-164)
-            sm.band[bsize & (kBandSlots - 1)][tid] = (uint32_t)(kNeg16 & 0xffff) | ((uint32_t)kNeg16 << 16);
+            *band_slot(sm, tid, bsize) = kBandSentinel;
             ++bsize;
         }
         if (bsize - first > kBandMax) return 1;
