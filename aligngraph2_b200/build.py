@@ -8,8 +8,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "libag2_b200.so")
 SOURCES = [os.path.join(PKG, "csrc", "ag2_b200.cu")]
-HEADERS = [os.path.join(PKG, "csrc", "xdrop_device.cuh"), os.path.join(PKG, "csrc", "xdrop_fast.cuh"),
-           os.path.join(PKG, "csrc", "h2ops.cuh"), os.path.join(ROOT, "include", "ag2_b200.h")]
+HEADERS = [os.path.join(PKG, "csrc", "xdrop_device.cuh"), os.path.join(PKG, "csrc", "xdrop_lane.cuh"), os.path.join(ROOT, "include", "ag2_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -4,7 +4,6 @@
 // live CUDA context and returns AG2_ENODEV / AG2_ECUDA otherwise.
 #include "../../include/ag2_b200.h"
 #include "xdrop_device.cuh"
-#include "xdrop_fast.cuh"
 #include "xdrop_lane.cuh"
 
 #include <algorithm>
@@ -21,8 +20,6 @@ static_assert(sizeof(ag2_record) == sizeof(Record), "ag2_record layout");
 
 namespace {
 
-constexpr int kChainWarps = 8;    // warps per CTA of the chain kernel
-constexpr int kFastMinCtas = 3;   // resident CTAs per SM the fast kernel is compiled for (24 warps)
 constexpr int kWideK = 23;        // 736 columns: covers every possible block (N <= 718)
 constexpr int kWideWarps = 2;
 
@@ -185,37 +182,6 @@ __global__ void assemble_kernel(Record *rec, const ExtGeom *geom, const ChainRes
     }
 }
 
-// Fast path: persistent warps pull chains (extension directions) from a global counter; chains whose
-// band outgrows the 128-column window are queued for the wide kernel below.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, kFastMinCtas) xdrop_chains_fast_kernel(ChainArgs g)
-{
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    FastSmem *smem = reinterpret_cast<FastSmem *>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    FastSmem &sm = smem[warp];
-    uint8_t *tb = g.tb + ((size_t)blockIdx.x * WARPS + warp) * g.tb_stride;
-    ChainCounters ctr = {0, 0, 0, 0, 0};
-    for (;;) {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(g.next, 1ull);
-        t = __shfl_sync(kFull, t, 0);
-        if ((int64_t)t >= g.n_chains) break;
-        const bool done = run_chain_fast(g, (int64_t)t, sm, tb, lane, ctr);
-        if (!done) {
-            ctr.wide += 1;
-            if (lane == 0) g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)t;
-        }
-    }
-    if (lane == 0) {
-        atomicAdd(&g.counters->cells, ctr.cells);
-        atomicAdd(&g.counters->rows, ctr.rows);
-        atomicAdd(&g.counters->blocks, ctr.blocks);
-        atomicAdd(&g.counters->interior, ctr.interior);
-        atomicAdd(&g.counters->wide, ctr.wide);
-    }
-}
-
 // Wide path (any band a block can have): the int32 row kernel with K columns per lane.
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
@@ -261,29 +227,6 @@ __global__ void extend_finalize_kernel(const Candidate *cand, const ExtGeom *geo
         rec[i] = o;
         str_begin[i] = sb;
         ok_len[i] = o.ok ? o.aln_len : 0;
-    }
-}
-
-// One CTA per record: workspace columns -> dense output, and fills aln_off.
-__global__ void compact_kernel(Record *rec, const int64_t *str_begin, const int64_t *dense_off, int64_t dense_base,
-                               int64_t first, int64_t n, const char *ws_q, const char *ws_t, char *out_q, char *out_t,
-                               unsigned long long *aligned, unsigned long long *columns)
-{
-    for (int64_t k = blockIdx.x; k < n; k += gridDim.x) {
-        const int64_t i = first + k;
-        const int64_t dst = dense_base + dense_off[i];
-        if (threadIdx.x == 0) rec[i].aln_off = dst;
-        if (!rec[i].ok) continue;
-        const int len = rec[i].aln_len;
-        const char *sq = ws_q + str_begin[i], *st = ws_t + str_begin[i];
-        for (int c = threadIdx.x; c < len; c += blockDim.x) {
-            out_q[dst + c] = sq[c];
-            out_t[dst + c] = st[c];
-        }
-        if (threadIdx.x == 0) {
-            atomicAdd(aligned, (unsigned long long)(rec[i].qe - rec[i].qb));
-            atomicAdd(columns, (unsigned long long)len);
-        }
     }
 }
 
@@ -582,14 +525,8 @@ int ag2_extend_run(ag2_ctx *ctx)
     RESERVE(ctx->ws_t, max_chunk + 64);
     RESERVE(ctx->meta, (max_meta + 16) * 4);
     // upper bound of the dense strings: every column consumes a base of the read or of its window
-    {
-        const Candidate *hc = nullptr;
-        (void)hc;
-        size_t bound = 0;
-        for (int64_t i = 0; i < n; ++i) bound += (size_t)(pf[i + 1] - pf[i]);
-        RESERVE(ctx->out_q, bound + 64);
-        RESERVE(ctx->out_t, bound + 64);
-    }
+    RESERVE(ctx->out_q, (size_t)pf[n] + 64);
+    RESERVE(ctx->out_t, (size_t)pf[n] + 64);
     while (ctx->chain_events.size() < chunks.size()) {
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));

@@ -30,6 +30,11 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of xdrop_lane_kernel from the ncu --set full capture
+# profiles/kernel_r01d_lane.md (100k reads: 206.75 GB for 1 052 318 181 aligned bases); DRAM bytes per
+# aligned base do not depend on the batch size, so the per-launch figure is that ratio x this launch's bases
+TRAFFIC_BYTES_PER_ALIGNED_BASE = 206.750790e9 / 1052318181
+TRAFFIC_NOTE = "ncu dram bytes per aligned base (profiles/kernel_r01d_lane.md, 100k-read launch) x aligned bases of this launch"
 METRIC = "aligned_gbp_per_s"
 UNIT = "Gbp/s"
 
@@ -320,7 +325,8 @@ def main():
     kern_s = kernel_ms / args.steps * 1e-3
     achieved = b_alg * st["aligned"] / kern_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "xdrop_chains_kernel<4,8>", "kernel_ms_per_launch": kernel_ms / args.steps,
+                "traffic": TRAFFIC_BYTES_PER_ALIGNED_BASE * st["aligned"], "traffic_note": TRAFFIC_NOTE,
+                "kernel": "xdrop_lane_kernel", "kernel_ms_per_launch": kernel_ms / args.steps,
                 "algorithmic_bytes_per_aligned_base": b_alg, "cells_per_aligned_base": cbar,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0}
 

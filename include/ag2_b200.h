@@ -65,10 +65,10 @@ typedef struct ag2_extend_stats {
     int64_t blocks;       /* xdrop_align calls */
     int64_t aligned;      /* sum of (qe - qb) over ok records */
     int64_t columns;      /* alignment columns emitted over ok records */
-    int64_t wide_chains;  /* extension directions that left the 128-column fast path */
-    int64_t interior;     /* rows that needed the exact interior-pruned-cell fix-up */
+    int64_t wide_chains;  /* extension directions rerun on the wide (row-parallel) kernel */
+    int64_t interior;     /* wide kernel: rows that needed the interior-pruned-cell fix-up */
     int64_t launches;     /* kernel launches made by the call */
-    double kernel_ms;     /* CUDA-event time of the dominant kernel (xdrop_chains_kernel) */
+    double kernel_ms;     /* CUDA-event time of the dominant kernel (xdrop_lane_kernel) */
 } ag2_extend_stats;
 
 int ag2_ctx_create(int device, ag2_ctx **ctx);

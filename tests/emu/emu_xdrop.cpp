@@ -3,7 +3,6 @@
 // tests/emu/libemu_xdrop.so and loaded by tests/test_emu_xdrop.py.
 #define AG2_EMU 1
 #include "../../aligngraph2_b200/csrc/xdrop_device.cuh"
-#include "../../aligngraph2_b200/csrc/xdrop_fast.cuh"
 #include "../../aligngraph2_b200/csrc/xdrop_lane.cuh"
 
 #include <vector>
@@ -49,47 +48,6 @@ void block_impl(const uint8_t *A, int M, const uint8_t *B, int N, int *ae, int *
     for (int i = 0; i < r_n; ++i) ops[i] = map[sm.ops[i]];
 }
 
-void fast_block_impl(const uint8_t *A, int M, const uint8_t *B, int N, int *ae, int *be, uint8_t *ops, int *nops,
-                     long *cells, int *overflow, long *interior)
-{
-    static FastSmem sm;
-    std::vector<uint8_t> tb((size_t)(kMaxBlk + 2) * 64 + 64);
-    uint8_t *tbp = tb.data() + (16 - ((uintptr_t)tb.data() & 15)) % 16;
-    memcpy(sm.A, A, M);
-    memcpy(sm.B, B, N);
-    for (int i = 0; i < kLutCols; ++i)
-        for (int k = 0; k < 4; ++k) sm.lut[k][i] = i >= (N <= kXdrop ? N + 1 : N) ? 0xFC : ((i >= 1 && B[i - 1] == k) ? 0x3C : 0xBC);
-    int r_ae = 0, r_be = 0, r_n = 0, r_over = 0;
-    ChainCounters ctr = {0, 0, 0, 0, 0};
-    warp_emu::run_warp([&]() {
-        const int lane = warp_emu::st().cur;
-        ChainCounters lc = {0, 0, 0, 0, 0};
-        int a = 0, b = 0;
-        const int over = dp_block_h2(sm, M, N, tbp, lane, a, b, lc);
-        __syncwarp();
-        int n = 0;
-        if (!over) {
-            int q, t, ac, m, w;
-            n = walk_block_fast(tbp, a, b, sm, lane, q, t, ac, m, w);
-        }
-        if (lane == 0) {
-            r_over = over;
-            ctr = lc;
-            r_n = n;
-            r_ae = a;
-            r_be = b;
-        }
-    });
-    *ae = r_ae;
-    *be = r_be;
-    *nops = r_n;
-    *overflow = r_over;
-    *cells = (long)ctr.cells;
-    *interior = (long)ctr.interior;
-    static const uint8_t map[3] = {3, 0, 6};
-    for (int i = 0; i < r_n; ++i) ops[i] = map[sm.ops[i]];
-}
-
 void pack2(const char *s, int64_t n, std::vector<uint32_t> &w2, std::vector<uint32_t> &irr, int64_t base)
 {
     for (int64_t i = 0; i < n; ++i) {
@@ -118,8 +76,7 @@ extern "C" {
 void emu_dp_block(int K, const uint8_t *A, int M, const uint8_t *B, int N, int *ae, int *be, uint8_t *ops,
                   int *nops, long *cells, int *overflow, long *interior)
 {
-    if (K == 0) fast_block_impl(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
-    else if (K == 2) block_impl<2>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
+    if (K == 2) block_impl<2>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
     else if (K == 3) block_impl<3>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
     else if (K == 4) block_impl<4>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
     else if (K == 8) block_impl<8>(A, M, B, N, ae, be, ops, nops, cells, overflow, interior);
@@ -148,7 +105,6 @@ int emu_extend(int K, const char *ref, long ref_len, const char *read, int read_
     ChainCounters ctr = {0, 0, 0, 0, 0};
     std::vector<uint8_t> tb((size_t)(kMaxBlk + 2) * TbLayout<23>::kRowBytes);
     static WarpSmem sm;
-    static FastSmem fsm;
     ChainArgs a = {};
     a.seqs = sq;
     a.cand = &c;
@@ -163,8 +119,7 @@ int emu_extend(int K, const char *ref, long ref_len, const char *read, int read_
         ChainCounters lc = {0, 0, 0, 0, 0};
         for (int chain = 0; chain < 2; ++chain) {
             bool ok;
-            if (K == 0) ok = run_chain_fast(a, chain, fsm, (uint8_t *)(((uintptr_t)tb.data() + 15) & ~(uintptr_t)15), lane, lc);
-            else if (K == 2) ok = run_chain<2>(a, chain, sm, tb.data(), lane, lc);
+            if (K == 2) ok = run_chain<2>(a, chain, sm, tb.data(), lane, lc);
             else if (K == 3) ok = run_chain<3>(a, chain, sm, tb.data(), lane, lc);
             else if (K == 4) ok = run_chain<4>(a, chain, sm, tb.data(), lane, lc);
             else ok = run_chain<23>(a, chain, sm, tb.data(), lane, lc);

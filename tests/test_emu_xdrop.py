@@ -22,7 +22,33 @@ def emu():
     L.emu_dp_block.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 7
     L.emu_extend.argtypes = [C.c_int, C.c_char_p, C.c_long, C.c_char_p, C.c_int, C.c_int, C.c_long, C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p]
+    L.emu_lane_batch.argtypes = [C.c_char_p, C.c_long, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
     return L
+
+
+def emu_lane_batch(L, ref, reads, cands):
+    """The lane path (xdrop_lane.cuh) for a batch: setup -> lane kernel body (one emulated warp, queue
+    refill) -> wide rerun -> finalize -> assemble."""
+    offs = np.zeros(len(reads) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in reads], out=offs[1:])
+    cat = b"".join(reads)
+    n = len(cands)
+    c = np.ascontiguousarray(np.array(cands, dtype=np.int64))
+    rec = np.zeros(8 * n, dtype=np.int64)
+    aoff = np.zeros(n, dtype=np.int64)
+    cap = int(offs[-1]) * 3 + 100000
+    qa, ta = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    st = np.zeros(2, dtype=np.int64)
+    L.emu_lane_batch(ref, len(ref), cat, offs.ctypes.data, len(reads), c.ctypes.data, n, rec.ctypes.data,
+                     aoff.ctypes.data, qa, ta, st.ctypes.data)
+    out = []
+    for i in range(n):
+        r = rec[8 * i:8 * i + 8]
+        ln, a = int(r[5]), int(aoff[i])
+        out.append(dict(ok=int(r[0]), qb=int(r[1]), qe=int(r[2]), sb=int(r[3]), se=int(r[4]), aln_size=ln,
+                        qaln=qa.raw[a:a + ln] if r[0] else b"", taln=ta.raw[a:a + ln] if r[0] else b"",
+                        modes=(int(r[6]), int(r[7]))))
+    return out, int(st[0]), int(st[1])
 
 
 def emu_block(L, K, A, B):
@@ -87,3 +113,49 @@ def test_emulated_extend_matches_golden(emu):
         if e["ok"]:
             assert (e["qb"], e["qe"], e["sb"], e["se"]) == (int(r["qb"]), int(r["qe"]), int(r["sb"]), int(r["se"]))
             assert e["qaln"] == r["qaln"].tobytes() and e["taln"] == r["taln"].tobytes()
+
+
+def test_emulated_lane_path_matches_oracle(emu, oracle):
+    # more directions than lanes (queue refill), ragged reads, both strands, soft-masked / N bases,
+    # seeds at the read ends, and unrelated extensions whose band leaves the lane window (wide rerun)
+    rng = np.random.default_rng(21)
+    ref = synth.make_reference(rng, 40_000)
+    reads, cands, exp, cells = [], [], [], 0
+    for i in range(40):
+        tl = int(rng.integers(60, 2600))
+        rd, start, ops = synth.make_read(rng, ref, tl, False)
+        cnt = np.ones(tl, dtype=np.int64)
+        cnt[ops == 1] = 2
+        cnt[ops == 2] = 0
+        off = np.concatenate(([0], np.cumsum(cnt)))
+        good = [p for p in range(0, max(1, tl - 13)) if (ops[p:p + 13] == 0).all()]
+        p = good[int(rng.integers(0, len(good)))] if good else 0
+        loc2 = int(off[p + 1] - 1) if good else 0
+        loc1 = start + p + 1
+        fwd = rd.tobytes()
+        if i % 5 == 0:
+            b = bytearray(fwd)
+            for k in rng.integers(0, len(b), size=5):
+                b[k] = ord("N")
+            for k in rng.integers(0, len(b), size=20):
+                b[k] |= 0x20
+            fwd = bytes(b)
+        strand = i & 1
+        given = fwd if not strand else synth.orient(fwd, 1)
+        if i % 11 == 3:
+            loc2 = 0
+        if i % 11 == 7:
+            loc2 = len(fwd)
+        reads.append(given)
+        cands.append((i, strand, loc1, loc2))
+        a = oracle.extend(ref.tobytes(), synth.orient(given, strand), loc1, loc2)
+        exp.append(a)
+        cells += a["cells"]
+    got, got_cells, wide = emu_lane_batch(emu, ref.tobytes(), reads, cands)
+    for a, b in zip(exp, got):
+        assert a["ok"] == b["ok"]
+        if a["ok"]:
+            for k in ("qb", "qe", "sb", "se", "aln_size", "qaln", "taln"):
+                assert a[k] == b[k], k
+    assert got_cells == cells
+    assert wide > 0, "no direction was handed to the wide path: that hand-over is part of this test"
