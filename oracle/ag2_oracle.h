@@ -53,6 +53,50 @@ int orc_extend_candidate(orc_xdrop *x, const char *ref, long ref_size, const cha
 /* cumulative counters over the lifetime of the orc_xdrop */
 void orc_xdrop_counters(const orc_xdrop *x, long *cells, long *rows, long *calls);
 
+/* ---- index (rows A2-A4), seeding + candidates (A5-A7), rescue + output (A11, A12): ag2_mapper.c ---- */
+typedef struct orc_index {
+    long R;              /* concatenated reference length */
+    char *ref;           /* reference characters as creat_ref_index keeps them */
+    int cbl;             /* similarity block size (-z) */
+    long nblk;           /* R / cbl + 1 */
+    int *rcnt;           /* masked read 13-mer counts [4^13]      (countin1) */
+    int *cnt;            /* masked reference 13-mer counts [4^13] (countin) */
+    uint32_t *off;       /* CSR bucket offsets [4^13 + 1] */
+    uint32_t *pos;       /* 1-based k-mer start positions, ascending inside a bucket (allloc) */
+    int *kcount;         /* per similarity block (sim::k_count), 10 zero entries of slack */
+    float *vote;         /* per similarity block (sim::vote), 10 zero entries of slack */
+    float ave;
+} orc_index;
+
+typedef struct orc_cand { /* candidate_save, mecat2ref_defs.h:90-95 */
+    long loc1, loc2, left1, left2, right1, right2;
+    int score, num1, num2;
+    char chain;
+} orc_cand;
+
+typedef struct orc_block { /* Back_List, mecat2ref_defs.h:84-88 */
+    short score, score2, loczhi[20], seedno[20], seednum;
+    int index;
+} orc_block;
+
+typedef struct orc_mapper orc_mapper;
+
+void orc_read_hist13(const char *seq, long n, int *counts);
+long orc_read_index_prefix(const long *offs, long nreads);
+orc_index *orc_index_build(const char *ref, long R, const int *rcnt, int cbl, double alpha, double beta);
+void orc_index_free(orc_index *ix);
+orc_mapper *orc_mapper_new(const orc_index *ix, int maxc, int num_output);
+void orc_mapper_free(orc_mapper *m);
+/* reference_mapping's loop body for one read; appends `.r` records to out (may be NULL) */
+int orc_map_read(orc_mapper *m, int read_id, const char *read, int len, FILE *out);
+/* pass-1 candidates of the read orc_map_read saw last, in canidate_loc[] order */
+int orc_mapper_last_candidates(const orc_mapper *m, orc_cand *out, int *pass2);
+long orc_mapper_cells(const orc_mapper *m);
+long orc_mapper_calls(const orc_mapper *m);
+long orc_mapper_aligned(const orc_mapper *m);
+long orc_map_batch(const char *ref, long R, const char *reads, const long *offs, const int *ids, long n, int cbl, double alpha,
+                   double beta, int maxc, int num_output, const char *r_path, long *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -172,3 +172,34 @@ class RefLib:
             return dict(ok=0)
         qa = self._qa.value
         return dict(ok=1, qb=oi[0], qe=oi[1], sb=ol[0], se=ol[1], qaln=qa, taln=self._ta.value, aln_size=len(qa))
+
+
+class MapperOracle:
+    """oracle/ag2_mapper.c: index, votes, seeding, candidates, extension, rescue, second pass -> `.r` records."""
+
+    def __init__(self) -> None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        self.lib = C.CDLL(ORACLE_SO)
+        self.lib.orc_map_batch.restype = C.c_long
+        self.lib.orc_map_batch.argtypes = [C.c_char_p, C.c_long, C.c_char_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int,
+                                           C.c_double, C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_void_p]
+
+    @staticmethod
+    def upper_ref(genome: bytes) -> bytes:
+        """creat_ref_index keeps the FASTA characters and upper-cases those above 'Z' (impl_large.cpp:432-437)."""
+        a = np.frombuffer(genome, dtype=np.uint8).copy()
+        a[a > 90] -= 32
+        return a.tobytes()
+
+    def map_batch(self, genome: bytes, bases: bytes, offsets, ids, r_path: str, cbl=200, alpha=0.5, beta=2.0,
+                  maxc=10, num_output=1):
+        ref = self.upper_ref(genome)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        st = np.zeros(8, dtype=np.int64)
+        n = self.lib.orc_map_batch(ref, len(ref), bases, offsets.ctypes.data, ids.ctypes.data, len(ids), cbl, alpha, beta,
+                                   maxc, num_output, r_path.encode(), st.ctypes.data)
+        keys = ("cells", "calls", "aligned", "pass2_reads", "insert_loc", "rescue_extensions", "multi_candidate_reads",
+                "votes_ne_1")
+        return n, dict(zip(keys, (int(v) for v in st)))
