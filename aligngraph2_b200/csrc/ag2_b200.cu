@@ -5,6 +5,7 @@
 #include "../../include/ag2_b200.h"
 #include "xdrop_device.cuh"
 #include "xdrop_lane.cuh"
+#include "index_kernels.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -42,24 +43,6 @@ __device__ __forceinline__ unsigned encode_ascii(unsigned c, unsigned &irregular
     default: break;
     }
     return code;
-}
-
-// one thread = 16 bases = one output word
-__global__ void pack_ref_kernel(const char *__restrict__ ascii, int64_t n, uint32_t *__restrict__ out)
-{
-    const int64_t nw = (n + 15) >> 4;
-    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t v = 0;
-        const int64_t base = w << 4;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (base + i < n) {
-                unsigned irr;
-                v |= encode_ascii((unsigned char)ascii[base + i], irr) << (2 * i);
-            }
-        }
-        out[w] = v;
-    }
 }
 
 // one thread = 32 bases of one read = two 2-bit words + one "irregular" word.
@@ -247,8 +230,16 @@ struct ag2_ctx {
     std::string err;
 
     DevBuf ascii;                       // staging for ASCII uploads
-    DevBuf ref2;
+    DevBuf ref2, ref_irr, ref_ascii, ref_offs;
     int64_t ref_len = 0;
+    // index (A2-A4) and seeding (A5-A7)
+    DevBuf ix_rcnt, ix_cnt, ix_off, ix_pos, ix_fill, ix_tiles, ix_kcount, ix_vote;
+    int64_t ix_npos = 0, ix_nblk = 0;
+    int ix_cbl = 0;
+    bool ref_indexed = false, votes_ready = false;
+    int64_t read_prefix_len = 0;       // bytes of the concatenated reads that enter the read index (A2)
+    DevBuf seed_need, seed_prefix, seed_scratch, seed_cands, seed_ncand;
+    size_t seed_scratch_limit = (size_t)4 << 30;
     DevBuf reads2, reads_irr, read_off, read_len, ascii_offs;
     int64_t n_reads = 0, read_bases = 0;
 
@@ -378,7 +369,9 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *all[] = {&ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
+    DevBuf *all[] = {&ctx->ref_irr, &ctx->ref_ascii, &ctx->ref_offs, &ctx->ix_rcnt, &ctx->ix_cnt, &ctx->ix_off, &ctx->ix_pos,
+                     &ctx->ix_fill, &ctx->ix_tiles, &ctx->ix_kcount, &ctx->ix_vote, &ctx->seed_need, &ctx->seed_prefix,
+                     &ctx->seed_scratch, &ctx->seed_cands, &ctx->seed_ncand, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
                      &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->wide_queue, &ctx->scalars};
@@ -398,17 +391,27 @@ void *ag2_ctx_stream(ag2_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr;
 
 int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len)
 {
-    if (!ctx || !ref || ref_len <= 0) return fail(ctx, AG2_EINVAL, "ag2_ref_load: bad argument");
+    if (!ctx || !ref || ref_len <= 0 || ref_len > 0xfffffff0ll) return fail(ctx, AG2_EINVAL, "ag2_ref_load: bad argument");
     CK(cudaSetDevice(ctx->device));
-    RESERVE(ctx->ascii, (size_t)ref_len);
-    const int64_t nw = (ref_len + 15) >> 4;
-    RESERVE(ctx->ref2, (size_t)(nw + 4) * 4);
-    CK(cudaMemcpyAsync(ctx->ascii.p, ref, (size_t)ref_len, cudaMemcpyHostToDevice, ctx->stream));
-    pack_ref_kernel<<<grid_for(nw, 256, ctx->sm_count), 256, 0, ctx->stream>>>((const char *)ctx->ascii.p, ref_len,
-                                                                              (uint32_t *)ctx->ref2.p);
+    cudaStream_t st = ctx->stream;
+    const int64_t groups = (ref_len + 31) >> 5;
+    RESERVE(ctx->ref_ascii, (size_t)ref_len + 64);
+    RESERVE(ctx->ref2, (size_t)(groups * 2 + 8) * 4);
+    RESERVE(ctx->ref_irr, (size_t)(groups + 8) * 4);
+    RESERVE(ctx->ref_offs, 4 * 8);
+    const int64_t h_offs[4] = {0, ref_len, 0, groups << 5}; // ASCII offsets {0, R}, packed offsets {0, end}
+    CK(cudaMemcpyAsync(ctx->ref_ascii.p, ref, (size_t)ref_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->ref_offs.p, h_offs, sizeof h_offs, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->ref2.p, 0, (size_t)(groups * 2 + 8) * 4, st));
+    CK(cudaMemsetAsync(ctx->ref_irr.p, 0, (size_t)(groups + 8) * 4, st));
+    pack_reads_kernel<<<grid_for(groups, 256, ctx->sm_count), 256, 0, st>>>(
+        (const char *)ctx->ref_ascii.p, (const int64_t *)ctx->ref_offs.p, (const int64_t *)ctx->ref_offs.p + 2, 1, groups,
+        (uint32_t *)ctx->ref2.p, (uint32_t *)ctx->ref_irr.p);
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(st)); // h_offs is on the stack
     ctx->ref_len = ref_len;
+    ctx->ref_indexed = false;
+    ctx->votes_ready = false;
     return AG2_OK;
 }
 
@@ -447,6 +450,15 @@ int ag2_reads_load(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t
     CK(cudaStreamSynchronize(ctx->stream)); // poff/lens are stack-owned
     ctx->n_reads = n;
     ctx->read_bases = total;
+    {   // which reads enter the read index: the first <= 100 000 while the running length (+1 each) < 1e9 (:277)
+        int64_t lenl = 0, k = 0;
+        while (k < n && k < 100000 && lenl < 1000000000ll) {
+            lenl += (offs[k + 1] - offs[k]) + 1;
+            ++k;
+        }
+        ctx->read_prefix_len = offs[k];
+    }
+    ctx->votes_ready = false;
     return AG2_OK;
 }
 
@@ -661,6 +673,162 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
     r = ag2_extend_run(ctx);
     if (r != AG2_OK) return r;
     return ag2_extend_fetch(ctx, rec_out, qaln_out, saln_out, aln_cap, aln_used);
+}
+
+
+// ---- index (A2-A4) ------------------------------------------------------------------------------
+static int scan_counts(ag2_ctx *ctx, const int32_t *cnt, uint32_t *off, int64_t *total_out)
+{
+    cudaStream_t st = ctx->stream;
+    const int n_tiles = (kNCodes + kScanTile - 1) / kScanTile;
+    RESERVE(ctx->ix_tiles, (size_t)(n_tiles + 2) * 4);
+    uint32_t *tiles = (uint32_t *)ctx->ix_tiles.p;
+    scan_tile_sums_kernel<<<n_tiles, 1024, 0, st>>>(cnt, kNCodes, tiles);
+    scan_tiles_kernel<<<1, 1024, 0, st>>>(tiles, n_tiles, tiles + n_tiles);
+    scan_apply_kernel<<<n_tiles, 1024, 0, st>>>(cnt, kNCodes, tiles, off);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(off + kNCodes, tiles + n_tiles, 4, cudaMemcpyDeviceToDevice, st));
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, tiles + n_tiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *total_out = total;
+    return AG2_OK;
+}
+
+static int build_ref_csr(ag2_ctx *ctx)
+{
+    cudaStream_t st = ctx->stream;
+    const int64_t R = ctx->ref_len;
+    RESERVE(ctx->ix_cnt, (size_t)kNCodes * 4);
+    RESERVE(ctx->ix_off, (size_t)(kNCodes + 1) * 4);
+    RESERVE(ctx->ix_fill, (size_t)kNCodes * 4);
+    int32_t *cnt = (int32_t *)ctx->ix_cnt.p;
+    CK(cudaMemsetAsync(cnt, 0, (size_t)kNCodes * 4, st));
+    const int g = grid_for(R, 256, ctx->sm_count);
+    ref_kmer_kernel<0><<<g, 256, 0, st>>>((const uint32_t *)ctx->ref2.p, (const uint32_t *)ctx->ref_irr.p, R, cnt, nullptr, nullptr,
+                                          nullptr, nullptr, nullptr, 1);
+    mask_counts_kernel<<<grid_for(kNCodes, 256, ctx->sm_count), 256, 0, st>>>(cnt, kNCodes);
+    CK(cudaGetLastError());
+    int64_t total = 0;
+    int rc = scan_counts(ctx, cnt, (uint32_t *)ctx->ix_off.p, &total);
+    if (rc != AG2_OK) return rc;
+    ctx->ix_npos = total;
+    RESERVE(ctx->ix_pos, (size_t)(total + 4) * 4);
+    CK(cudaMemsetAsync(ctx->ix_fill.p, 0, (size_t)kNCodes * 4, st));
+    ref_kmer_kernel<1><<<g, 256, 0, st>>>((const uint32_t *)ctx->ref2.p, (const uint32_t *)ctx->ref_irr.p, R, cnt,
+                                          (const uint32_t *)ctx->ix_off.p, (int32_t *)ctx->ix_fill.p, (uint32_t *)ctx->ix_pos.p,
+                                          nullptr, nullptr, 1);
+    sort_buckets_kernel<<<grid_for(kNCodes, 256, ctx->sm_count), 256, 0, st>>>(cnt, (const uint32_t *)ctx->ix_off.p,
+                                                                               (uint32_t *)ctx->ix_pos.p, kNCodes);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->ref_indexed = true;
+    return AG2_OK;
+}
+
+int ag2_index_build(ag2_ctx *ctx, int cbl, double alpha, double beta)
+{
+    if (!ctx || cbl <= 0) return fail(ctx, AG2_EINVAL, "ag2_index_build: bad argument");
+    if (!ctx->ref_len || !ctx->n_reads) return fail(ctx, AG2_ESTATE, "ag2_index_build: load reference and reads first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (!ctx->ref_indexed) {
+        int rc = build_ref_csr(ctx);
+        if (rc != AG2_OK) return rc;
+    }
+    // A2: masked 13-mer counts of the concatenated read prefix (the ASCII of the batch is still resident)
+    RESERVE(ctx->ix_rcnt, (size_t)kNCodes * 4);
+    int32_t *rcnt = (int32_t *)ctx->ix_rcnt.p;
+    CK(cudaMemsetAsync(rcnt, 0, (size_t)kNCodes * 4, st));
+    ascii_kmer_hist_kernel<<<grid_for(ctx->read_prefix_len, 256, ctx->sm_count), 256, 0, st>>>((const char *)ctx->ascii.p,
+                                                                                                ctx->read_prefix_len, rcnt);
+    mask_counts_kernel<<<grid_for(kNCodes, 256, ctx->sm_count), 256, 0, st>>>(rcnt, kNCodes);
+    // A3 (second half): per similarity block, the read counts of its reference k-mers; A4: votes
+    const int64_t nblk = ctx->ref_len / cbl + 1;
+    RESERVE(ctx->ix_kcount, (size_t)(nblk + 10) * 4);
+    RESERVE(ctx->ix_vote, (size_t)(nblk + 10) * 4);
+    CK(cudaMemsetAsync(ctx->ix_kcount.p, 0, (size_t)(nblk + 10) * 4, st));
+    Scalars *sc = (Scalars *)ctx->scalars.p;
+    CK(cudaMemsetAsync(&sc->aligned, 0, 8, st)); // reused as the k_count total
+    ref_kmer_kernel<2><<<grid_for(ctx->ref_len, 256, ctx->sm_count), 256, 0, st>>>(
+        (const uint32_t *)ctx->ref2.p, (const uint32_t *)ctx->ref_irr.p, ctx->ref_len, nullptr, nullptr, nullptr, nullptr, rcnt,
+        (int32_t *)ctx->ix_kcount.p, cbl);
+    sum_kcount_kernel<<<grid_for(nblk, 256, ctx->sm_count), 256, 0, st>>>((const int32_t *)ctx->ix_kcount.p, nblk, &sc->aligned);
+    vote_kernel<<<grid_for(nblk + 10, 256, ctx->sm_count), 256, 0, st>>>((const int32_t *)ctx->ix_kcount.p, nblk, &sc->aligned, alpha,
+                                                                         beta, (float *)ctx->ix_vote.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->ix_nblk = nblk;
+    ctx->ix_cbl = cbl;
+    ctx->votes_ready = true;
+    return AG2_OK;
+}
+
+int ag2_index_fetch(ag2_ctx *ctx, int32_t *rcnt, int32_t *cnt, uint32_t *off, uint32_t *pos, int64_t pos_cap, int64_t *n_pos,
+                    int32_t *kcount, float *vote, int64_t *nblk)
+{
+    if (!ctx) return AG2_EINVAL;
+    if (!ctx->votes_ready) return fail(ctx, AG2_ESTATE, "ag2_index_fetch: call ag2_index_build first");
+    CK(cudaSetDevice(ctx->device));
+    if (n_pos) *n_pos = ctx->ix_npos;
+    if (nblk) *nblk = ctx->ix_nblk;
+    if (rcnt) CK(cudaMemcpy(rcnt, ctx->ix_rcnt.p, (size_t)kNCodes * 4, cudaMemcpyDeviceToHost));
+    if (cnt) CK(cudaMemcpy(cnt, ctx->ix_cnt.p, (size_t)kNCodes * 4, cudaMemcpyDeviceToHost));
+    if (off) CK(cudaMemcpy(off, ctx->ix_off.p, (size_t)(kNCodes + 1) * 4, cudaMemcpyDeviceToHost));
+    if (pos) {
+        if (pos_cap < ctx->ix_npos) return fail(ctx, AG2_ECAP, "ag2_index_fetch: need %ld positions", (long)ctx->ix_npos);
+        CK(cudaMemcpy(pos, ctx->ix_pos.p, (size_t)ctx->ix_npos * 4, cudaMemcpyDeviceToHost));
+    }
+    if (kcount) CK(cudaMemcpy(kcount, ctx->ix_kcount.p, (size_t)(ctx->ix_nblk + 10) * 4, cudaMemcpyDeviceToHost));
+    if (vote) CK(cudaMemcpy(vote, ctx->ix_vote.p, (size_t)(ctx->ix_nblk + 10) * 4, cudaMemcpyDeviceToHost));
+    return AG2_OK;
+}
+
+// ---- seeding + candidate scoring (A5-A7) --------------------------------------------------------
+int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *out, int32_t *ncand_out)
+{
+    static_assert(sizeof(ag2_seed_candidate) == sizeof(SeedCand), "ag2_seed_candidate layout");
+    if (!ctx || pass < 0 || pass > 1 || maxc < 1 || maxc > kMaxCand) return fail(ctx, AG2_EINVAL, "ag2_seed_candidates: bad argument");
+    if (!ctx->votes_ready) return fail(ctx, AG2_ESTATE, "ag2_seed_candidates: call ag2_index_build first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = ctx->n_reads;
+    RefIndex ix = {ctx->ref_len, (const int32_t *)ctx->ix_cnt.p, (const uint32_t *)ctx->ix_off.p, (const uint32_t *)ctx->ix_pos.p,
+                   (const float *)ctx->ix_vote.p, ctx->ix_cbl};
+    RESERVE(ctx->seed_need, (size_t)n * 8);
+    RESERVE(ctx->seed_prefix, (size_t)(n + 1) * 8);
+    RESERVE(ctx->seed_cands, (size_t)n * maxc * sizeof(SeedCand));
+    RESERVE(ctx->seed_ncand, (size_t)n * 4);
+    seed_need_kernel<<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(ix, (const uint32_t *)ctx->reads2.p, (const uint32_t *)ctx->reads_irr.p,
+                                                                       (const int64_t *)ctx->read_off.p, (const int32_t *)ctx->read_len.p, n,
+                                                                       pass, (int64_t *)ctx->seed_need.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->seed_need.p, n, (int64_t *)ctx->seed_prefix.p);
+    CK(cudaGetLastError());
+    std::vector<int64_t> pf((size_t)n + 1);
+    CK(cudaMemcpyAsync(pf.data(), ctx->seed_prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    size_t max_chunk = 0;
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    for (int64_t lo = 0; lo < n;) {
+        int64_t hi = lo + 1;
+        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= ctx->seed_scratch_limit) ++hi;
+        chunks.push_back({lo, hi});
+        max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
+        lo = hi;
+    }
+    RESERVE(ctx->seed_scratch, max_chunk + 64);
+    for (auto &c : chunks) {
+        const int64_t cn = c.second - c.first;
+        seed_map_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(
+            ix, (const uint32_t *)ctx->reads2.p, (const uint32_t *)ctx->reads_irr.p, (const int64_t *)ctx->read_off.p,
+            (const int32_t *)ctx->read_len.p, c.first, cn, pass, maxc, (const int64_t *)ctx->seed_prefix.p, (uint8_t *)ctx->seed_scratch.p,
+            (SeedCand *)ctx->seed_cands.p, (int32_t *)ctx->seed_ncand.p);
+        CK(cudaGetLastError());
+    }
+    if (out) CK(cudaMemcpyAsync(out, ctx->seed_cands.p, (size_t)n * maxc * sizeof(SeedCand), cudaMemcpyDeviceToHost, st));
+    if (ncand_out) CK(cudaMemcpyAsync(ncand_out, ctx->seed_ncand.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AG2_OK;
 }
 
 } // extern "C"

@@ -20,7 +20,10 @@ CANDIDATE_DTYPE = np.dtype([("read", "<i4"), ("strand", "<i4"), ("loc1", "<i8"),
 RECORD_DTYPE = np.dtype([("ok", "<i4"), ("read", "<i4"), ("strand", "<i4"), ("vscore", "<i4"), ("qb", "<i4"),
                          ("qe", "<i4"), ("qs", "<i4"), ("aln_len", "<i4"), ("sb", "<i8"), ("se", "<i8"),
                          ("aln_off", "<i8")])
-assert CANDIDATE_DTYPE.itemsize == 24 and RECORD_DTYPE.itemsize == 56
+SEED_CAND_DTYPE = np.dtype([("loc1", "<i8"), ("loc2", "<i8"), ("left1", "<i8"), ("left2", "<i8"), ("right1", "<i8"),
+                            ("right2", "<i8"), ("score", "<i4"), ("num1", "<i4"), ("num2", "<i4"), ("chain", "<i4")])
+NCODES = 1 << 26
+assert CANDIDATE_DTYPE.itemsize == 24 and RECORD_DTYPE.itemsize == 56 and SEED_CAND_DTYPE.itemsize == 64
 
 
 class ExtendStats(C.Structure):
@@ -31,7 +34,7 @@ class ExtendStats(C.Structure):
 EXPORTS = [
     "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load",
     "ag2_xdrop_extend_batch", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
-    "ag2_ctx_stream",
+    "ag2_ctx_stream", "ag2_index_build", "ag2_index_fetch", "ag2_seed_candidates",
 ]
 
 
@@ -65,6 +68,9 @@ def load() -> C.CDLL:
     L.ag2_extend_run.argtypes = [vp]
     L.ag2_extend_fetch.argtypes = [vp, vp, vp, vp, i64, C.POINTER(i64)]
     L.ag2_extend_get_stats.argtypes = [vp, C.POINTER(ExtendStats)]
+    L.ag2_index_build.argtypes = [vp, i32, C.c_double, C.c_double]
+    L.ag2_index_fetch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(i64), vp, vp, C.POINTER(i64)]
+    L.ag2_seed_candidates.argtypes = [vp, i32, i32, vp, vp]
     L.ag2_ctx_stream.argtypes = [vp]
     L.ag2_ctx_stream.restype = vp
     _lib = L

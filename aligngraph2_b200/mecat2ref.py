@@ -17,7 +17,7 @@ from typing import Sequence
 import numpy as np
 
 from . import lib as _lib
-from .lib import CANDIDATE_DTYPE, RECORD_DTYPE, Ag2Error, ExtendStats
+from .lib import CANDIDATE_DTYPE, NCODES, RECORD_DTYPE, SEED_CAND_DTYPE, Ag2Error, ExtendStats
 
 
 def _as_bytes_array(x) -> np.ndarray:
@@ -76,6 +76,36 @@ class Mecat2RefDevice:
         n = offsets.size - 1
         self._check(self._L.ag2_reads_load(self._ctx, bases.ctypes.data, offsets.ctypes.data, n), "ag2_reads_load")
         self.n_reads = n
+
+    # -- index + seeding -------------------------------------------------------------------------
+    def build_index(self, cbl: int = 200, alpha: float = 0.5, beta: float = 2.0) -> None:
+        """build_read_index + creat_ref_index + get_vote (impl_large.cpp:258-608) for the loaded reference and
+        read batch; cbl / alpha / beta are mecat2ref+'s -z / -l / -u."""
+        self._check(self._L.ag2_index_build(self._ctx, cbl, alpha, beta), "ag2_index_build")
+
+    def fetch_index(self) -> dict:
+        """Host copies of the device index (tests / inspection)."""
+        n_pos, nblk = C.c_int64(), C.c_int64()
+        self._check(self._L.ag2_index_fetch(self._ctx, None, None, None, None, 0, C.byref(n_pos), None, None, C.byref(nblk)),
+                    "ag2_index_fetch")
+        d = dict(rcnt=np.empty(NCODES, np.int32), cnt=np.empty(NCODES, np.int32), off=np.empty(NCODES + 1, np.uint32),
+                 pos=np.empty(max(n_pos.value, 1), np.uint32), kcount=np.empty(nblk.value + 10, np.int32),
+                 vote=np.empty(nblk.value + 10, np.float32))
+        self._check(self._L.ag2_index_fetch(self._ctx, d["rcnt"].ctypes.data, d["cnt"].ctypes.data, d["off"].ctypes.data,
+                                            d["pos"].ctypes.data, d["pos"].size, C.byref(n_pos), d["kcount"].ctypes.data,
+                                            d["vote"].ctypes.data, C.byref(nblk)), "ag2_index_fetch")
+        d["pos"] = d["pos"][:n_pos.value]
+        d["nblk"] = nblk.value
+        return d
+
+    def seed_candidates(self, pass_: int = 0, maxc: int = 10):
+        """Seeding + candidate scoring of every loaded read (reference_mapping :776-991; pass_=1 is the
+        reference's second pass).  Returns (cands[n_reads, maxc] of SEED_CAND_DTYPE, ncand[n_reads])."""
+        cands = np.zeros((self.n_reads, maxc), dtype=SEED_CAND_DTYPE)
+        ncand = np.zeros(self.n_reads, dtype=np.int32)
+        self._check(self._L.ag2_seed_candidates(self._ctx, pass_, maxc, cands.ctypes.data, ncand.ctypes.data),
+                    "ag2_seed_candidates")
+        return cands, ncand
 
     # -- extension ---------------------------------------------------------------------------
     @staticmethod

@@ -101,6 +101,29 @@ int ag2_extend_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *sa
                      int64_t *aln_used);
 int ag2_extend_get_stats(ag2_ctx *ctx, ag2_extend_stats *out);
 
+/* ---- index build: build_read_index + creat_ref_index + get_vote (mecat2ref_impl_large.cpp:258-608) ----
+ * Uses the loaded reference and the loaded read batch (its first <= 100 000 reads / 1e9 characters, as the
+ * reference does).  cbl / alpha / beta are mecat2ref+'s -z / -l / -u.  The index stays on the device. */
+int ag2_index_build(ag2_ctx *ctx, int cbl, double alpha, double beta);
+
+/* Copies of the device index for inspection; any pointer may be NULL.  rcnt/cnt: 4^13 masked counts
+ * (countin1 / countin), off: 4^13+1 CSR offsets, pos: *n_pos 1-based k-mer starts (allloc), kcount/vote:
+ * *nblk + 10 entries (sim::k_count / sim::vote). */
+int ag2_index_fetch(ag2_ctx *ctx, int32_t *rcnt, int32_t *cnt, uint32_t *off, uint32_t *pos, int64_t pos_cap,
+                    int64_t *n_pos, int32_t *kcount, float *vote, int64_t *nblk);
+
+/* candidate_save (mecat2ref_defs.h:90-95) */
+typedef struct ag2_seed_candidate {
+    int64_t loc1, loc2, left1, left2, right1, right2;
+    int32_t score, num1, num2;
+    int32_t chain;   /* 'F' or 'R' */
+} ag2_seed_candidate;
+
+/* Seeding + candidate scoring of every loaded read (reference_mapping, mecat2ref_impl_large.cpp:776-991;
+ * pass = 1 is the reference's second pass :1049-1260).  out[r * maxc + i], i < ncand[r], in canidate_loc[]
+ * order; maxc is mecat2ref+'s -n (<= 16). */
+int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *out, int32_t *ncand);
+
 /* The CUDA stream the context launches on (cudaStream_t as void*), for callers that time with
  * their own events. */
 void *ag2_ctx_stream(ag2_ctx *ctx);

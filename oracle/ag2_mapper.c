@@ -792,6 +792,36 @@ static int output_results(orc_mapper *m, FILE *out) /* aux.cpp:541-559 */
     return written;
 }
 
+/* seeding + candidate scan only (no extension), pass 0 or the second pass; returns #candidates in out[maxc] */
+int orc_seed_candidates(orc_mapper *m, const char *read, int len, int pass, orc_cand *out)
+{
+    if (m->rev_cap < len + 1) {
+        m->rev_cap = len + 1;
+        m->rev = (char *)realloc(m->rev, (size_t)m->rev_cap);
+    }
+    for (int i = 0; i < len; ++i) {
+        char c = read[len - 1 - i];
+        switch (c) {
+        case 'A': c = 'T'; break;
+        case 'T': c = 'A'; break;
+        case 'C': c = 'G'; break;
+        case 'G': c = 'C'; break;
+        default: break;
+        }
+        m->rev[i] = c;
+    }
+    m->rev[len] = 0;
+    int BC = pass == 0 ? 5 + len / 1000 : 5;
+    if (BC > 20) BC = 20;
+    const long zv = pass == 0 ? ZV : ZVS;
+    m->ncand = 0;
+    seed_and_scan(m, read, len, BC, 0, zv, pass == 0 ? 6 : 4);
+    seed_and_scan(m, m->rev, len, BC, 1, zv, pass == 0 ? 6 : 4);
+    reset_blocks(m);
+    memcpy(out, m->cands, sizeof(orc_cand) * (size_t)m->ncand);
+    return m->ncand;
+}
+
 /* one read through reference_mapping's loop body (:776-1316).  Returns the number of records written. */
 int orc_map_read(orc_mapper *m, int read_id, const char *read, int len, FILE *out)
 {

@@ -89,6 +89,8 @@ orc_mapper *orc_mapper_new(const orc_index *ix, int maxc, int num_output);
 void orc_mapper_free(orc_mapper *m);
 /* reference_mapping's loop body for one read; appends `.r` records to out (may be NULL) */
 int orc_map_read(orc_mapper *m, int read_id, const char *read, int len, FILE *out);
+/* seeding + candidate scan of one read without extension (pass 0, or 1 = the reference's second pass) */
+int orc_seed_candidates(orc_mapper *m, const char *read, int len, int pass, orc_cand *out);
 /* pass-1 candidates of the read orc_map_read saw last, in canidate_loc[] order */
 int orc_mapper_last_candidates(const orc_mapper *m, orc_cand *out, int *pass2);
 long orc_mapper_cells(const orc_mapper *m);

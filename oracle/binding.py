@@ -203,3 +203,63 @@ class MapperOracle:
         keys = ("cells", "calls", "aligned", "pass2_reads", "insert_loc", "rescue_extensions", "multi_candidate_reads",
                 "votes_ne_1")
         return n, dict(zip(keys, (int(v) for v in st)))
+
+
+class _Index(C.Structure):
+    _fields_ = [("R", C.c_long), ("ref", C.c_void_p), ("cbl", C.c_int), ("nblk", C.c_long), ("rcnt", C.c_void_p),
+                ("cnt", C.c_void_p), ("off", C.c_void_p), ("pos", C.c_void_p), ("kcount", C.c_void_p), ("vote", C.c_void_p),
+                ("ave", C.c_float)]
+
+
+class _Cand(C.Structure):
+    _fields_ = [("loc1", C.c_long), ("loc2", C.c_long), ("left1", C.c_long), ("left2", C.c_long), ("right1", C.c_long),
+                ("right2", C.c_long), ("score", C.c_int), ("num1", C.c_int), ("num2", C.c_int), ("chain", C.c_char)]
+
+
+NCODES = 1 << 26
+
+
+class IndexOracle:
+    """orc_index_build (creat_ref_index + get_vote) and orc_seed_candidates, with numpy views of the arrays."""
+
+    def __init__(self, genome: bytes, bases: bytes, offsets, cbl=200, alpha=0.5, beta=2.0, maxc=10):
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        L = self.lib = C.CDLL(ORACLE_SO)
+        L.orc_read_hist13.argtypes = [C.c_char_p, C.c_long, C.c_void_p]
+        L.orc_read_index_prefix.restype = C.c_long
+        L.orc_read_index_prefix.argtypes = [C.c_void_p, C.c_long]
+        L.orc_index_build.restype = C.POINTER(_Index)
+        L.orc_index_build.argtypes = [C.c_char_p, C.c_long, C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.orc_index_free.argtypes = [C.POINTER(_Index)]
+        L.orc_mapper_new.restype = C.c_void_p
+        L.orc_mapper_new.argtypes = [C.POINTER(_Index), C.c_int, C.c_int]
+        L.orc_mapper_free.argtypes = [C.c_void_p]
+        L.orc_seed_candidates.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_Cand)]
+        self.ref = MapperOracle.upper_ref(genome)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        pre = L.orc_read_index_prefix(offsets.ctypes.data, len(offsets) - 1)
+        self.rcnt = np.zeros(NCODES, dtype=np.int32)
+        L.orc_read_hist13(bases, int(offsets[pre]), self.rcnt.ctypes.data)
+        self.ix = L.orc_index_build(self.ref, len(self.ref), self.rcnt.ctypes.data, cbl, alpha, beta)
+        ix = self.ix.contents
+        self.nblk = ix.nblk
+        self.cnt = np.ctypeslib.as_array(C.cast(ix.cnt, C.POINTER(C.c_int32)), (NCODES,))
+        self.off = np.ctypeslib.as_array(C.cast(ix.off, C.POINTER(C.c_uint32)), (NCODES + 1,))
+        self.pos = np.ctypeslib.as_array(C.cast(ix.pos, C.POINTER(C.c_uint32)), (int(self.off[-1]) + 1,))[:-1]
+        self.kcount = np.ctypeslib.as_array(C.cast(ix.kcount, C.POINTER(C.c_int32)), (ix.nblk + 10,))
+        self.vote = np.ctypeslib.as_array(C.cast(ix.vote, C.POINTER(C.c_float)), (ix.nblk + 10,))
+        self.maxc = maxc
+        self.m = C.c_void_p(L.orc_mapper_new(self.ix, maxc, 1))
+
+    def candidates(self, read: bytes, pass_: int = 0):
+        out = (_Cand * (self.maxc + 1))()
+        n = self.lib.orc_seed_candidates(self.m, read, len(read), pass_, out)
+        return [(c.loc1, c.loc2, c.left1, c.left2, c.right1, c.right2, c.score, c.num1, c.num2, ord(c.chain)) for c in out[:n]]
+
+    def __del__(self):
+        try:
+            self.lib.orc_mapper_free(self.m)
+            self.lib.orc_index_free(self.ix)
+        except Exception:
+            pass
