@@ -6,6 +6,7 @@
 #include "xdrop_device.cuh"
 #include "xdrop_lane.cuh"
 #include "index_kernels.cuh"
+#include "map_kernels.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -239,6 +240,11 @@ struct ag2_ctx {
     bool ref_indexed = false, votes_ready = false;
     int64_t read_prefix_len = 0;       // bytes of the concatenated reads that enter the read index (A2)
     DevBuf seed_need, seed_prefix, seed_scratch, seed_cands, seed_ncand;
+    // ag2_map_reads
+    DevBuf rec_pool, map_cand, map_cand_prefix, map_plans, map_rescue_n, map_rescue_prefix, map_out_refs, map_nout, map_flags,
+        map_list, map_out_prefix, map_out_rec;
+    int64_t map_n_out = 0;
+    bool mapped = false;
     size_t seed_scratch_limit = (size_t)4 << 30;
     DevBuf reads2, reads_irr, read_off, read_len, ascii_offs;
     int64_t n_reads = 0, read_bases = 0;
@@ -299,6 +305,23 @@ int reserve(ag2_ctx *ctx, DevBuf &b, size_t bytes)
     }
     const size_t want = bytes + bytes / 16 + 256;
     CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return AG2_OK;
+}
+
+// like reserve(), but the first `keep` bytes survive a reallocation
+int reserve_keep(ag2_ctx *ctx, DevBuf &b, size_t bytes, size_t keep)
+{
+    if (bytes <= b.cap) return AG2_OK;
+    const size_t want = bytes + bytes / 8 + 256;
+    void *np = nullptr;
+    CK(cudaMalloc(&np, want));
+    if (b.p) {
+        if (keep) CK(cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaFree(b.p));
+    }
+    b.p = np;
     b.cap = want;
     return AG2_OK;
 }
@@ -371,7 +394,9 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->ref_irr, &ctx->ref_ascii, &ctx->ref_offs, &ctx->ix_rcnt, &ctx->ix_cnt, &ctx->ix_off, &ctx->ix_pos,
                      &ctx->ix_fill, &ctx->ix_tiles, &ctx->ix_kcount, &ctx->ix_vote, &ctx->seed_need, &ctx->seed_prefix,
-                     &ctx->seed_scratch, &ctx->seed_cands, &ctx->seed_ncand, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
+                     &ctx->seed_scratch, &ctx->seed_cands, &ctx->seed_ncand, &ctx->rec_pool, &ctx->map_cand, &ctx->map_cand_prefix,
+                     &ctx->map_plans, &ctx->map_rescue_n, &ctx->map_rescue_prefix, &ctx->map_out_refs, &ctx->map_nout, &ctx->map_flags,
+                     &ctx->map_list, &ctx->map_out_prefix, &ctx->map_out_rec, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
                      &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->wide_queue, &ctx->scalars};
@@ -474,11 +499,11 @@ int ag2_extend_upload(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n)
     return AG2_OK;
 }
 
-int ag2_extend_run(ag2_ctx *ctx)
+// extend_candidate over n device-resident candidates.  Records go to d_rec[0..n); the strings of the ok records are
+// appended to the dense string pool at dense_base (which this returns advanced), earlier contents are kept.
+static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record *d_rec, int64_t dense_base_in, int64_t *dense_base_out,
+                        bool fresh_stats)
 {
-    if (!ctx || ctx->n_cand <= 0) return fail(ctx, AG2_ESTATE, "ag2_extend_run: no candidates uploaded");
-    CK(cudaSetDevice(ctx->device));
-    const int64_t n = ctx->n_cand;
     cudaStream_t st = ctx->stream;
     int launches = 0;
     RESERVE(ctx->geom, (size_t)n * sizeof(ExtGeom));
@@ -487,7 +512,6 @@ int ag2_extend_run(ag2_ctx *ctx)
     RESERVE(ctx->nmeta, (size_t)n * 8);
     RESERVE(ctx->meta_prefix, (size_t)(n + 1) * 8);
     RESERVE(ctx->res, (size_t)n * 2 * sizeof(ChainResult));
-    RESERVE(ctx->rec, (size_t)n * sizeof(Record));
     RESERVE(ctx->str_begin, (size_t)n * 8);
     RESERVE(ctx->ok_len, (size_t)n * 8);
     RESERVE(ctx->dense_off, (size_t)(n + 1) * 8);
@@ -507,8 +531,8 @@ int ag2_extend_run(ag2_ctx *ctx)
 
     const PackedSeqs sq = seqs_of(ctx);
     Scalars *sc = (Scalars *)ctx->scalars.p;
-    CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
-    extend_setup_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const Candidate *)ctx->cand.p, n, sq, ctx->n_reads,
+    if (fresh_stats) CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+    extend_setup_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(d_cand, n, sq, ctx->n_reads,
                                                                          (ExtGeom *)ctx->geom.p, (int64_t *)ctx->caps.p,
                                                                          (int64_t *)ctx->nmeta.p);
     exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->caps.p, n, (int64_t *)ctx->prefix.p);
@@ -537,8 +561,12 @@ int ag2_extend_run(ag2_ctx *ctx)
     RESERVE(ctx->ws_t, max_chunk + 64);
     RESERVE(ctx->meta, (max_meta + 16) * 4);
     // upper bound of the dense strings: every column consumes a base of the read or of its window
-    RESERVE(ctx->out_q, (size_t)pf[n] + 64);
-    RESERVE(ctx->out_t, (size_t)pf[n] + 64);
+    {
+        int rk = reserve_keep(ctx, ctx->out_q, (size_t)(dense_base_in + pf[n]) + 64, (size_t)dense_base_in);
+        if (rk != AG2_OK) return rk;
+        rk = reserve_keep(ctx, ctx->out_t, (size_t)(dense_base_in + pf[n]) + 64, (size_t)dense_base_in);
+        if (rk != AG2_OK) return rk;
+    }
     while (ctx->chain_events.size() < chunks.size()) {
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
@@ -548,7 +576,7 @@ int ag2_extend_run(ag2_ctx *ctx)
 
     // per chunk: lane kernel -> (wide rerun) -> finalize -> scan of the ok lengths -> assemble into the
     // dense output at the running base
-    int64_t dense_base = 0;
+    int64_t dense_base = dense_base_in;
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const int64_t lo = chunks[ci].first, cn = chunks[ci].second - chunks[ci].first;
         set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p,
@@ -556,7 +584,7 @@ int ag2_extend_run(ag2_ctx *ctx)
         CK(cudaMemsetAsync(&sc->next_fast, 0, 2 * sizeof(unsigned long long) + sizeof(unsigned int), st));
         LaneArgs a = {};
         a.seqs = sq;
-        a.cand = (const Candidate *)ctx->cand.p + lo;
+        a.cand = d_cand + lo;
         a.geom = (const ExtGeom *)ctx->geom.p + lo;
         a.res = (ChainResult *)ctx->res.p + 2 * lo;
         a.meta = (uint32_t *)ctx->meta.p;
@@ -598,8 +626,8 @@ int ag2_extend_run(ag2_ctx *ctx)
             ++launches;
         }
         extend_finalize_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>(
-            (const Candidate *)ctx->cand.p, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p,
-            (const int32_t *)ctx->read_len.p, lo, cn, (Record *)ctx->rec.p, (int64_t *)ctx->str_begin.p,
+            d_cand, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p,
+            (const int32_t *)ctx->read_len.p, lo, cn, d_rec, (int64_t *)ctx->str_begin.p,
             (int64_t *)ctx->ok_len.p);
         exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->ok_len.p + lo, cn, (int64_t *)ctx->dense_off.p + lo);
         launches += 2;
@@ -607,7 +635,7 @@ int ag2_extend_run(ag2_ctx *ctx)
         CK(cudaMemcpyAsync(&chunk_total, (int64_t *)ctx->dense_off.p + lo + cn, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         assemble_kernel<<<grid_for(cn * 32, 256, ctx->sm_count), 256, 0, st>>>(
-            (Record *)ctx->rec.p, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p, (const uint32_t *)ctx->meta.p,
+            d_rec, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p, (const uint32_t *)ctx->meta.p,
             (const int64_t *)ctx->dense_off.p, dense_base, lo, cn, (const char *)ctx->ws_q.p, (const char *)ctx->ws_t.p,
             (char *)ctx->out_q.p, (char *)ctx->out_t.p, &sc->aligned, &sc->columns);
         ++launches;
@@ -615,7 +643,7 @@ int ag2_extend_run(ag2_ctx *ctx)
         dense_base += chunk_total;
     }
     CK(cudaStreamSynchronize(st));
-    ctx->out_total = dense_base;
+    *dense_base_out = dense_base;
 
     Scalars hs;
     CK(cudaMemcpy(&hs, sc, sizeof hs, cudaMemcpyDeviceToHost));
@@ -627,16 +655,29 @@ int ag2_extend_run(ag2_ctx *ctx)
     s.wide_chains = (int64_t)hs.ctr.wide;
     s.aligned = (int64_t)hs.aligned;
     s.columns = (int64_t)hs.columns;
-    s.launches = launches;
-    s.kernel_ms = 0;
+    s.launches = (fresh_stats ? 0 : s.launches) + launches;
+    if (fresh_stats) s.kernel_ms = 0;
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx->chain_events[ci].first, ctx->chain_events[ci].second));
         s.kernel_ms += ms;
     }
+    return AG2_OK;
+}
+
+int ag2_extend_run(ag2_ctx *ctx)
+{
+    if (!ctx || ctx->n_cand <= 0) return fail(ctx, AG2_ESTATE, "ag2_extend_run: no candidates uploaded");
+    CK(cudaSetDevice(ctx->device));
+    RESERVE(ctx->rec, (size_t)ctx->n_cand * sizeof(Record));
+    int64_t total = 0;
+    const int rc = extend_batch(ctx, (const Candidate *)ctx->cand.p, ctx->n_cand, (Record *)ctx->rec.p, 0, &total, true);
+    if (rc != AG2_OK) return rc;
+    ctx->out_total = total;
     ctx->ran = true;
     return AG2_OK;
 }
+
 
 int ag2_extend_get_stats(ag2_ctx *ctx, ag2_extend_stats *out)
 {
@@ -829,6 +870,201 @@ int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *ou
     if (ncand_out) CK(cudaMemcpyAsync(ncand_out, ctx->seed_ncand.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return AG2_OK;
+}
+
+// The seed candidates of the last ag2_seed_candidates call become the extension candidates, on the device.
+int ag2_extend_upload_from_seeds(ag2_ctx *ctx, int maxc, int64_t *n_out)
+{
+    if (!ctx || maxc < 1 || maxc > kMaxCand) return fail(ctx, AG2_EINVAL, "ag2_extend_upload_from_seeds: bad argument");
+    if (!ctx->seed_ncand.p || !ctx->votes_ready) return fail(ctx, AG2_ESTATE, "ag2_extend_upload_from_seeds: call ag2_seed_candidates first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = ctx->n_reads;
+    RESERVE(ctx->seed_need, (size_t)n * 8);
+    RESERVE(ctx->seed_prefix, (size_t)(n + 1) * 8);
+    widen_i32_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const int32_t *)ctx->seed_ncand.p, n, (int64_t *)ctx->seed_need.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->seed_need.p, n, (int64_t *)ctx->seed_prefix.p);
+    int64_t total = 0;
+    CK(cudaMemcpyAsync(&total, (int64_t *)ctx->seed_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_out) *n_out = total;
+    ctx->n_cand = 0;
+    ctx->ran = false;
+    if (total == 0) return AG2_OK;
+    RESERVE(ctx->cand, (size_t)total * sizeof(Candidate));
+    seeds_to_candidates_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const SeedCand *)ctx->seed_cands.p,
+                                                                                (const int32_t *)ctx->seed_ncand.p,
+                                                                                (const int64_t *)ctx->seed_prefix.p, n, maxc,
+                                                                                (Candidate *)ctx->cand.p);
+    CK(cudaGetLastError());
+    ctx->n_cand = total;
+    return AG2_OK;
+}
+
+// ---- the whole per-read path: reference_mapping()'s loop body for a batch (impl_large.cpp:776-1316) ----
+// One pass (pass 0, or the reference's second pass over `reads`, a device list of read indices):
+// seed -> extend every candidate -> plan rescue -> extend the rescue candidates -> link + choose the output.
+static int map_pass(ag2_ctx *ctx, int pass, int maxc, int num_output, const int32_t *d_reads, int64_t n, int64_t *pool_n, int64_t *dense_base,
+                    bool first_batch)
+{
+    cudaStream_t st = ctx->stream;
+    const PackedSeqs sq = seqs_of(ctx);
+    RefIndex ix = {ctx->ref_len, (const int32_t *)ctx->ix_cnt.p, (const uint32_t *)ctx->ix_off.p, (const uint32_t *)ctx->ix_pos.p,
+                   (const float *)ctx->ix_vote.p, ctx->ix_cbl};
+    const int g = grid_for(n, 128, ctx->sm_count);
+    // seeding + candidates
+    RESERVE(ctx->seed_need, (size_t)n * 8);
+    RESERVE(ctx->seed_prefix, (size_t)(n + 1) * 8);
+    RESERVE(ctx->seed_cands, (size_t)n * maxc * sizeof(SeedCand));
+    RESERVE(ctx->seed_ncand, (size_t)n * 4);
+    seed_need_sub_kernel<<<g, 128, 0, st>>>(ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads, n, pass, (int64_t *)ctx->seed_need.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->seed_need.p, n, (int64_t *)ctx->seed_prefix.p);
+    CK(cudaGetLastError());
+    std::vector<int64_t> pf((size_t)n + 1);
+    CK(cudaMemcpyAsync(pf.data(), ctx->seed_prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    size_t max_chunk = 0;
+    std::vector<std::pair<int64_t, int64_t>> chunks;
+    for (int64_t lo = 0; lo < n;) {
+        int64_t hi = lo + 1;
+        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= ctx->seed_scratch_limit) ++hi;
+        chunks.push_back({lo, hi});
+        max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
+        lo = hi;
+    }
+    RESERVE(ctx->seed_scratch, max_chunk + 64);
+    for (auto &c : chunks) {
+        const int64_t cn = c.second - c.first;
+        seed_map_sub_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads,
+                                                                              c.first, cn, pass, maxc, (const int64_t *)ctx->seed_prefix.p,
+                                                                              (uint8_t *)ctx->seed_scratch.p, (SeedCand *)ctx->seed_cands.p,
+                                                                              (int32_t *)ctx->seed_ncand.p);
+    }
+    CK(cudaGetLastError());
+    // candidates of all reads, in order
+    RESERVE(ctx->map_cand_prefix, (size_t)(n + 1) * 8);
+    RESERVE(ctx->map_rescue_n, (size_t)n * 8);
+    widen_i32_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const int32_t *)ctx->seed_ncand.p, n, (int64_t *)ctx->map_rescue_n.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->map_rescue_n.p, n, (int64_t *)ctx->map_cand_prefix.p);
+    int64_t n_cand = 0;
+    CK(cudaMemcpyAsync(&n_cand, (int64_t *)ctx->map_cand_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t base0 = *pool_n;
+    {
+        int rk = reserve_keep(ctx, ctx->rec_pool, (size_t)(base0 + n_cand + 1) * sizeof(Record), (size_t)base0 * sizeof(Record));
+        if (rk != AG2_OK) return rk;
+    }
+    if (n_cand > 0) {
+        RESERVE(ctx->map_cand, (size_t)n_cand * sizeof(Candidate));
+        seeds_to_candidates_sub_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(
+            (const SeedCand *)ctx->seed_cands.p, (const int32_t *)ctx->seed_ncand.p, (const int64_t *)ctx->map_cand_prefix.p, d_reads, n, maxc,
+            (Candidate *)ctx->map_cand.p);
+        CK(cudaGetLastError());
+        int rc = extend_batch(ctx, (const Candidate *)ctx->map_cand.p, n_cand, (Record *)ctx->rec_pool.p + base0, *dense_base, dense_base,
+                              first_batch);
+        if (rc != AG2_OK) return rc;
+    }
+    *pool_n = base0 + n_cand;
+    // rescue planning (same scratch layout as the seeding)
+    RESERVE(ctx->map_plans, (size_t)n * sizeof(ReadPlan));
+    RESERVE(ctx->map_rescue_prefix, (size_t)(n + 1) * 8);
+    for (auto &c : chunks) {
+        const int64_t cn = c.second - c.first;
+        plan_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads, c.first, cn,
+                                                                      pass, (const int32_t *)ctx->seed_ncand.p,
+                                                                      (const int64_t *)ctx->map_cand_prefix.p, (const Record *)ctx->rec_pool.p,
+                                                                      base0, (const int64_t *)ctx->seed_prefix.p, (uint8_t *)ctx->seed_scratch.p,
+                                                                      (ReadPlan *)ctx->map_plans.p, (int64_t *)ctx->map_rescue_n.p);
+    }
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->map_rescue_n.p, n, (int64_t *)ctx->map_rescue_prefix.p);
+    CK(cudaGetLastError());
+    int64_t n_resc = 0;
+    CK(cudaMemcpyAsync(&n_resc, (int64_t *)ctx->map_rescue_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int64_t base1 = *pool_n;
+    if (n_resc > 0) {
+        int rk = reserve_keep(ctx, ctx->rec_pool, (size_t)(base1 + n_resc + 1) * sizeof(Record), (size_t)base1 * sizeof(Record));
+        if (rk != AG2_OK) return rk;
+        RESERVE(ctx->map_cand, (size_t)n_resc * sizeof(Candidate));
+        rescue_gather_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const ReadPlan *)ctx->map_plans.p,
+                                                                              (const int64_t *)ctx->map_rescue_prefix.p, d_reads, n,
+                                                                              (Candidate *)ctx->map_cand.p);
+        CK(cudaGetLastError());
+        int rc = extend_batch(ctx, (const Candidate *)ctx->map_cand.p, n_resc, (Record *)ctx->rec_pool.p + base1, *dense_base, dense_base, false);
+        if (rc != AG2_OK) return rc;
+        *pool_n = base1 + n_resc;
+    }
+    finish_kernel<<<g, 128, 0, st>>>((ReadPlan *)ctx->map_plans.p, (const int64_t *)ctx->map_rescue_prefix.p, d_reads, n, sq.read_len,
+                                     (const Record *)ctx->rec_pool.p, base1, num_output, (int64_t *)ctx->map_out_refs.p,
+                                     (int32_t *)ctx->map_nout.p, pass == 0 ? (int32_t *)ctx->map_flags.p : nullptr);
+    CK(cudaGetLastError());
+    return AG2_OK;
+}
+
+int ag2_map_reads(ag2_ctx *ctx, int maxc, int num_output, int64_t *n_records)
+{
+    if (!ctx || maxc < 1 || maxc > kMaxCand || num_output < 1) return fail(ctx, AG2_EINVAL, "ag2_map_reads: bad argument");
+    if (!ctx->votes_ready) return fail(ctx, AG2_ESTATE, "ag2_map_reads: call ag2_index_build first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = ctx->n_reads;
+    if (num_output > maxc) num_output = maxc; // mecat2ref.cpp:196-201
+    RESERVE(ctx->map_out_refs, (size_t)n * kOutCap * 8);
+    RESERVE(ctx->map_nout, (size_t)n * 4);
+    RESERVE(ctx->map_flags, (size_t)n * 4);
+    RESERVE(ctx->map_list, (size_t)n * 4);
+    RESERVE(ctx->map_out_prefix, (size_t)(n + 1) * 8);
+    int64_t pool_n = 0, dense = 0;
+    int rc = map_pass(ctx, 0, maxc, num_output, nullptr, n, &pool_n, &dense, true);
+    if (rc != AG2_OK) return rc;
+    // second pass for the reads none of whose candidates extended (:1049)
+    flags_to_i64_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const int32_t *)ctx->map_flags.p, n, (int64_t *)ctx->map_rescue_n.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->map_rescue_n.p, n, (int64_t *)ctx->map_out_prefix.p);
+    compact_reads_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const int32_t *)ctx->map_flags.p, (const int64_t *)ctx->map_out_prefix.p, n,
+                                                                          (int32_t *)ctx->map_list.p);
+    int64_t n2 = 0;
+    CK(cudaMemcpyAsync(&n2, (int64_t *)ctx->map_out_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n2 > 0) {
+        rc = map_pass(ctx, 1, maxc, num_output, (const int32_t *)ctx->map_list.p, n2, &pool_n, &dense, false);
+        if (rc != AG2_OK) return rc;
+    }
+    // records in thread-file order
+    widen_i32_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const int32_t *)ctx->map_nout.p, n, (int64_t *)ctx->map_rescue_n.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->map_rescue_n.p, n, (int64_t *)ctx->map_out_prefix.p);
+    int64_t n_out = 0;
+    CK(cudaMemcpyAsync(&n_out, (int64_t *)ctx->map_out_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    RESERVE(ctx->map_out_rec, (size_t)(n_out + 1) * sizeof(Record));
+    gather_output_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((const int64_t *)ctx->map_out_refs.p, (const int32_t *)ctx->map_nout.p,
+                                                                          (const int64_t *)ctx->map_out_prefix.p, n, (const Record *)ctx->rec_pool.p,
+                                                                          (Record *)ctx->map_out_rec.p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->map_n_out = n_out;
+    ctx->out_total = dense;
+    ctx->mapped = true;
+    ctx->stats.aligned = 0; // per-call totals of the extension batches are in cells / rows / blocks; aligned counts every extension
+    if (n_records) *n_records = n_out;
+    return AG2_OK;
+}
+
+int ag2_map_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used)
+{
+    if (!ctx || !rec_out) return fail(ctx, AG2_EINVAL, "ag2_map_fetch: bad argument");
+    if (!ctx->mapped) return fail(ctx, AG2_ESTATE, "ag2_map_fetch: call ag2_map_reads first");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(rec_out, ctx->map_out_rec.p, (size_t)ctx->map_n_out * sizeof(Record), cudaMemcpyDeviceToHost, ctx->stream));
+    if (aln_used) *aln_used = ctx->out_total;
+    int rc = AG2_OK;
+    if (qaln_out && saln_out && aln_cap >= ctx->out_total) {
+        CK(cudaMemcpyAsync(qaln_out, ctx->out_q.p, (size_t)ctx->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(saln_out, ctx->out_t.p, (size_t)ctx->out_total, cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (qaln_out || saln_out) {
+        rc = fail(ctx, AG2_ECAP, "ag2_map_fetch: need %ld bytes per string, have %ld", (long)ctx->out_total, (long)aln_cap);
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
 }
 
 } // extern "C"

@@ -14,6 +14,7 @@
 #pragma once
 
 #include "seed_device.cuh"
+#include "xdrop_device.cuh"
 
 namespace ag2 {
 
@@ -263,6 +264,30 @@ __global__ void seed_map_kernel(RefIndex ix, const uint32_t *reads2, const uint3
         ncand[r] = nc;
         for (int i = 0; i < nc; ++i) cands[r * maxc + i] = local[i];
     }
+}
+
+// every seed candidate of every read becomes one extension candidate, reads in order, canidate_loc[] order inside
+__global__ void seeds_to_candidates_kernel(const SeedCand *cands, const int32_t *ncand, const int64_t *prefix, int64_t n_reads,
+                                           int maxc, Candidate *out)
+{
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_reads; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t base = prefix[r];
+        for (int i = 0; i < ncand[r]; ++i) {
+            const SeedCand &c = cands[r * maxc + i];
+            Candidate o;
+            o.read = (int32_t)r;
+            o.strand = c.chain == 'F' ? 0 : 1;
+            o.loc1 = c.loc1;
+            o.loc2 = (int32_t)c.loc2;
+            o.score = c.score;
+            out[base + i] = o;
+        }
+    }
+}
+
+__global__ void widen_i32_kernel(const int32_t *in, int64_t n, int64_t *out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
 
 } // namespace ag2

@@ -35,6 +35,7 @@ EXPORTS = [
     "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load",
     "ag2_xdrop_extend_batch", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
     "ag2_ctx_stream", "ag2_index_build", "ag2_index_fetch", "ag2_seed_candidates",
+    "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch",
 ]
 
 
@@ -71,6 +72,9 @@ def load() -> C.CDLL:
     L.ag2_index_build.argtypes = [vp, i32, C.c_double, C.c_double]
     L.ag2_index_fetch.argtypes = [vp, vp, vp, vp, vp, i64, C.POINTER(i64), vp, vp, C.POINTER(i64)]
     L.ag2_seed_candidates.argtypes = [vp, i32, i32, vp, vp]
+    L.ag2_extend_upload_from_seeds.argtypes = [vp, i32, C.POINTER(i64)]
+    L.ag2_map_reads.argtypes = [vp, i32, i32, C.POINTER(i64)]
+    L.ag2_map_fetch.argtypes = [vp, vp, vp, vp, i64, C.POINTER(i64)]
     L.ag2_ctx_stream.argtypes = [vp]
     L.ag2_ctx_stream.restype = vp
     _lib = L

@@ -107,6 +107,48 @@ class Mecat2RefDevice:
                     "ag2_seed_candidates")
         return cands, ncand
 
+    def extend_seed_candidates(self, maxc: int = 10):
+        """extend_candidate over every candidate of the last seed_candidates(maxc=...) call, without a host round
+        trip for the candidates.  Returns (records, qaln, saln) like extend()."""
+        n = C.c_int64()
+        self._check(self._L.ag2_extend_upload_from_seeds(self._ctx, maxc, C.byref(n)), "ag2_extend_upload_from_seeds")
+        rec = np.zeros(n.value, dtype=RECORD_DTYPE)
+        if n.value == 0:
+            return rec, np.zeros(0, np.uint8), np.zeros(0, np.uint8)
+        self._n_cand = n.value
+        self.run()
+        used = C.c_int64()
+        self._check(self._L.ag2_extend_fetch(self._ctx, rec.ctypes.data, None, None, 0, C.byref(used)), "ag2_extend_fetch")
+        qa = np.empty(max(used.value, 1), dtype=np.uint8)
+        sa = np.empty(max(used.value, 1), dtype=np.uint8)
+        self._check(self._L.ag2_extend_fetch(self._ctx, rec.ctypes.data, qa.ctypes.data, sa.ctypes.data, qa.size, C.byref(used)),
+                    "ag2_extend_fetch")
+        return rec, qa[:used.value], sa[:used.value]
+
+    def map_reads(self, maxc: int = 10, num_output: int = 1):
+        """reference_mapping()'s loop body for the whole batch (seeding, candidates, extension, rescue, second pass,
+        output choice).  Returns (records, qaln, saln): the records in thread-file order."""
+        n = C.c_int64()
+        self._check(self._L.ag2_map_reads(self._ctx, maxc, num_output, C.byref(n)), "ag2_map_reads")
+        rec = np.zeros(n.value, dtype=RECORD_DTYPE)
+        used = C.c_int64()
+        self._check(self._L.ag2_map_fetch(self._ctx, rec.ctypes.data, None, None, 0, C.byref(used)), "ag2_map_fetch")
+        qa = np.empty(max(used.value, 1), dtype=np.uint8)
+        sa = np.empty(max(used.value, 1), dtype=np.uint8)
+        self._check(self._L.ag2_map_fetch(self._ctx, rec.ctypes.data, qa.ctypes.data, sa.ctypes.data, qa.size, C.byref(used)),
+                    "ag2_map_fetch")
+        return rec, qa[:used.value], sa[:used.value]
+
+    @staticmethod
+    def write_thread_file(path: str, rec, qaln, saln, read_ids) -> None:
+        """output_temp_result (output.cpp:237-251) for every record: the `<wrk>/N.r` text."""
+        with open(path, "wb") as f:
+            for r in rec:
+                o, n = int(r["aln_off"]), int(r["aln_len"])
+                f.write(b"%d\t%c\t%d\t%d\t%d\t%d\t%d\t%d\n" % (read_ids[r["read"]], b"FR"[r["strand"]], r["vscore"], r["qb"], r["qe"],
+                                                              r["qs"], r["sb"], r["se"]))
+                f.write(qaln[o:o + n].tobytes() + b"\n" + saln[o:o + n].tobytes() + b"\n")
+
     # -- extension ---------------------------------------------------------------------------
     @staticmethod
     def make_candidates(read, strand, loc1, loc2, score=None) -> np.ndarray:

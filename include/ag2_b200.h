@@ -124,6 +124,19 @@ typedef struct ag2_seed_candidate {
  * order; maxc is mecat2ref+'s -n (<= 16). */
 int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *out, int32_t *ncand);
 
+/* Makes every seed candidate of the last ag2_seed_candidates call (same maxc) an extension candidate, on the
+ * device (reads in order, canidate_loc[] order inside a read); then ag2_extend_run / ag2_extend_fetch. */
+int ag2_extend_upload_from_seeds(ag2_ctx *ctx, int maxc, int64_t *n_candidates);
+
+/* ---- the whole per-read path: the loop body of reference_mapping() (mecat2ref_impl_large.cpp:776-1316) ----
+ * for every loaded read: seeding, candidate scoring, extension of every candidate, rescue_clipped_align,
+ * output_results, and the second pass for reads without any alignment.  maxc / num_output are mecat2ref+'s
+ * -n / -b.  The records come back in thread-file order (read order, output_results order inside a read):
+ * exactly the sequence of output_temp_result() calls of a `-t 1` run.  ag2_record.read is the index of the read
+ * in the loaded batch.  Needs ag2_index_build. */
+int ag2_map_reads(ag2_ctx *ctx, int maxc, int num_output, int64_t *n_records);
+int ag2_map_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used);
+
 /* The CUDA stream the context launches on (cudaStream_t as void*), for callers that time with
  * their own events. */
 void *ag2_ctx_stream(ag2_ctx *ctx);

@@ -1,0 +1,64 @@
+"""GPU parity of the whole per-read path (ag2_map_reads = reference_mapping()'s loop body):
+the `.r` thread file written from the device results must be byte-identical to the reference binary's
+(committed golden copy) and to the oracle's on other inputs."""
+import lzma
+import os
+
+import numpy as np
+import pytest
+
+from aligngraph2_b200 import synth
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from aligngraph2_b200.mecat2ref import Mecat2RefDevice
+    d = Mecat2RefDevice(0)
+    yield d
+    d.close()
+
+
+def _thread_file(dev, genome: bytes, bases: bytes, offs, path, cbl=200, alpha=0.5, beta=2.0, maxc=10, num_output=1):
+    from oracle.binding import MapperOracle
+    dev.load_reference(np.frombuffer(MapperOracle.upper_ref(genome), dtype=np.uint8))
+    dev.load_reads(bases=np.frombuffer(bases, dtype=np.uint8), offsets=offs)
+    dev.build_index(cbl, alpha, beta)
+    rec, qa, sa = dev.map_reads(maxc, num_output)
+    dev.write_thread_file(path, rec, qa, sa, np.arange(1, len(offs)))
+    return rec
+
+
+def test_stress_fixture_matches_reference_thread_file(dev, tmp_path):
+    z = np.load(os.path.join(GOLDEN, "mapper_stress.npz"))
+    out = str(tmp_path / "1.r")
+    rec = _thread_file(dev, z["genome"].tobytes(), z["bases"].tobytes(), z["offsets"].astype(np.int64), out)
+    golden = lzma.open(os.path.join(GOLDEN, "mapper_stress.r.xz")).read()
+    assert open(out, "rb").read() == golden
+    assert len(rec) == golden.count(b"\n") // 3
+
+
+def test_clr_reads_match_oracle_thread_file(dev, tmp_path):
+    from oracle.binding import MapperOracle
+    d = synth.make_batch_torch(31337, 2_000_000, 400, 10000)
+    genome, bases, offs = d["ref"].numpy().tobytes(), d["bases"].numpy().tobytes(), d["offsets"].numpy()
+    out = str(tmp_path / "gpu.r")
+    _thread_file(dev, genome, bases, offs, out)
+    exp = str(tmp_path / "oracle.r")
+    n, st = MapperOracle().map_batch(genome, bases, offs, np.arange(1, len(offs)), exp)
+    assert n >= 399
+    assert open(out, "rb").read() == open(exp, "rb").read()
+
+
+def test_more_outputs_and_fewer_candidates(dev, tmp_path):
+    # -b 3 -n 5 -z 10000 (AlignGraph2.py really passes -z = its -a default)
+    from oracle.binding import MapperOracle
+    z = np.load(os.path.join(GOLDEN, "mapper_stress.npz"))
+    genome, bases, offs = z["genome"].tobytes(), z["bases"].tobytes(), z["offsets"].astype(np.int64)
+    out = str(tmp_path / "gpu.r")
+    _thread_file(dev, genome, bases, offs, out, cbl=10000, maxc=5, num_output=3)
+    exp = str(tmp_path / "oracle.r")
+    MapperOracle().map_batch(genome, bases, offs, np.arange(1, len(offs)), exp, cbl=10000, maxc=5, num_output=3)
+    assert open(out, "rb").read() == open(exp, "rb").read()
