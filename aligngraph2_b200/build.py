@@ -8,9 +8,25 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "libag2_b200.so")
 SOURCES = [os.path.join(PKG, "csrc", "ag2_b200.cu")]
-HEADERS = [os.path.join(PKG, "csrc", "xdrop_device.cuh"), os.path.join(PKG, "csrc", "xdrop_lane.cuh"), os.path.join(ROOT, "include", "ag2_b200.h")]
+HEADERS = [os.path.join(PKG, "csrc", n) for n in ("xdrop_device.cuh", "xdrop_lane.cuh", "seed_device.cuh", "index_kernels.cuh",
+                                                   "rescue_device.cuh", "map_kernels.cuh")] + [ os.path.join(ROOT, "include", "ag2_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
+
+
+HOST_SRC = os.path.join(PKG, "host", "mecat2ref_main.cpp")
+HOST_BIN = os.path.join(PKG, "bin", "mecat2ref")
+
+
+def build_host(force: bool = False) -> str:
+    """The drop-in `mecat2ref` executable (C++ host over the C ABI)."""
+    if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) > max(os.path.getmtime(HOST_SRC), os.path.getmtime(SO)):
+        return HOST_BIN
+    os.makedirs(os.path.dirname(HOST_BIN), exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-O2", "-std=c++17", "-Wall", "-o", HOST_BIN, HOST_SRC, "-L" + PKG, "-lag2_b200",
+                    "-Wl,-rpath,$ORIGIN/.."], check=True, cwd=ROOT)
+    return HOST_BIN
 
 
 def stale() -> bool:

@@ -483,7 +483,6 @@ int ag2_reads_load(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t
         }
         ctx->read_prefix_len = offs[k];
     }
-    ctx->votes_ready = false;
     return AG2_OK;
 }
 

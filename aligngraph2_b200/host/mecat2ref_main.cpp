@@ -1,0 +1,639 @@
+// mecat2ref_main.cpp -- drop-in replacement of the mecat2ref+ executable: same argv, same files,
+// same exit codes; the per-read work runs on the GPU through the C ABI of include/ag2_b200.h.
+//
+// Mirrors mecat_plus/MECAT-master_1/src/mecat2ref/mecat2ref.cpp:
+//   param_read_t :98-219 (getopt string, checks, -b clamped to -n, working dir created), firsttask :398-434
+//   (reads -> <wrk>/0.fq, reference -> <wrk>/ref.fq, ./config.txt), main :951-1016, result_combine :523-599,
+//   polish_result :625-867, get_chr_id :444-462, output_query_results :499-520; and of
+//   mecat2ref_impl_large.cpp: creat_ref_index's FASTA reading and chrindex.txt :421-450, load_fastq's batching
+//   :1965-1991, the timing lines of config.txt :2017-2033,2133-2138.
+//
+// Differences that are deliberate and visible:
+//   * -t is accepted and recorded, but the mapping always behaves like `-t 1`: all records go to <wrk>/1.r in read
+//     order (2.r..N.r and refN.r are created empty).  The reference's own per-read results do not depend on -t
+//     (SURVEY F6), only their order and, through polish_result's "last group of every thread file is not
+//     filtered" rule (:854), which groups escape the filter -- with one thread file that is deterministic.
+//   * -x is parsed and ignored, as in the reference.
+//   * no CPU fallback: without a usable GPU the program exits 1 (AlignGraph2.py:280-296 then falls back to the
+//     vanilla mecat2ref exactly as it does for any mecat2ref+ failure).
+// AG2_SKIP_MAP=1 in the environment skips the GPU stage and reuses the thread files already in <wrk> (used by
+// the CPU-side tests of the file handling, result_combine and polish_result).
+#include "../../include/ag2_b200.h"
+
+#include <dirent.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <unistd.h>
+
+#include <cassert>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+constexpr int kSVM = 100000;              // reads per batch (mecat2ref_defs.h:27)
+constexpr long kMAXSTR = 1000000000L;     // characters per batch (:25)
+
+struct Options {
+    const char *reads = nullptr, *reference = nullptr, *wrk_dir = nullptr, *output = nullptr, *refoutput = nullptr;
+    int num_cores = 1, num_candidates = 10, num_output = 10, output_format = 0, tech = 0, block = 200;
+    double alpha = 0.5, beta = 2.0, delta = 0.9;
+};
+
+const char *prog_name = "mecat2ref";
+
+void print_usage()
+{
+    fprintf(stderr, "\n\nusage:\n%s [-d reads] [-r reference] [-o output][-p refoutput] [-w working dir] [-t threads]\n\n", prog_name);
+    fprintf(stderr, "options:\n-d <string>\treads file name\n-r <string>\treference file name\n-o <string>\toutput file name\n");
+    fprintf(stderr, "-p <string>\trefoutput file name\n-w <string>\tworking folder name, will be created if not exist\n");
+    fprintf(stderr, "-t <integer>\tnumber of cput threads\n\t\tdefault: 1\n-n <integer>\tnumber of of candidates for gap extension\n\t\tdefault: 10\n");
+    fprintf(stderr, "-b <integer>\toutput the best b alignments\n\t\tdefault: 10\n-m <0/1/2>\toutput format: 0 = ref, 1 = m4, 2 = sam\n\t\tdefault: 0\n");
+    fprintf(stderr, "-x <0/1>\tsequencing technology: 0 = pacbio, 1 = nanopore\n\t\tdefault: 0\n");
+    fprintf(stderr, "-l <real>\tlower bound of k-mer scoring function for mecat2ref+\n\t\tdefault: 0.5\n");
+    fprintf(stderr, "-u <real>\tupper bound of k-mer scoring function for mecat2ref+\n\t\tdefault: 2.0\n");
+    fprintf(stderr, "-z <integer>\tsize of similar genome blocks for mecat2ref+\n\t\tdefault: 200\n-y <integer>\tthreshold for alignment scoring\n\t\tdefault: 0.9\n");
+}
+
+int parse_options(int argc, char **argv, Options &o)
+{
+    opterr = 0;
+    int c;
+    while ((c = getopt(argc, argv, "d:r:w:o:p:t:n:b:m:x:l:u:z:y:")) != -1) {
+        switch (c) {
+        case 'd': o.reads = optarg; break;
+        case 'r': o.reference = optarg; break;
+        case 'w': o.wrk_dir = optarg; break;
+        case 'o': o.output = optarg; break;
+        case 'p': o.refoutput = optarg; break;
+        case 't': o.num_cores = atoi(optarg); break;
+        case 'n': o.num_candidates = atoi(optarg); break;
+        case 'b': o.num_output = atoi(optarg); break;
+        case 'm': o.output_format = atoi(optarg); break;
+        case 'x':
+            if (optarg[0] == '0') o.tech = 0;
+            else if (optarg[0] == '1') o.tech = 1;
+            else { fprintf(stderr, "Invalid argument to option 'x': %s\n", optarg); abort(); }
+            break;
+        case 'l': o.alpha = atof(optarg); break;
+        case 'u': o.beta = atof(optarg); break;
+        case 'z': o.block = atoi(optarg); break;
+        case 'y': o.delta = atof(optarg); break;
+        case ':': fprintf(stderr, "Error: unrecogised option '%c'\n", (char)optopt); return -1;
+        case '?': fprintf(stderr, "Error: argument to option '%c' is missing!\n", (char)optopt); return -1;
+        }
+    }
+    const char *msg = nullptr;
+    if (!o.reads) msg = "dataset must be specified";
+    else if (!o.reference) msg = "reference must be specified";
+    else if (!o.output) msg = "output must be specified";
+    else if (!o.refoutput) msg = "refoutput must be specified";
+    else if (!o.wrk_dir) msg = "working directory must be specified";
+    else if (o.num_cores < 1) msg = "cpu cores must be > 0";
+    else if (o.num_candidates < 1) msg = "candidates must be > 0";
+    else if (o.num_output < 1) msg = "output alignments must be > 0";
+    else if (o.num_candidates > 16) msg = "candidates must be <= 16";
+    if (msg) {
+        fprintf(stderr, "Error: %s\n", msg);
+        return -1;
+    }
+    if (o.num_output > o.num_candidates) {
+        fprintf(stderr, "warning: number of output (%d) is greater than number of candidates (%d), we reset it to %d", o.num_output,
+                o.num_candidates, o.num_candidates);
+        o.num_output = o.num_candidates;
+    }
+    DIR *d = opendir(o.wrk_dir);
+    if (!d) {
+        if (mkdir(o.wrk_dir, S_IRWXU) == -1) {
+            fprintf(stderr, "Fail to create folder %s!\n", o.wrk_dir);
+            return -1;
+        }
+    } else {
+        closedir(d);
+    }
+    return 1;
+}
+
+// chang_fastqfile / change_ref_fq (mecat2ref.cpp:272-395): FASTA -> ids 0.., FASTQ (4 lines) -> ids 1..
+int convert_to_fq(const char *in_path, const std::string &out_path)
+{
+    FILE *fp = fopen(in_path, "r");
+    if (!fp) { fprintf(stderr, "failed to open file %s for reading.\n", in_path); exit(1); }
+    FILE *ot = fopen(out_path.c_str(), "w");
+    if (!ot) { fprintf(stderr, "failed to open file %s for writing.\n", out_path.c_str()); exit(1); }
+    std::vector<char> obuf(1 << 24);
+    setvbuf(ot, obuf.data(), _IOFBF, obuf.size());
+    int kk = 0;
+    int ch = getc(fp);
+    std::string one;
+    if (ch == '>') {
+        for (; ch != EOF; ch = getc(fp)) {
+            if (ch == '>') {
+                while ((ch = getc(fp)) != EOF && ch != '\n') {}
+                if (ch == '\n') ungetc(ch, fp);
+                if (kk > 0) fprintf(ot, "%d\t%d\t%s\n", kk - 1, (int)one.size(), one.c_str());
+                one.clear();
+                kk++;
+            } else if (ch != '\n' && ch != '\r') {
+                one.push_back((char)ch);
+            }
+        }
+        fprintf(ot, "%d\t%d\t%s\n", kk - 1, (int)one.size(), one.c_str());
+    } else {
+        fseek(fp, 0L, SEEK_SET);
+        char *line = nullptr;
+        size_t cap = 0;
+        // name line, sequence token, '+' line, quality token (the reference's fscanf("%[^\n]s") / fscanf("%s\n") pairs)
+        for (;;) {
+            if (getline(&line, &cap, fp) < 0) break;             // @name
+            ssize_t n = getline(&line, &cap, fp);                 // sequence
+            if (n < 0) break;
+            std::string seq(line, (size_t)n);
+            while (!seq.empty() && (seq.back() == '\n' || seq.back() == '\r')) seq.pop_back();
+            if (getline(&line, &cap, fp) < 0) break;             // +
+            if (getline(&line, &cap, fp) < 0) break;             // quality
+            fprintf(ot, "%d\t%d\t%s\n", ++kk, (int)seq.size(), seq.c_str());
+        }
+        free(line);
+    }
+    fclose(fp);
+    fclose(ot);
+    return kk;
+}
+
+struct ChrInfo {
+    long start, size;
+    char name[64];
+};
+
+// creat_ref_index's FASTA reading (impl_large.cpp:421-450): concatenated sequence, upper-cased above 'Z',
+// <wrk>/chrindex.txt
+void load_reference(const char *path, const std::string &wrk, std::string &seq)
+{
+    FILE *fasta = fopen(path, "r");
+    if (!fasta) { fprintf(stderr, "failed to open file %s for reading.\n", path); exit(1); }
+    FILE *idx = fopen((wrk + "/chrindex.txt").c_str(), "w");
+    if (!idx) { fprintf(stderr, "failed to open %s/chrindex.txt for writing.\n", wrk.c_str()); exit(1); }
+    long rsize = 0, count = 0;
+    seq.clear();
+    char nameall[1 << 16];
+    for (int ch = getc(fasta); ch != EOF; ch = getc(fasta)) {
+        if (ch == '>') {
+            if (fscanf(fasta, "%65535[^\n]", nameall) != 1) nameall[0] = 0;
+            if (rsize) fprintf(idx, "%ld\n", rsize);
+            rsize = 0;
+            size_t i;
+            for (i = 0; i < strlen(nameall); i++)
+                if (nameall[i] == ' ' || nameall[i] == '\t') break;
+            nameall[i] = '\0';
+            fprintf(idx, "%ld\t%s\t", count, nameall);
+        } else if (ch != '\n' && ch != '\r') {
+            if (ch > 'Z') ch = toupper(ch);
+            seq.push_back((char)ch);
+            ++count;
+            ++rsize;
+        }
+    }
+    fclose(fasta);
+    fprintf(idx, "%ld\n", rsize);
+    fprintf(idx, "%ld\t%s\n", count, "FileEnd");
+    fclose(idx);
+}
+
+std::vector<ChrInfo> read_chrindex(const std::string &wrk)
+{
+    const std::string path = wrk + "/chrindex.txt";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) { fprintf(stderr, "failed to open file %s for reading.\n", path.c_str()); abort(); }
+    char buffer[1024];
+    int num_chr = 0;
+    while (fgets(buffer, 1024, f)) ++num_chr;
+    --num_chr;
+    fseek(f, 0L, SEEK_SET);
+    std::vector<ChrInfo> v((size_t)(num_chr > 0 ? num_chr : 0));
+    for (int i = 0; i < num_chr; ++i) {
+        const int flag = fscanf(f, "%ld\t%63s\t%ld\n", &v[i].start, v[i].name, &v[i].size);
+        assert(flag == 3);
+        (void)flag;
+    }
+    fclose(f);
+    return v;
+}
+
+int get_chr_id(const std::vector<ChrInfo> &chr, long offset) // mecat2ref.cpp:444-462
+{
+    const int num_chr = (int)chr.size();
+    int left = 0, right = num_chr, mid = 0;
+    while (left < right) {
+        mid = (left + right) >> 1;
+        if (offset >= chr[mid].start) {
+            if (mid == num_chr - 1) break;
+            if (offset < chr[mid + 1].start) break;
+            left = mid + 1;
+        } else {
+            right = mid;
+        }
+    }
+    return mid;
+}
+
+struct TempResult {
+    int read_id = 0, vscore = 0, qb = 0, qe = 0, qs = 0;
+    char read_dir = 0;
+    long sb = 0, se = 0;
+    std::string qmap, smap;
+};
+
+bool load_temp_result(TempResult &r, FILE *in, char *&line, size_t &cap) // output.cpp:270-289
+{
+    if (getline(&line, &cap, in) < 0) return false;
+    if (sscanf(line, "%d\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld", &r.read_id, &r.read_dir, &r.vscore, &r.qb, &r.qe, &r.qs, &r.sb, &r.se) != 8) return false;
+    ssize_t n = getline(&line, &cap, in);
+    if (n < 0) return false;
+    r.qmap.assign(line, (size_t)n);
+    while (!r.qmap.empty() && r.qmap.back() == '\n') r.qmap.pop_back();
+    n = getline(&line, &cap, in);
+    if (n < 0) return false;
+    r.smap.assign(line, (size_t)n);
+    while (!r.smap.empty() && r.smap.back() == '\n') r.smap.pop_back();
+    return true;
+}
+
+void output_cigar(int qstart, int qend, int qsize, const std::string &qmap, const std::string &smap, FILE *out)
+{
+    if (qstart) fprintf(out, "%dH", qstart);
+    int i = 0, j;
+    const int n = (int)qmap.size();
+    while (i < n) {
+        if (qmap[i] == '-') {
+            j = i + 1;
+            while (j < n && qmap[j] == '-') ++j;
+            fprintf(out, "%dD", j - i);
+        } else if (smap[i] == '-') {
+            j = i + 1;
+            while (j < n && smap[j] == '-') ++j;
+            fprintf(out, "%dI", j - i);
+        } else {
+            j = i + 1;
+            while (j < n && qmap[j] != '-' && smap[j] != '-') ++j;
+            fprintf(out, "%dM", j - i);
+        }
+        i = j;
+    }
+    if (qend != qsize) fprintf(out, "%dH", qsize - qend);
+}
+
+// output_one_result (output.cpp:6-43 ref, :45-88 m4, :150-186 sam)
+void output_one(const TempResult &r, const ChrInfo &c, int format, FILE *out)
+{
+    const long sstart = r.sb - c.start, send = r.se - c.start;
+    int qb = r.qb, qe = r.qe;
+    if (format == 0) {
+        if (r.read_dir == 'R') {
+            qb = r.qs - r.qe;
+            qe = r.qs - r.qb;
+        }
+        fprintf(out, "%d\t%s\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld\t%ld\n%s\n%s\n", r.read_id, c.name, r.read_dir == 'R' ? 'R' : 'F', r.vscore, qb, qe,
+                r.qs, sstart, send, c.size, r.qmap.c_str(), r.smap.c_str());
+    } else if (format == 1) {
+        if (r.read_dir == 'R') {
+            qb = r.qs - r.qe;
+            qe = r.qs - r.qb;
+        }
+        double ident = 0.0;
+        const int n = (int)r.qmap.size();
+        for (int i = 0; i < n; ++i)
+            if (r.qmap[i] == r.smap[i]) ident += 1.0;
+        ident = ident / n;
+        ident *= 100.0;
+        fprintf(out, "%d\t%s\t%.4f\t%d\t%d\t%d\t%d\t%d\t0\t%ld\t%ld\t%ld\n", r.read_id, c.name, ident, r.vscore, r.read_dir == 'F' ? 0 : 1, qb,
+                qe, r.qs, sstart, send, c.size);
+    } else if (format == 2) {
+        fprintf(out, "%d\t%d\t%s\t%ld\t255\t", r.read_id, r.read_dir == 'R' ? 0x10 : 0, c.name, sstart + 1);
+        output_cigar(r.qb, r.qe, r.qs, r.qmap, r.smap, out);
+        fprintf(out, "\t*\t0\t0\t");
+        for (char ch : r.qmap)
+            if (ch != '-') fputc(ch, out);
+        fprintf(out, "\t*\n");
+    }
+}
+
+void sam_header(const std::vector<ChrInfo> &chr, int argc, char **argv, FILE *out)
+{
+    fprintf(out, "@HD\tVN:1.4\tSO:unknown\tGO:query\n");
+    for (const ChrInfo &c : chr) fprintf(out, "@SQ\tSN:%s\tLN:%ld\n", c.name, c.size);
+    fprintf(out, "@PG\tID:0\tVN:0.0.1\tCL:");
+    for (int i = 0; i < argc; ++i) fprintf(out, "%s ", argv[i]);
+    fprintf(out, "\tPN:mecat2ref\n");
+}
+
+void output_query_results(const std::vector<ChrInfo> &chr, const std::vector<const TempResult *> &p, int num_output, int format, FILE *out)
+{
+    int cnt = 0;
+    for (const TempResult *r : p) { // mecat2ref.cpp:499-520
+        output_one(*r, chr[(size_t)get_chr_id(chr, r->sb)], format, out);
+        if (++cnt == num_output) break;
+    }
+}
+
+// result_combine (mecat2ref.cpp:523-599): thread files -> -o, grouped by read id, first num_output of a group
+void result_combine(const Options &o, const std::vector<ChrInfo> &chr, int argc, char **argv)
+{
+    fprintf(stderr, "output file name: %s\n", o.output);
+    FILE *out = fopen(o.output, "w");
+    if (!out) { fprintf(stderr, "failed to open file %s for writing.\n", o.output); abort(); }
+    if (o.output_format == 2) sam_header(chr, argc, argv, out);
+    char *line = nullptr;
+    size_t cap = 0;
+    for (int i = 1; i <= o.num_cores; ++i) {
+        const std::string path = std::string(o.wrk_dir) + "/" + std::to_string(i) + ".r";
+        FILE *f = fopen(path.c_str(), "r");
+        if (!f) { fprintf(stderr, "failed to open file %s for reading.\n", path.c_str()); abort(); }
+        std::vector<TempResult> group;
+        TempResult t;
+        bool ok = load_temp_result(t, f, line, cap);
+        int last = 0;
+        if (ok) {
+            group.push_back(t);
+            last = t.read_id;
+        }
+        auto flush = [&]() {
+            std::vector<const TempResult *> p;
+            for (const TempResult &g : group) p.push_back(&g);
+            output_query_results(chr, p, o.num_output, o.output_format, out);
+            group.clear();
+        };
+        while (ok) {
+            ok = load_temp_result(t, f, line, cap);
+            if (!ok) break;
+            if (t.read_id != last) flush();
+            last = t.read_id;
+            group.push_back(t);
+        }
+        if (!group.empty()) flush();
+        fclose(f);
+    }
+    free(line);
+    fclose(out);
+}
+
+// polish_result (mecat2ref.cpp:625-867): thread files -> -p with the co-linearity vote per read group.  The last
+// group of every thread file is written unfiltered (:854), as in the reference.
+void polish_result(const Options &o, const std::vector<ChrInfo> &chr, int argc, char **argv)
+{
+    fprintf(stderr, "output file name: %s\n", o.refoutput);
+    FILE *out = fopen(o.refoutput, "w");
+    if (!out) { fprintf(stderr, "failed to open file %s for writing.\n", o.refoutput); abort(); }
+    if (o.output_format == 2) sam_header(chr, argc, argv, out);
+    char *line = nullptr;
+    size_t cap = 0;
+    for (int ww = 1; ww <= o.num_cores; ww++) {
+        const std::string path = std::string(o.wrk_dir) + "/" + std::to_string(ww) + ".r";
+        FILE *f = fopen(path.c_str(), "r");
+        if (!f) { fprintf(stderr, "failed to open file %s for reading\n", path.c_str()); abort(); }
+        std::vector<TempResult> pptr;
+        TempResult t;
+        bool rok = load_temp_result(t, f, line, cap);
+        int last_id = 0;
+        if (rok) {
+            pptr.push_back(t);
+            last_id = t.read_id;
+        }
+        int vote[16] = {0}, mark[16] = {0};
+        int flag3 = 0, flag4 = 0;
+        while (rok) {
+            rok = load_temp_result(t, f, line, cap);
+            if (!rok) break;
+            if (t.read_id != last_id) {
+                const int num_results = (int)pptr.size();
+                std::vector<const TempResult *> outp;
+                for (int i = 0; i < num_results; i++)
+                    for (int j = i + 1; j < num_results; j++) {
+                        const int sid = get_chr_id(chr, pptr[i].sb), sid2 = get_chr_id(chr, pptr[j].sb);
+                        if (sid == sid2 && labs(pptr[j].qb - pptr[i].qb) > 1000 && labs(pptr[i].qe - pptr[j].qe) > 1000 &&
+                            pptr[i].sb != pptr[j].sb &&
+                            fabs((double)((pptr[i].qb - pptr[j].qb) / (pptr[i].sb - pptr[j].sb) - 1)) < o.delta) {
+                            vote[i]++;
+                            vote[j]++;
+                            mark[i] = 1;
+                            mark[j] = 1;
+                        }
+                    }
+                for (int k = 0; k < num_results; k++) {
+                    int delete_flag = 0;
+                    if (mark[k] == 0) outp.push_back(&pptr[k]);
+                    if (mark[k] == 1) {
+                        int maxi_vote = vote[k], maxi = k;
+                        const int sid = get_chr_id(chr, pptr[k].sb);
+                        for (int p = k + 1; p < num_results; p++) {
+                            if (sid != get_chr_id(chr, pptr[p].sb)) continue;
+                            const int lk = pptr[k].qe - pptr[k].qb, lp = pptr[p].qe - pptr[p].qb;
+                            if (labs(pptr[p].qb - pptr[k].qb) < 1500) {
+                                mark[p] = 2;
+                                delete_flag = 1;
+                                if (labs(lk - lp) > 3000) {
+                                    maxi = lk > lp ? k : p;
+                                } else {
+                                    if (maxi_vote > vote[p]) maxi = k;
+                                    if (maxi_vote == vote[p]) maxi = lk > lp ? k : p;
+                                    if (maxi_vote < vote[p]) {
+                                        maxi = p;
+                                        maxi_vote = vote[p];
+                                    }
+                                }
+                            } else {
+                                for (int q = p + 1; q < num_results; q++)
+                                    if (sid == get_chr_id(chr, pptr[q].sb)) {
+                                        flag3 = 1;
+                                        break;
+                                    }
+                                if (flag3 == 0) outp.push_back(&pptr[k]);
+                                flag3 = 0;
+                            }
+                        }
+                        if (delete_flag == 1) outp.push_back(&pptr[maxi]);
+                        for (int w = k + 1; w < num_results; w++)
+                            if (sid == get_chr_id(chr, pptr[w].sb)) {
+                                flag4 = 1;
+                                break;
+                            }
+                        if (flag4 == 0) outp.push_back(&pptr[k]);
+                        flag4 = 0;
+                    }
+                }
+                output_query_results(chr, outp, o.num_output, o.output_format, out);
+                pptr.clear();
+                for (int i = 0; i < 16; i++) mark[i] = vote[i] = 0;
+            }
+            last_id = t.read_id;
+            pptr.push_back(t);
+        }
+        if (!pptr.empty()) {
+            std::vector<const TempResult *> p;
+            for (const TempResult &g : pptr) p.push_back(&g);
+            output_query_results(chr, p, o.num_output, o.output_format, out);
+        }
+        fclose(f);
+    }
+    free(line);
+    fclose(out);
+}
+
+double now_sec()
+{
+    struct timeval t;
+    gettimeofday(&t, nullptr);
+    return t.tv_sec + t.tv_usec * 1e-6;
+}
+
+void die_ag2(ag2_ctx *ctx, const char *what, int rc)
+{
+    fprintf(stderr, "mecat2ref (aligngraph2_b200): %s failed (%d): %s\n", what, rc, ag2_last_error(ctx));
+    exit(1);
+}
+
+// the mapping part of meap_ref_impl_large (:1994-2149) on the GPU; returns seconds {read index, ref index, mapping}
+void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
+{
+    ag2_ctx *ctx = nullptr;
+    int rc = ag2_ctx_create(0, &ctx);
+    if (rc != AG2_OK) {
+        fprintf(stderr, "mecat2ref (aligngraph2_b200): no usable CUDA device (%d); there is no CPU path\n", rc);
+        exit(1);
+    }
+    double t0 = now_sec();
+    if ((rc = ag2_ref_load(ctx, ref_seq.data(), (int64_t)ref_seq.size())) != AG2_OK) die_ag2(ctx, "ag2_ref_load", rc);
+    secs[1] = now_sec() - t0;
+    const std::string wrk = o.wrk_dir;
+    FILE *fq = fopen((wrk + "/0.fq").c_str(), "r");
+    if (!fq) { fprintf(stderr, "failed to open %s/0.fq\n", wrk.c_str()); exit(1); }
+    FILE *out = fopen((wrk + "/1.r").c_str(), "w");
+    if (!out) { fprintf(stderr, "failed to open %s/1.r for writing\n", wrk.c_str()); exit(1); }
+    std::vector<char> obuf(1 << 24);
+    setvbuf(out, obuf.data(), _IOFBF, obuf.size());
+    for (int t = 2; t <= o.num_cores; ++t) fclose(fopen((wrk + "/" + std::to_string(t) + ".r").c_str(), "w"));
+    for (int t = 1; t <= o.num_cores; ++t) fclose(fopen((wrk + "/ref" + std::to_string(t) + ".r").c_str(), "w"));
+
+    char *line = nullptr;
+    size_t cap = 0;
+    bool first_batch = true, more = true;
+    secs[0] = secs[2] = 0;
+    std::vector<ag2_record> rec;
+    std::vector<char> qaln, saln;
+    while (more) {
+        // load_fastq (:1965-1991): up to SVM reads / MAXSTR characters, plus the record that ended the loop
+        std::string bases;
+        std::vector<int64_t> offs(1, 0);
+        std::vector<int> ids;
+        long sum = 0;
+        more = false;
+        for (;;) {
+            const ssize_t n = getline(&line, &cap, fq);
+            if (n < 0) break;
+            int readno = 0, readlen = 0;
+            int consumed = 0;
+            if (sscanf(line, "%d\t%d\t%n", &readno, &readlen, &consumed) < 2) continue;
+            size_t len = (size_t)n - (size_t)consumed;
+            while (len && (line[consumed + len - 1] == '\n' || line[consumed + len - 1] == '\r')) --len;
+            const bool within = (int)ids.size() < kSVM && sum < kMAXSTR;
+            bases.append(line + consumed, len);
+            offs.push_back((int64_t)bases.size());
+            ids.push_back(readno);
+            sum += (long)len + 1;
+            if (!within) {
+                more = true;
+                break;
+            }
+        }
+        if (ids.empty()) break;
+        t0 = now_sec();
+        if ((rc = ag2_reads_load(ctx, bases.data(), offs.data(), (int64_t)ids.size())) != AG2_OK) die_ag2(ctx, "ag2_reads_load", rc);
+        if (first_batch) {
+            // build_read_index uses the first <= 100 000 reads of the file; the index is built once (:2017-2033)
+            const double ti = now_sec();
+            if ((rc = ag2_index_build(ctx, o.block, o.alpha, o.beta)) != AG2_OK) die_ag2(ctx, "ag2_index_build", rc);
+            secs[0] = now_sec() - ti;
+            first_batch = false;
+            t0 = now_sec();
+        }
+        int64_t n_rec = 0, used = 0;
+        if ((rc = ag2_map_reads(ctx, o.num_candidates, o.num_output, &n_rec)) != AG2_OK) die_ag2(ctx, "ag2_map_reads", rc);
+        rec.resize((size_t)n_rec + 1);
+        if ((rc = ag2_map_fetch(ctx, rec.data(), nullptr, nullptr, 0, &used)) != AG2_OK) die_ag2(ctx, "ag2_map_fetch", rc);
+        qaln.resize((size_t)used + 1);
+        saln.resize((size_t)used + 1);
+        if ((rc = ag2_map_fetch(ctx, rec.data(), qaln.data(), saln.data(), used, &used)) != AG2_OK) die_ag2(ctx, "ag2_map_fetch", rc);
+        secs[2] += now_sec() - t0;
+        for (int64_t k = 0; k < n_rec; ++k) { // output_temp_result (output.cpp:237-251)
+            const ag2_record &r = rec[(size_t)k];
+            fprintf(out, "%d\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld\n", ids[(size_t)r.read], r.strand ? 'R' : 'F', r.vscore, r.qb, r.qe, r.qs, (long)r.sb,
+                    (long)r.se);
+            fwrite(qaln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
+            fputc('\n', out);
+            fwrite(saln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
+            fputc('\n', out);
+        }
+    }
+    free(line);
+    fclose(fq);
+    fclose(out);
+    ag2_ctx_destroy(ctx);
+}
+
+} // namespace
+
+int main(int argc, char **argv)
+{
+    prog_name = argv[0];
+    const double t_start = now_sec();
+    Options o;
+    if (parse_options(argc, argv, o) == -1) {
+        print_usage();
+        return 1;
+    }
+    const std::string wrk = o.wrk_dir;
+    const int readcount = convert_to_fq(o.reads, wrk + "/0.fq");
+    const int refcount = convert_to_fq(o.reference, wrk + "/ref.fq");
+    {
+        FILE *cfg = fopen("config.txt", "w");
+        if (!cfg) { fprintf(stderr, "failed to open config.txt for writing\n"); return 1; }
+        fprintf(cfg, "%s\n%s\n%s\n%s\n%s\n%d\t%d\n%d\n", o.wrk_dir, o.reference, o.reads, o.output, o.refoutput, o.num_cores, readcount, refcount);
+        fclose(cfg);
+    }
+    printf("first task is sucess\n");
+    double secs[3] = {0, 0, 0};
+    {
+        std::string ref_seq;
+        const double t0 = now_sec();
+        load_reference(o.reference, wrk, ref_seq);
+        const double t_load = now_sec() - t0;
+        if (!getenv("AG2_SKIP_MAP")) map_on_gpu(o, ref_seq, secs);
+        secs[1] += t_load;
+    }
+    {
+        FILE *cfg = fopen("config.txt", "a");
+        fprintf(cfg, "The Building read Index Time: %f sec\n", secs[0]);
+        fprintf(cfg, "The Building  Reference  Index Time: %f sec\n", secs[1]);
+        fprintf(cfg, "The Mapping Time: %f sec\n", secs[2]);
+        fclose(cfg);
+    }
+    const std::vector<ChrInfo> chr = read_chrindex(wrk);
+    result_combine(o, chr, argc, argv);
+    polish_result(o, chr, argc, argv);
+    {
+        FILE *cfg = fopen("config.txt", "a");
+        fprintf(cfg, "The total Time : %f sec\n", now_sec() - t_start);
+        fclose(cfg);
+    }
+    const std::string cmd = std::string("cp -r config.txt \"") + o.refoutput + ".config\"";
+    const int st = system(cmd.c_str());
+    if (st != 0) {
+        fprintf(stderr, "[main, %u] system() error. Error code is %d.\n", __LINE__, st);
+        return 1;
+    }
+    return EXIT_SUCCESS;
+}

@@ -318,6 +318,21 @@ def main():
                "h2d_bytes_per_step": int(total_bases + h_off.nbytes + h_cand.nbytes),
                "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used), "ms_per_step": float(t2.item()) / args.steps}
 
+    # ---- the stages in front of the extension on the same batch (not part of the headline metric) ----
+    stages = None
+    if rank == 0:
+        def timed(fn):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) * 1e3
+        dev.load_reads(bases=bases_np, offsets=h_off)
+        dev.build_index(200, 0.5, 2.0)
+        stages = {"index_build_ms": timed(lambda: dev.build_index(200, 0.5, 2.0)),
+                  "seed_candidates_ms": timed(lambda: dev.seed_candidates(0, 10)),
+                  "note": "ag2_index_build (A2-A4) and ag2_seed_candidates (A5-A7, incl. the D2H of the candidates) on the bench batch"}
+
     # ---- roofline of the dominant kernel (xdrop_chains_kernel) ----
     peak, peak_src = peaks()
     cbar = st["cells"] / max(1, st["aligned"])
@@ -341,7 +356,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-                "e2e": e2e, "gpu_launches": int(st["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": e2e, "gpu_launches": int(st["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
                 "stats": {k: st[k] for k in ("cells", "rows", "blocks", "aligned", "columns", "wide_chains", "interior")}}
         print(json.dumps(line))
     dev.close()

@@ -68,3 +68,14 @@ def random_block(rng):
         B = rng.integers(0, 4, size=int(rng.integers(1, 719))).astype(np.uint8)
     B = B[:718]
     return A, B
+
+
+def golden_ref_outputs():
+    """{name: bytes} of what the unmodified reference binary wrote for the stress fixture (gen_mapper_golden.py)."""
+    import lzma
+    import tarfile
+    out = {}
+    with lzma.open(os.path.join(GOLDEN, "mapper_stress_ref.tar.xz")) as xz, tarfile.open(fileobj=xz) as tar:
+        for m in tar.getmembers():
+            out[m.name] = tar.extractfile(m).read()
+    return out

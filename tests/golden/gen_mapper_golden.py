@@ -3,17 +3,22 @@ rescue, second pass) and its golden `.r` thread file from the UNMODIFIED referen
 
   python tests/golden/gen_mapper_golden.py            # needs oracle/_ref/mecat2ref (build container)
 
-Writes tests/golden/mapper_stress.npz (inputs) and tests/golden/mapper_stress.r.xz (what
-`mecat2ref -t 1 ... -z 200` left in <wrk>/1.r).  The inputs are built to reach the branches a uniform
+Writes tests/golden/mapper_stress.npz (inputs) and tests/golden/mapper_stress_ref.tar.xz: what
+`mecat2ref -t 1 ... -z 200` wrote -- <wrk>/1.r (thread file), <wrk>/chrindex.txt, the -o and -p outputs -- plus
+the sha256 of <wrk>/0.fq and <wrk>/ref.fq (mapper_stress_ref.json).  The inputs are built to reach the branches a uniform
 random genome never does: k-mer buckets above the 128 mask, similarity votes != 1, more than 20 seeds
 per 1000-bp block (insert_loc), several candidates per read, chimeric reads (rescue_clipped_align),
 unalignable reads (second pass), short reads, N and lower-case bases.
 """
+import hashlib
+import io
+import json
 import lzma
 import os
 import shutil
 import subprocess
 import sys
+import tarfile
 import tempfile
 
 import numpy as np
@@ -114,12 +119,22 @@ def run_reference(d, threads=1):
     return open(os.path.join(d, "wrk", "1.r"), "rb").read()
 
 
+REF_FILES = ("wrk/1.r", "wrk/chrindex.txt", "o.txt", "p.txt")
+
+
+def collect_reference_outputs(d):
+    files = {n: open(os.path.join(d, n), "rb").read() for n in REF_FILES}
+    hashes = {n: hashlib.sha256(open(os.path.join(d, n), "rb").read()).hexdigest() for n in ("wrk/0.fq", "wrk/ref.fq")}
+    return files, hashes
+
+
 if __name__ == "__main__":
     chroms, reads = build()
     d = tempfile.mkdtemp(prefix="m2r_golden_")
     try:
         write_inputs(d, chroms, reads)
         r = run_reference(d)
+        files, hashes = collect_reference_outputs(d)
     finally:
         keep = os.environ.get("KEEP")
         if not keep:
@@ -133,6 +148,11 @@ if __name__ == "__main__":
                         chrom_lens=np.array([len(s) for _, s in chroms]),
                         genome=np.frombuffer(b"".join(s for _, s in chroms), dtype=np.uint8),
                         bases=np.frombuffer(b"".join(reads), dtype=np.uint8), offsets=offs)
-    with lzma.open(os.path.join(HERE, "mapper_stress.r.xz"), "wb", preset=9) as f:
-        f.write(r)
+    with lzma.open(os.path.join(HERE, "mapper_stress_ref.tar.xz"), "wb", preset=9 | lzma.PRESET_EXTREME) as xz:
+        with tarfile.open(fileobj=xz, mode="w") as tar:
+            for name in REF_FILES:
+                ti = tarfile.TarInfo(name)
+                ti.size = len(files[name])
+                tar.addfile(ti, io.BytesIO(files[name]))
+    json.dump(hashes, open(os.path.join(HERE, "mapper_stress_ref.json"), "w"), indent=1)
     print("records:", r.count(b"\n") // 3, "bytes:", len(r))

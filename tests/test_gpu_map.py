@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from aligngraph2_b200 import synth
-from conftest import GOLDEN
+from conftest import GOLDEN, golden_ref_outputs
 
 pytestmark = pytest.mark.gpu
 
@@ -35,7 +35,7 @@ def test_stress_fixture_matches_reference_thread_file(dev, tmp_path):
     z = np.load(os.path.join(GOLDEN, "mapper_stress.npz"))
     out = str(tmp_path / "1.r")
     rec = _thread_file(dev, z["genome"].tobytes(), z["bases"].tobytes(), z["offsets"].astype(np.int64), out)
-    golden = lzma.open(os.path.join(GOLDEN, "mapper_stress.r.xz")).read()
+    golden = golden_ref_outputs()["wrk/1.r"]
     assert open(out, "rb").read() == golden
     assert len(rec) == golden.count(b"\n") // 3
 

@@ -1,0 +1,115 @@
+"""The drop-in `mecat2ref` executable (aligngraph2_b200/host/mecat2ref_main.cpp).
+
+CPU: with AG2_SKIP_MAP=1 the GPU stage is skipped and the program runs its file handling (0.fq, ref.fq,
+chrindex.txt, config.txt) plus result_combine / polish_result on the reference's own thread file; every file must be
+byte-identical to what the unmodified reference binary wrote (tests/golden/mapper_stress_ref.*).
+GPU: the whole program, same comparison, thread file included."""
+import hashlib
+import importlib.util
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_ref_outputs
+
+ARGS = ["-d", "reads.fq", "-r", "ref.fa", "-b", "1", "-w", "./wrk", "-o", "o.txt", "-p", "p.txt", "-l", "0.5", "-u", "2.0",
+        "-z", "200", "-y", "0.9"]
+
+
+@pytest.fixture(scope="module")
+def binary():
+    from aligngraph2_b200 import build
+    build.build()
+    return build.build_host()
+
+
+def _inputs(d):
+    spec = importlib.util.spec_from_file_location("gen_mapper_golden", os.path.join(GOLDEN, "gen_mapper_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    chroms, reads = gen.build()
+    z = np.load(os.path.join(GOLDEN, "mapper_stress.npz"))
+    assert b"".join(reads) == z["bases"].tobytes()       # the generator still makes the committed fixture
+    gen.write_inputs(str(d), chroms, reads)
+
+
+def _sha(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+def _check_outputs(d, gold, thread_file: bool):
+    hashes = json.load(open(os.path.join(GOLDEN, "mapper_stress_ref.json")))
+    assert _sha(d / "wrk" / "0.fq") == hashes["wrk/0.fq"]
+    assert _sha(d / "wrk" / "ref.fq") == hashes["wrk/ref.fq"]
+    assert (d / "wrk" / "chrindex.txt").read_bytes() == gold["wrk/chrindex.txt"]
+    if thread_file:
+        assert (d / "wrk" / "1.r").read_bytes() == gold["wrk/1.r"]
+    assert (d / "o.txt").read_bytes() == gold["o.txt"]
+    assert (d / "p.txt").read_bytes() == gold["p.txt"]
+    cfg = (d / "config.txt").read_text().splitlines()
+    assert cfg[:7] == ["./wrk", "ref.fa", "reads.fq", "o.txt", "p.txt", "1\t90", "2"]
+    assert cfg[7].startswith("The Building read Index Time:") and cfg[9].startswith("The Mapping Time:")
+    assert (d / "p.txt.config").exists()
+
+
+def test_files_combine_and_polish_match_reference(binary, tmp_path):
+    gold = golden_ref_outputs()
+    _inputs(tmp_path)
+    (tmp_path / "wrk").mkdir()
+    (tmp_path / "wrk" / "1.r").write_bytes(gold["wrk/1.r"])
+    r = subprocess.run([binary] + ARGS, cwd=tmp_path, env=dict(os.environ, AG2_SKIP_MAP="1"), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    _check_outputs(tmp_path, gold, thread_file=False)
+
+
+def test_usage_errors_exit_1(binary, tmp_path):
+    r = subprocess.run([binary, "-d", "x.fq"], cwd=tmp_path, capture_output=True)
+    assert r.returncode == 1 and b"reference must be specified" in r.stderr
+    r = subprocess.run([binary] + ARGS + ["-n", "0"], cwd=tmp_path, capture_output=True)
+    assert r.returncode == 1 and b"candidates must be > 0" in r.stderr
+
+
+def test_without_gpu_exits_1(binary, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    _inputs(tmp_path)
+    r = subprocess.run([binary] + ARGS, cwd=tmp_path, capture_output=True)
+    assert r.returncode == 1 and b"no CPU path" in r.stderr     # AlignGraph2.py:280-296 then falls back to vanilla mecat2ref
+
+
+@pytest.mark.gpu
+def test_whole_program_matches_reference(binary, tmp_path):
+    gold = golden_ref_outputs()
+    _inputs(tmp_path)
+    r = subprocess.run([binary] + ARGS + ["-t", "4"], cwd=tmp_path, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    cfg = (tmp_path / "config.txt").read_text().splitlines()
+    assert cfg[5] == "4\t90"
+    (tmp_path / "config.txt").write_text("\n".join(cfg[:5] + ["1\t90"] + cfg[6:]) + "\n")
+    _check_outputs(tmp_path, gold, thread_file=True)
+    assert (tmp_path / "wrk" / "4.r").read_bytes() == b""
+
+
+@pytest.mark.gpu
+def test_whole_program_matches_reference_binary_run(binary, tmp_path):
+    from oracle import binding
+    if not os.path.exists(binding.REF_BIN):
+        pytest.skip("oracle/_ref/mecat2ref not built on this box")
+    spec = importlib.util.spec_from_file_location("gen_mapper_golden", os.path.join(GOLDEN, "gen_mapper_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    chroms, reads = gen.build(seed=99)
+    a, b = tmp_path / "ref", tmp_path / "gpu"
+    for d in (a, b):
+        d.mkdir()
+        gen.write_inputs(str(d), chroms, reads[:60])
+    args = [x if x != "1" else "2" for x in ARGS]       # -b 2
+    subprocess.run([binding.REF_BIN, "-t", "1"] + args, cwd=a, check=True, capture_output=True)
+    r = subprocess.run([binary] + args, cwd=b, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    for name in ("wrk/0.fq", "wrk/ref.fq", "wrk/chrindex.txt", "wrk/1.r", "o.txt", "p.txt"):
+        assert (a / name).read_bytes() == (b / name).read_bytes(), name

@@ -11,7 +11,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from conftest import GOLDEN
+from conftest import GOLDEN, golden_ref_outputs
 
 
 @pytest.fixture(scope="module")
@@ -33,7 +33,7 @@ def test_thread_file_matches_golden(mapper, tmp_path):
     offs = z["offsets"]
     out = str(tmp_path / "1.r")
     n, st = mapper.map_batch(z["genome"].tobytes(), z["bases"].tobytes(), offs, np.arange(1, len(offs)), out)
-    golden = lzma.open(os.path.join(GOLDEN, "mapper_stress.r.xz")).read()
+    golden = golden_ref_outputs()["wrk/1.r"]
     assert open(out, "rb").read() == golden
     assert n == golden.count(b"\n") // 3
     # the fixture reaches the branches a uniform random genome never does
