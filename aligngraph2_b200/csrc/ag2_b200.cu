@@ -258,7 +258,10 @@ struct ag2_ctx {
     DevBuf tb, tb_wide;
     DevBuf wide_queue;
     DevBuf scalars;                     // ChainCounters + work counters + totals
-    size_t ws_limit = (size_t)6 << 30;  // bytes per workspace string per chunk
+    size_t ws_limit = (size_t)24 << 30; // bytes per workspace string per chunk (resident runs: one chunk, no drain tails)
+    size_t ws_limit_streamed = (size_t)3 << 30; // chunk size when results stream to host buffers while the next chunk computes
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done = nullptr;
     bool ran = false;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -377,6 +380,8 @@ int ag2_ctx_create(int device, ag2_ctx **out)
     }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMalloc(&ctx->scalars.p, sizeof(Scalars)) != cudaSuccess) {
         delete ctx;
@@ -408,6 +413,8 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
     }
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->chunk_done) cudaEventDestroy(ctx->chunk_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -500,8 +507,15 @@ int ag2_extend_upload(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n)
 
 // extend_candidate over n device-resident candidates.  Records go to d_rec[0..n); the strings of the ok records are
 // appended to the dense string pool at dense_base (which this returns advanced), earlier contents are kept.
+struct HostSink { // caller-owned host buffers that receive each chunk's results while the next chunk computes
+    ag2_record *rec = nullptr;
+    char *q = nullptr, *t = nullptr;
+    int64_t cap = 0;
+    bool overflow = false;
+};
+
 static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record *d_rec, int64_t dense_base_in, int64_t *dense_base_out,
-                        bool fresh_stats)
+                        bool fresh_stats, HostSink *sink = nullptr)
 {
     cudaStream_t st = ctx->stream;
     int launches = 0;
@@ -550,7 +564,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     std::vector<std::pair<int64_t, int64_t>> chunks;
     for (int64_t lo = 0; lo < n;) {
         int64_t hi = lo + 1;
-        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= ctx->ws_limit) ++hi;
+        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= (sink ? ctx->ws_limit_streamed : ctx->ws_limit)) ++hi;
         chunks.push_back({lo, hi});
         max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
         max_meta = std::max(max_meta, (size_t)(mf[hi] - mf[lo]));
@@ -639,9 +653,21 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             (char *)ctx->out_q.p, (char *)ctx->out_t.p, &sc->aligned, &sc->columns);
         ++launches;
         CK(cudaGetLastError());
+        if (sink) { // this chunk's records and strings go home on the copy stream while the next chunk computes
+            CK(cudaEventRecord(ctx->chunk_done, st));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done, 0));
+            CK(cudaMemcpyAsync(sink->rec + lo, d_rec + lo, (size_t)cn * sizeof(Record), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (sink->q && sink->t && dense_base + chunk_total <= sink->cap) {
+                CK(cudaMemcpyAsync(sink->q + dense_base, (char *)ctx->out_q.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                CK(cudaMemcpyAsync(sink->t + dense_base, (char *)ctx->out_t.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            } else if (sink->q || sink->t) {
+                sink->overflow = true;
+            }
+        }
         dense_base += chunk_total;
     }
     CK(cudaStreamSynchronize(st));
+    if (sink) CK(cudaStreamSynchronize(ctx->copy_stream));
     *dense_base_out = dense_base;
 
     Scalars hs;
@@ -710,9 +736,22 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
 {
     int r = ag2_extend_upload(ctx, cand, n);
     if (r != AG2_OK) return r;
-    r = ag2_extend_run(ctx);
+    if (!rec_out) return fail(ctx, AG2_EINVAL, "ag2_xdrop_extend_batch: rec_out is required");
+    CK(cudaSetDevice(ctx->device));
+    RESERVE(ctx->rec, (size_t)n * sizeof(Record));
+    HostSink sink;
+    sink.rec = rec_out;
+    sink.q = qaln_out;
+    sink.t = saln_out;
+    sink.cap = aln_cap;
+    int64_t total = 0;
+    r = extend_batch(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, 0, &total, true, &sink);
     if (r != AG2_OK) return r;
-    return ag2_extend_fetch(ctx, rec_out, qaln_out, saln_out, aln_cap, aln_used);
+    ctx->out_total = total;
+    ctx->ran = true;
+    if (aln_used) *aln_used = total;
+    if (sink.overflow) return fail(ctx, AG2_ECAP, "ag2_xdrop_extend_batch: need %ld bytes per string, have %ld", (long)total, (long)aln_cap);
+    return AG2_OK;
 }
 
 

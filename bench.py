@@ -315,8 +315,8 @@ def main():
         if world > 1:
             dist.all_reduce(a2, op=dist.ReduceOp.SUM)
         e2e = {"value": float(a2.item()) * args.steps / (float(t2.item()) * 1e-3) / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(total_bases + h_off.nbytes + h_cand.nbytes),
-               "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used), "ms_per_step": float(t2.item()) / args.steps}
+               "h2d_bytes_per_step": int(total_bases + h_off.nbytes + h_cand.nbytes) * world,
+               "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used) * world, "ms_per_step": float(t2.item()) / args.steps}
 
     # ---- the stages in front of the extension on the same batch (not part of the headline metric) ----
     stages = None
