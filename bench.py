@@ -277,13 +277,9 @@ def main():
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     st = dev.stats()
-    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-    agg = torch.tensor([float(st["aligned"]), float(st["cells"])], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
-    aligned_all = float(agg[0].item())
+    from aligngraph2_b200.shard import reduce_measurement
+    ms_max, summed = reduce_measurement(ms, {"aligned": st["aligned"], "cells": st["cells"]}, device="cuda")
+    aligned_all = summed["aligned"]
     value = aligned_all * args.steps / (ms_max * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers: `e2e` ----
