@@ -9,24 +9,28 @@ ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "libag2_b200.so")
 SOURCES = [os.path.join(PKG, "csrc", "ag2_b200.cu")]
 HEADERS = [os.path.join(PKG, "csrc", n) for n in ("xdrop_device.cuh", "xdrop_lane.cuh", "seed_device.cuh", "index_kernels.cuh",
-                                                   "rescue_device.cuh", "map_kernels.cuh")] + [ os.path.join(ROOT, "include", "ag2_b200.h")]
+                                                   "rescue_device.cuh", "map_kernels.cuh", "kmer_kernels.cuh")] + [ os.path.join(ROOT, "include", "ag2_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
 HOST_SRC = os.path.join(PKG, "host", "mecat2ref_main.cpp")
 HOST_BIN = os.path.join(PKG, "bin", "mecat2ref")
+HOST_PROGRAMS = {"mecat2ref": "mecat2ref_main.cpp", "kmer_counter": "kmer_counter_main.cpp"}
 
 
-def build_host(force: bool = False) -> str:
-    """The drop-in `mecat2ref` executable (C++ host over the C ABI)."""
-    if not force and os.path.exists(HOST_BIN) and os.path.getmtime(HOST_BIN) > max(os.path.getmtime(HOST_SRC), os.path.getmtime(SO)):
-        return HOST_BIN
+def build_host(force: bool = False, name: str = "mecat2ref") -> str:
+    """The drop-in executables (C++ hosts over the C ABI): `mecat2ref`, `kmer_counter`.
+    Builds all of them, returns the path of `name`."""
     os.makedirs(os.path.dirname(HOST_BIN), exist_ok=True)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.run([cxx, "-O2", "-std=c++17", "-Wall", "-o", HOST_BIN, HOST_SRC, "-L" + PKG, "-lag2_b200",
-                    "-Wl,-rpath,$ORIGIN/.."], check=True, cwd=ROOT)
-    return HOST_BIN
+    for prog, src in HOST_PROGRAMS.items():
+        src_path, out = os.path.join(PKG, "host", src), os.path.join(PKG, "bin", prog)
+        if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src_path), os.path.getmtime(SO)):
+            continue
+        subprocess.run([cxx, "-O2", "-std=c++17", "-Wall", "-o", out, src_path, "-L" + PKG, "-lag2_b200",
+                        "-Wl,-rpath,$ORIGIN/.."], check=True, cwd=ROOT)
+    return os.path.join(PKG, "bin", name)
 
 
 def stale() -> bool:

@@ -7,6 +7,7 @@
 #include "xdrop_lane.cuh"
 #include "index_kernels.cuh"
 #include "map_kernels.cuh"
+#include "kmer_kernels.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -240,6 +241,10 @@ struct ag2_ctx {
     bool ref_indexed = false, votes_ready = false;
     int64_t read_prefix_len = 0;       // bytes of the concatenated reads that enter the read index (A2)
     DevBuf seed_need, seed_prefix, seed_scratch, seed_cands, seed_ncand;
+    // ag2_kmer_* (PAGraph kmer_counter)
+    DevBuf km_table, km_hist, km_flags, km_offs, km_out;
+    int km_k = 0;
+    int64_t km_n_solid = 0;
     // ag2_map_reads
     DevBuf rec_pool, map_cand, map_cand_prefix, map_plans, map_rescue_n, map_rescue_prefix, map_out_refs, map_nout, map_flags,
         map_list, map_out_prefix, map_out_rec;
@@ -401,7 +406,8 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
                      &ctx->ix_fill, &ctx->ix_tiles, &ctx->ix_kcount, &ctx->ix_vote, &ctx->seed_need, &ctx->seed_prefix,
                      &ctx->seed_scratch, &ctx->seed_cands, &ctx->seed_ncand, &ctx->rec_pool, &ctx->map_cand, &ctx->map_cand_prefix,
                      &ctx->map_plans, &ctx->map_rescue_n, &ctx->map_rescue_prefix, &ctx->map_out_refs, &ctx->map_nout, &ctx->map_flags,
-                     &ctx->map_list, &ctx->map_out_prefix, &ctx->map_out_rec, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
+                     &ctx->map_list, &ctx->map_out_prefix, &ctx->map_out_rec, &ctx->km_table, &ctx->km_hist, &ctx->km_flags, &ctx->km_offs,
+                     &ctx->km_out, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
                      &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->wide_queue, &ctx->scalars};
@@ -1103,6 +1109,113 @@ int ag2_map_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return rc;
+}
+
+// ---- PAGraph kmer_counter (B1) -------------------------------------------------------------------
+int ag2_kmer_begin(ag2_ctx *ctx, int k)
+{
+    if (!ctx || k < 1 || k > 15) return fail(ctx, AG2_EINVAL, "ag2_kmer_begin: k must be in 1..15");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t nbins = 1ll << (2 * k);
+    RESERVE(ctx->km_table, (size_t)nbins * 4);
+    CK(cudaMemsetAsync(ctx->km_table.p, 0, (size_t)nbins * 4, ctx->stream));
+    ctx->km_k = k;
+    ctx->km_n_solid = 0;
+    return AG2_OK;
+}
+
+int ag2_kmer_add_reads(ag2_ctx *ctx)
+{
+    if (!ctx || !ctx->km_k) return fail(ctx, AG2_ESTATE, "ag2_kmer_add_reads: call ag2_kmer_begin first");
+    if (!ctx->n_reads) return fail(ctx, AG2_ESTATE, "ag2_kmer_add_reads: no reads loaded");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<int64_t> last(1);
+    CK(cudaMemcpy(last.data(), (const int64_t *)ctx->read_off.p + ctx->n_reads, 8, cudaMemcpyDeviceToHost));
+    const int64_t groups = last[0] >> 5;
+    if (groups > 0) {
+        kmer_abundance_kernel<<<grid_for(groups * 32, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+            (const uint32_t *)ctx->reads2.p, (const int64_t *)ctx->read_off.p, (const int32_t *)ctx->read_len.p, ctx->n_reads, groups,
+            ctx->km_k, (uint32_t *)ctx->km_table.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return AG2_OK;
+}
+
+int ag2_kmer_solid(ag2_ctx *ctx, double threshold, int64_t *min_abundance, int64_t *n_solid)
+{
+    if (!ctx || !ctx->km_k) return fail(ctx, AG2_ESTATE, "ag2_kmer_solid: call ag2_kmer_begin first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nbins = 1ll << (2 * ctx->km_k);
+    RESERVE(ctx->km_hist, (size_t)(kAbWindow + 2) * 8);
+    unsigned long long *hist = (unsigned long long *)ctx->km_hist.p;
+    unsigned int *d_max = (unsigned int *)(hist + kAbWindow);
+    // the abundance cut (:58-77): ascending abundances until 1 - bins_so_far / 4^k <= threshold
+    std::vector<unsigned long long> h((size_t)kAbWindow + 1);
+    unsigned long long sum = 0;
+    int64_t cut = 0;
+    bool found = false;
+    for (uint32_t lo = 0; !found; lo += kAbWindow) {
+        CK(cudaMemsetAsync(hist, 0, (size_t)(kAbWindow + 2) * 8, st));
+        abundance_hist_kernel<<<ctx->sm_count * 4, 512, 0, st>>>((const uint32_t *)ctx->km_table.p, nbins, lo, hist, d_max);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h.data(), hist, (size_t)(kAbWindow + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const unsigned int mx = (unsigned int)h[(size_t)kAbWindow];
+        for (int a = 0; a < kAbWindow; ++a) {
+            if (!h[(size_t)a]) continue;
+            sum += h[(size_t)a];
+            if (1 - sum * 1.0 / (double)nbins <= threshold) {
+                cut = (int64_t)lo + a;
+                found = true;
+                break;
+            }
+        }
+        if (!found && (uint64_t)lo + kAbWindow > mx) break; // no abundance qualified: the reference keeps minAbundance = 0
+    }
+    // solid k-mers, ascending: tiles of the 4^13-element scan (the flags reuse the scan of the index build)
+    RESERVE(ctx->km_flags, (size_t)kNCodes * 4);
+    RESERVE(ctx->km_offs, (size_t)(kNCodes + 1) * 4);
+    int64_t total = 0;
+    // pass 1: count, pass 2: scatter
+    std::vector<int64_t> slab_count;
+    const int64_t slab = nbins < kNCodes ? nbins : kNCodes;
+    for (int pass = 0; pass < 2; ++pass) {
+        int64_t base = 0;
+        if (pass == 1) RESERVE(ctx->km_out, (size_t)(total + 1) * 8);
+        for (int64_t first = 0, si = 0; first < nbins; first += slab, ++si) {
+            solid_flags_kernel<<<grid_for(slab, 256, ctx->sm_count), 256, 0, st>>>((const uint32_t *)ctx->km_table.p + first, slab, (uint32_t)cut,
+                                                                                   (int32_t *)ctx->km_flags.p);
+            if (slab < kNCodes) CK(cudaMemsetAsync((int32_t *)ctx->km_flags.p + slab, 0, (size_t)(kNCodes - slab) * 4, st));
+            int64_t cnt = 0;
+            int rc = scan_counts(ctx, (const int32_t *)ctx->km_flags.p, (uint32_t *)ctx->km_offs.p, &cnt);
+            if (rc != AG2_OK) return rc;
+            if (pass == 0) {
+                total += cnt;
+            } else {
+                solid_scatter_kernel<<<grid_for(slab, 256, ctx->sm_count), 256, 0, st>>>((const int32_t *)ctx->km_flags.p,
+                                                                                        (const uint32_t *)ctx->km_offs.p, first, slab,
+                                                                                        (uint64_t)base, (uint64_t *)ctx->km_out.p);
+                CK(cudaGetLastError());
+                base += cnt;
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    ctx->km_n_solid = total;
+    if (min_abundance) *min_abundance = cut;
+    if (n_solid) *n_solid = total;
+    return AG2_OK;
+}
+
+int ag2_kmer_fetch(ag2_ctx *ctx, uint64_t *codes_out, int64_t cap)
+{
+    if (!ctx || !codes_out) return fail(ctx, AG2_EINVAL, "ag2_kmer_fetch: bad argument");
+    if (cap < ctx->km_n_solid) return fail(ctx, AG2_ECAP, "ag2_kmer_fetch: need room for %ld codes", (long)ctx->km_n_solid);
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->km_n_solid) CK(cudaMemcpy(codes_out, ctx->km_out.p, (size_t)ctx->km_n_solid * 8, cudaMemcpyDeviceToHost));
+    return AG2_OK;
 }
 
 } // extern "C"

@@ -149,6 +149,18 @@ class Mecat2RefDevice:
                                                               r["qs"], r["sb"], r["se"]))
                 f.write(qaln[o:o + n].tobytes() + b"\n" + saln[o:o + n].tobytes() + b"\n")
 
+    # -- PAGraph kmer_counter ------------------------------------------------------------------------
+    def solid_kmers(self, k: int = 14, threshold: float = 0.2):
+        """kmerCounter (PAGraph/src/main/kmer_counter.cpp:19-96) over the loaded read batch: returns
+        (ascending solid k-mer codes as uint64, min abundance)."""
+        self._check(self._L.ag2_kmer_begin(self._ctx, k), "ag2_kmer_begin")
+        self._check(self._L.ag2_kmer_add_reads(self._ctx), "ag2_kmer_add_reads")
+        cut, n = C.c_int64(), C.c_int64()
+        self._check(self._L.ag2_kmer_solid(self._ctx, threshold, C.byref(cut), C.byref(n)), "ag2_kmer_solid")
+        out = np.empty(max(n.value, 1), dtype=np.uint64)
+        self._check(self._L.ag2_kmer_fetch(self._ctx, out.ctypes.data, out.size), "ag2_kmer_fetch")
+        return out[:n.value], cut.value
+
     # -- extension ---------------------------------------------------------------------------
     @staticmethod
     def make_candidates(read, strand, loc1, loc2, score=None) -> np.ndarray:

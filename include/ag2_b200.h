@@ -137,6 +137,17 @@ int ag2_extend_upload_from_seeds(ag2_ctx *ctx, int maxc, int64_t *n_candidates);
 int ag2_map_reads(ag2_ctx *ctx, int maxc, int num_output, int64_t *n_records);
 int ag2_map_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used);
 
+/* ---- PAGraph kmer_counter (PAGraph/src/main/kmer_counter.cpp:19-96) ----
+ * ag2_kmer_begin zeroes the 4^k abundance table (k <= 15); ag2_kmer_add_reads adds every k-mer of the loaded read
+ * batch (call ag2_reads_load + ag2_kmer_add_reads per batch); ag2_kmer_solid applies the cut -- the smallest abundance
+ * a with 1 - bins(abundance <= a) / 4^k <= threshold -- and selects the k-mers with abundance >= cut;
+ * ag2_kmer_fetch copies their codes (2 bits per base, first base most significant, A0 C1 G2 T3) in ascending order,
+ * the order `kmer_counter -t 1` writes. */
+int ag2_kmer_begin(ag2_ctx *ctx, int k);
+int ag2_kmer_add_reads(ag2_ctx *ctx);
+int ag2_kmer_solid(ag2_ctx *ctx, double threshold, int64_t *min_abundance, int64_t *n_solid);
+int ag2_kmer_fetch(ag2_ctx *ctx, uint64_t *codes_out, int64_t cap);
+
 /* The CUDA stream the context launches on (cudaStream_t as void*), for callers that time with
  * their own events. */
 void *ag2_ctx_stream(ag2_ctx *ctx);

@@ -99,6 +99,10 @@ long orc_mapper_aligned(const orc_mapper *m);
 long orc_map_batch(const char *ref, long R, const char *reads, const long *offs, const int *ids, long n, int cbl, double alpha,
                    double beta, int maxc, int num_output, const char *r_path, long *stats);
 
+/* ---- PAGraph kmer_counter (row B1): ag2_kmer.c ---- */
+long orc_solid_kmers(const char *reads, const long *offs, long n_reads, int k, double threshold, uint64_t *codes_out, long cap,
+                     long *min_abundance);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "libag2_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_mecat.so")
 REF_BIN = os.path.join(HERE, "_ref", "mecat2ref")
+REF_KMER_COUNTER = os.path.join(HERE, "_ref", "kmer_counter")
 
 MAX_ALN = 500000  # MC/defs.h:202 MAX_SEQ_SIZE
 
@@ -263,3 +264,18 @@ class IndexOracle:
             self.lib.orc_index_free(self.ix)
         except Exception:
             pass
+
+
+def solid_kmers(bases: bytes, offsets, k: int, threshold: float = 0.2):
+    """oracle/ag2_kmer.c: (sorted solid k-mer codes as uint64, min abundance)."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    L = C.CDLL(ORACLE_SO)
+    L.orc_solid_kmers.restype = C.c_long
+    L.orc_solid_kmers.argtypes = [C.c_char_p, C.c_void_p, C.c_long, C.c_int, C.c_double, C.c_void_p, C.c_long, C.POINTER(C.c_long)]
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    cut = C.c_long()
+    n = L.orc_solid_kmers(bases, offsets.ctypes.data, len(offsets) - 1, k, threshold, None, 0, C.byref(cut))
+    out = np.empty(n, dtype=np.uint64)
+    L.orc_solid_kmers(bases, offsets.ctypes.data, len(offsets) - 1, k, threshold, out.ctypes.data, n, C.byref(cut))
+    return out, cut.value
