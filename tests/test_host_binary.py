@@ -113,3 +113,29 @@ def test_whole_program_matches_reference_binary_run(binary, tmp_path):
     assert r.returncode == 0, r.stderr.decode()
     for name in ("wrk/0.fq", "wrk/ref.fq", "wrk/chrindex.txt", "wrk/1.r", "o.txt", "p.txt"):
         assert (a / name).read_bytes() == (b / name).read_bytes(), name
+
+
+@pytest.mark.gpu
+def test_more_than_one_load_fastq_batch(binary, tmp_path):
+    # 100 200 short reads: load_fastq hands out 100 001 reads, then the rest (impl_large.cpp:1965-1991), and the read
+    # index only sees the first 100 000 (:277).  Whole program against a fresh `-t 1` run of the reference binary.
+    from oracle import binding
+    if not os.path.exists(binding.REF_BIN):
+        pytest.skip("oracle/_ref/mecat2ref not built on this box")
+    from aligngraph2_b200 import synth
+    d = synth.make_batch_torch(4711, 1_500_000, 100_200, 1150, device="cuda")
+    ref, bases, off = d["ref"].cpu().numpy(), d["bases"].cpu().numpy(), d["offsets"].cpu().numpy()
+    a, b = tmp_path / "ref", tmp_path / "gpu"
+    for dd in (a, b):
+        dd.mkdir()
+        synth.write_fasta(str(dd / "ref.fa"), "chr1", ref)
+        with open(dd / "reads.fq", "wb") as f:
+            for i in range(len(off) - 1):
+                rd = bases[off[i]:off[i + 1]].tobytes()
+                f.write(b"@r%d\n" % i + rd + b"\n+\n" + b"I" * len(rd) + b"\n")
+    subprocess.run([binding.REF_BIN, "-t", "1"] + ARGS, cwd=a, check=True, capture_output=True)
+    r = subprocess.run([binary] + ARGS, cwd=b, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    for name in ("wrk/0.fq", "wrk/chrindex.txt", "wrk/1.r", "o.txt", "p.txt"):
+        assert (a / name).read_bytes() == (b / name).read_bytes(), name
+    assert (b / "p.txt").read_bytes().count(b"\n") > 3 * 99_000
