@@ -39,17 +39,17 @@ constexpr int kLaneScratch = kLaneTbBytes + 256; // + normalised query codes of 
 // (MIN_SCORE, MIN_SCORE) (:161-162).  Two consecutive columns of a thread share one 32-bit word
 // so that lane i only ever touches bank i.
 struct LaneSmem {
-    uint16_t band[kBandSlots / 2][kLaneThreads][2];
+    int16_t band[kBandSlots / 2][kLaneThreads][2];
     uint32_t tseq[kSeqWords][kLaneThreads];  // target block, 16 codes per word, extension order
 };
 
-__device__ __forceinline__ uint16_t *band_slot(LaneSmem &sm, int tid, int b)
+__device__ __forceinline__ int16_t *band_slot(LaneSmem &sm, int tid, int b)
 {
     const int slot = b & (kBandSlots - 1);
     return &sm.band[slot >> 1][tid][slot & 1];
 }
-__device__ __forceinline__ uint16_t band_live(int h) { return (uint16_t)(h * 2); }
-constexpr uint16_t kBandSentinel = (uint16_t)(((kNeg16 + 1) * 2) | 1);
+__device__ __forceinline__ int16_t band_live(int h) { return (int16_t)(h * 2); }
+constexpr int16_t kBandSentinel = (int16_t)(((kNeg16 + 1) * 2) | 1);
 
 struct LaneArgs {
     PackedSeqs seqs;
@@ -150,7 +150,7 @@ __device__ int lane_dp(LaneSmem &sm, int tid, const uint32_t *__restrict__ qcode
         const int ac = (int)(aw & 3u);
         aw >>= 2;
         uint32_t *trow = reinterpret_cast<uint32_t *>(tb + (size_t)a * 64);
-        int diag = kNeg16, hgap = kNeg16, last = first;
+        int diag = kNeg16, hgap = kNeg16;
         int thr = best - xd;
         cells += (unsigned)(bsize - first);
         ++rows;
@@ -159,8 +159,8 @@ __device__ int lane_dp(LaneSmem &sm, int tid, const uint32_t *__restrict__ qcode
         uint32_t bw = sm.tseq[first >> 4][tid] >> (2 * (first & 15));
         int b;
         for (b = first; b < bsize; ++b) { // (:84-140)
-            uint16_t *cell = band_slot(sm, tid, b);
-            const int st = (int)(short)*cell;
+            int16_t *cell = band_slot(sm, tid, b);
+            const int st = *cell;
             const int x = st >> 1;
             const int e = x - 1;
             const int h = (st & 1) ? kNeg16 : x;
@@ -173,9 +173,8 @@ __device__ int lane_dp(LaneSmem &sm, int tid, const uint32_t *__restrict__ qcode
             if (sc < hgap) { sc = hgap; nib = kOpGapA; }
             if (sc < thr) { // best - sc > x_dropoff (:109)
                 if (first == b) ++first;         // dropped from the band: the column is dead
-                else *cell = (uint16_t)(st | 1); // h = MIN_SCORE, e unchanged (:111)
+                else *cell = (int16_t)(st | 1); // h = MIN_SCORE, e unchanged (:111)
             } else {
-                last = b;
                 if (sc > best) { best = sc; thr = sc - xd; ae = a; be = b; }
                 if (e >= sc) nib |= kExtA;     // e - ge >= sc - goe (:121-126)
                 if (hgap >= sc) nib |= kExtB;  // (:129-133)
@@ -192,6 +191,10 @@ __device__ int lane_dp(LaneSmem &sm, int tid, const uint32_t *__restrict__ qcode
             }
         }
         if (first == bsize) break; // (:142)
+        // last_b_index (:113): the last cell of this row that was not pruned.  Every band cell was just rewritten, and
+        // a pruned one carries the dead bit, so walk back from the end instead of tracking it per cell.
+        int last = bsize - 1;
+        while (*band_slot(sm, tid, last) & 1) --last;
         if (last < bsize - 1) {
             if (sh != 0) trow[((b - 1) & (kBandSlots - 1)) >> 3] = tbw;
             bsize = last + 1; // (:144-145)

@@ -157,6 +157,10 @@ def cpu_baseline(ref, bases, off, strand, loc1, loc2, n_sample: int, cores: int)
                       f"{cores} processes x 1 thread, slowest worker {busy:.1f} s (pool wall {wall:.1f} s)"}
 
 
+def cbar_guard(st) -> float:
+    return max(1.0, st["cells"] / max(1, st["aligned"]))
+
+
 def host_cores() -> int:
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -325,9 +329,19 @@ def main():
             return (time.perf_counter() - t0) * 1e3
         dev.load_reads(bases=bases_np, offsets=h_off)
         dev.build_index(200, 0.5, 2.0)
+        import ctypes as C
+        n_rec = C.c_int64()
+
+        def map_all():
+            dev._check(dev._L.ag2_map_reads(dev._ctx, 10, 1, C.byref(n_rec)), "ag2_map_reads")
         stages = {"index_build_ms": timed(lambda: dev.build_index(200, 0.5, 2.0)),
-                  "seed_candidates_ms": timed(lambda: dev.seed_candidates(0, 10)),
-                  "note": "ag2_index_build (A2-A4) and ag2_seed_candidates (A5-A7, incl. the D2H of the candidates) on the bench batch"}
+                  "seed_candidates_ms": timed(lambda: dev.seed_candidates(0, 10))}
+        t_map = timed(map_all)
+        stages.update({"map_reads_ms": t_map, "map_reads_records": int(n_rec.value),
+                       "map_reads_gbp_per_s": float(dev.stats()["cells"]) / cbar_guard(st) / (t_map * 1e-3) / 1e9,
+                       "note": "same batch, resident inputs: ag2_index_build (A2-A4); ag2_seed_candidates (A5-A7, incl. the D2H of the "
+                               "candidates); ag2_map_reads = the whole per-read path (seed, extend every candidate, rescue, second pass, "
+                               "output choice; -n 10 -b 1), its Gbp/s estimated as DP cells / cells-per-aligned-base of the extend-only run"})
 
     # ---- roofline of the dominant kernel (xdrop_chains_kernel) ----
     peak, peak_src = peaks()
