@@ -279,3 +279,36 @@ def solid_kmers(bases: bytes, offsets, k: int, threshold: float = 0.2):
     out = np.empty(n, dtype=np.uint64)
     L.orc_solid_kmers(bases, offsets.ctypes.data, len(offsets) - 1, k, threshold, out.ctypes.data, n, C.byref(cut))
     return out, cut.value
+
+
+REF_PAGRAPH_DUMP = os.path.join(HERE, "_ref", "pagraph_dump")
+
+
+def pagraph_dump(d: str, out: str, eps: int = 10, cov: int = 2, solid: str = "solid.bin", ctg: str = "ctg.fasta",
+                 ref: str = "ref.fasta", aln: str = "c2r.ref") -> bytes:
+    """The restated A-Bruijn build (oracle/ag2_pagraph.cpp) on a pagraph input directory; returns the dump text."""
+    if not os.path.exists(ORACLE_SO):
+        build(ref=False)
+    L = C.CDLL(ORACLE_SO)
+    L.ag2o_pagraph_dump.argtypes = [C.c_char_p] * 5 + [C.c_long] * 2 + [C.c_char_p]
+    j = lambda n: os.path.join(d, n).encode()
+    rc = L.ag2o_pagraph_dump(j(solid), j(ctg), j(ref), d.encode(), j(aln), eps, cov, j(out))
+    if rc != 0:
+        raise RuntimeError(f"ag2o_pagraph_dump -> {rc}")
+    return open(os.path.join(d, out), "rb").read()
+
+
+def parse_graph_dump(blob: bytes):
+    """dump text -> list (one per config) of {vertex idx: (code, [(ctg, ref, count)...], [(to, step)...])}."""
+    cfgs = []
+    for line in blob.decode().split("\n"):
+        if line.startswith("#config"):
+            cfgs.append({})
+        elif line.startswith("V "):
+            t = line.split(" ")
+            npos = int(t[4])
+            pos = [tuple(int(x) for x in s.split(",")) for s in t[5:5 + npos]]
+            nedge = int(t[6 + npos])
+            edges = [tuple(int(x) for x in s.split(",")) for s in t[7 + npos:7 + npos + nedge]]
+            cfgs[-1][int(t[1])] = (int(t[2]), pos, edges)
+    return cfgs
