@@ -1,0 +1,247 @@
+"""ctypes mirror of include/ag2_pagraph.h: PAGraph's A-Bruijn graph build on the GPU.
+
+``Job`` follows run2() of PAGraph/src/main/pagraph.cpp:69-243 over the file-level entry points: open the input set, then
+per config block load_block() + build() (+ dump()).  There is no CPU path: without the CUDA library or a GPU the calls
+raise.  ``build_distributed`` is the multi-GPU form (reads sharded over ranks, one all-to-all of vertex tuples by owner
+rank) on torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+
+
+class Params(C.Structure):
+    _fields_ = [("outer_sample", C.c_int32), ("read_to_ctg_topk", C.c_int32), ("read_to_ref_topk", C.c_int32),
+                ("read_to_ctg_ratio", C.c_double), ("read_to_ref_ratio", C.c_double), ("epsilon", C.c_int64),
+                ("cov_filter", C.c_int64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_vertices", C.c_int64), ("lanes", C.c_int64 * 2), ("columns", C.c_int64 * 2), ("samples", C.c_int64 * 2),
+                ("tuples", C.c_int64 * 2), ("edges_raw", C.c_int64 * 2), ("positions", C.c_int64), ("edges", C.c_int64),
+                ("launches", C.c_int64), ("extract_ms", C.c_double), ("join_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: (list(getattr(self, n)) if hasattr(getattr(self, n), "__len__") else getattr(self, n)) for n, _ in self._fields_}
+
+
+ALN_DTYPE = np.dtype([("query", "<i4"), ("target", "<i4"), ("score", "<u8"), ("qb", "<i8"), ("qe", "<i8"), ("tb", "<i8"),
+                      ("te", "<i8"), ("forward", "<i4"), ("ncols", "<i4"), ("q_off", "<i8"), ("t_off", "<i8")])
+assert ALN_DTYPE.itemsize == 72
+
+EXPORTS = [
+    "ag2_pg_create", "ag2_pg_destroy", "ag2_pg_last_error", "ag2_pg_params_default", "ag2_pg_set_kmers", "ag2_pg_fetch_codes",
+    "ag2_pg_set_targets", "ag2_pg_set_reads", "ag2_pg_set_alignments", "ag2_pg_set_filters", "ag2_pg_build", "ag2_pg_extract",
+    "ag2_pg_partition", "ag2_pg_stream_dev", "ag2_pg_import_dev", "ag2_pg_join", "ag2_pg_get_stats", "ag2_pg_graph_fetch",
+    "ag2_pg_stream", "ag2_pg_job_open", "ag2_pg_job_close", "ag2_pg_job_error", "ag2_pg_job_blocks", "ag2_pg_job_block_ref",
+    "ag2_pg_job_handle", "ag2_pg_job_load_block", "ag2_pg_job_dump",
+]
+
+_bound = False
+
+
+def _L():
+    global _bound
+    L = _lib.load()
+    if _bound:
+        return L
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.ag2_pg_create.argtypes = [i32, C.POINTER(vp)]
+    L.ag2_pg_destroy.argtypes = [vp]
+    L.ag2_pg_destroy.restype = None
+    L.ag2_pg_last_error.argtypes = [vp]
+    L.ag2_pg_last_error.restype = C.c_char_p
+    L.ag2_pg_params_default.argtypes = [C.POINTER(Params)]
+    L.ag2_pg_params_default.restype = None
+    L.ag2_pg_set_kmers.argtypes = [vp, vp, i64, C.POINTER(i64)]
+    L.ag2_pg_fetch_codes.argtypes = [vp, vp, i64]
+    L.ag2_pg_set_targets.argtypes = [vp, vp, i64, vp, i64]
+    L.ag2_pg_set_reads.argtypes = [vp, vp, vp, i64, i64]
+    L.ag2_pg_set_alignments.argtypes = [vp, i32, vp, i64, vp, i64]
+    L.ag2_pg_set_filters.argtypes = [vp, vp, vp, vp]
+    for n in ("ag2_pg_build", "ag2_pg_extract", "ag2_pg_join"):
+        getattr(L, n).argtypes = [vp, C.POINTER(Params)]
+    L.ag2_pg_partition.argtypes = [vp, i32, vp]
+    L.ag2_pg_stream_dev.argtypes = [vp, C.POINTER(i64), vp, C.POINTER(i64), vp]
+    L.ag2_pg_import_dev.argtypes = [vp, i64, vp, i64, vp]
+    L.ag2_pg_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.ag2_pg_graph_fetch.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, i64]
+    L.ag2_pg_stream.argtypes = [vp]
+    L.ag2_pg_stream.restype = vp
+    L.ag2_pg_job_open.argtypes = [i32, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    L.ag2_pg_job_close.argtypes = [vp]
+    L.ag2_pg_job_close.restype = None
+    L.ag2_pg_job_error.argtypes = [vp]
+    L.ag2_pg_job_error.restype = C.c_char_p
+    L.ag2_pg_job_blocks.argtypes = [vp]
+    L.ag2_pg_job_block_ref.argtypes = [vp, i32]
+    L.ag2_pg_job_block_ref.restype = C.c_char_p
+    L.ag2_pg_job_handle.argtypes = [vp]
+    L.ag2_pg_job_handle.restype = vp
+    L.ag2_pg_job_load_block.argtypes = [vp, i32, i32, i32]
+    L.ag2_pg_job_dump.argtypes = [vp, i32, C.c_char_p, i32]
+    _bound = True
+    return L
+
+
+def default_params(epsilon: int = 10, cov: int = 1) -> Params:
+    p = Params()
+    _L().ag2_pg_params_default(C.byref(p))
+    p.epsilon, p.cov_filter = epsilon, cov
+    return p
+
+
+class Graph:
+    """CSR copy of the device graph (ag2_pg_graph_fetch)."""
+
+    def __init__(self, pos_off, ctg, ref, count, edge_off, edge_to, edge_step):
+        self.pos_off, self.ctg, self.ref, self.count = pos_off, ctg, ref, count
+        self.edge_off, self.edge_to, self.edge_step = edge_off, edge_to, edge_step
+
+
+class Job:
+    """One pagraph input set (the -k -c -R -p -a arguments of `pagraph`, AlignGraph2.py:414-427)."""
+
+    def __init__(self, kmer: str, ctg: str, ref: str, pre_dir: str, aln: str, device: int = 0):
+        self.L = _L()
+        self.h = C.c_void_p()
+        rc = self.L.ag2_pg_job_open(device, kmer.encode(), ctg.encode(), ref.encode(), pre_dir.encode(), aln.encode(), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.ag2_pg_job_error(self.h).decode() if self.h else ""
+            if self.h:
+                self.L.ag2_pg_job_close(self.h)
+                self.h = None
+            raise _lib.Ag2Error(f"ag2_pg_job_open -> {_lib.ERRORS.get(rc, rc)}: {msg}")
+        self.pg = self.L.ag2_pg_job_handle(self.h)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise _lib.Ag2Error(f"{what} -> {_lib.ERRORS.get(rc, rc)}: {self.L.ag2_pg_job_error(self.h).decode()} "
+                                f"{self.L.ag2_pg_last_error(self.pg).decode()}")
+
+    @property
+    def n_blocks(self) -> int:
+        return self.L.ag2_pg_job_blocks(self.h)
+
+    def load_block(self, block: int, rank: int = 0, world: int = 1) -> None:
+        self._check(self.L.ag2_pg_job_load_block(self.h, block, rank, world), "ag2_pg_job_load_block")
+
+    def build(self, params: Params) -> Stats:
+        self._check(self.L.ag2_pg_build(self.pg, C.byref(params)), "ag2_pg_build")
+        return self.stats()
+
+    def extract(self, params: Params) -> Stats:
+        self._check(self.L.ag2_pg_extract(self.pg, C.byref(params)), "ag2_pg_extract")
+        return self.stats()
+
+    def join(self, params: Params) -> Stats:
+        self._check(self.L.ag2_pg_join(self.pg, C.byref(params)), "ag2_pg_join")
+        return self.stats()
+
+    def stats(self) -> Stats:
+        s = Stats()
+        self.L.ag2_pg_get_stats(self.pg, C.byref(s))
+        return s
+
+    def dump(self, block: int, path: str, append: bool = False) -> None:
+        self._check(self.L.ag2_pg_job_dump(self.h, block, path.encode(), 1 if append else 0), "ag2_pg_job_dump")
+
+    def graph(self) -> Graph:
+        s = self.stats()
+        nv = s.n_vertices
+        po, eo = np.zeros(nv + 1, np.int64), np.zeros(nv + 1, np.int64)
+        ctg, ref = np.zeros(max(s.positions, 1), np.uint32), np.zeros(max(s.positions, 1), np.uint32)
+        cnt = np.zeros(max(s.positions, 1), np.uint16)
+        to, step = np.zeros(max(s.edges, 1), np.uint32), np.zeros(max(s.edges, 1), np.int32)
+        self._check(self.L.ag2_pg_graph_fetch(self.pg, po.ctypes.data, ctg.ctypes.data, ref.ctypes.data, cnt.ctypes.data, len(ctg),
+                                              eo.ctypes.data, to.ctypes.data, step.ctypes.data, len(to)), "ag2_pg_graph_fetch")
+        return Graph(po, ctg[:s.positions], ref[:s.positions], cnt[:s.positions], eo, to[:s.edges], step[:s.edges])
+
+    # ---- multi-GPU: streams as torch tensors over the handle's device memory -------------------------------------
+    def partition(self, n_owners: int) -> np.ndarray:
+        counts = np.zeros(2 * n_owners, np.int64)
+        self._check(self.L.ag2_pg_partition(self.pg, n_owners, counts.ctypes.data), "ag2_pg_partition")
+        return counts.reshape(2, n_owners)
+
+    def stream_pointers(self):
+        nt, ne = C.c_int64(), C.c_int64()
+        tp, ep = (C.c_void_p * 3)(), (C.c_void_p * 3)()
+        self._check(self.L.ag2_pg_stream_dev(self.pg, C.byref(nt), tp, C.byref(ne), ep), "ag2_pg_stream_dev")
+        return nt.value, [tp[i] or 0 for i in range(3)], ne.value, [ep[i] or 0 for i in range(3)]
+
+    def import_streams(self, n_tuples: int, tuple_ptrs, n_edges: int, edge_ptrs) -> None:
+        tp, ep = (C.c_void_p * 3)(*tuple_ptrs), (C.c_void_p * 3)(*edge_ptrs)
+        self._check(self.L.ag2_pg_import_dev(self.pg, n_tuples, tp, n_edges, ep), "ag2_pg_import_dev")
+
+    def close(self) -> None:
+        if self.h:
+            self.L.ag2_pg_job_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def exchange_plan(counts_all: np.ndarray, rank: int):
+    """Split sizes of the all-to-all from the gathered per-owner counts.
+
+    counts_all[r][o] = items rank r holds for owner o.  Returns (send splits of this rank, receive splits): the receive
+    buffer is the rank-major concatenation, i.e. global read order inside every vertex once it is stably sorted by vertex.
+    """
+    counts_all = np.asarray(counts_all, dtype=np.int64)
+    return counts_all[rank].tolist(), counts_all[:, rank].tolist()
+
+
+def _device_tensor(ptr: int, n: int, device):
+    """uint32/int32 view (as int32) of n 4-byte items of library-owned device memory."""
+    import torch
+
+    if n == 0:
+        return torch.empty(0, dtype=torch.int32, device=device)
+
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+
+    return torch.as_tensor(_Arr(), device=device)
+
+
+def build_distributed(job: Job, block: int, params: Params, group=None) -> Stats:
+    """Reads sharded over the ranks of the (NCCL) process group: extract per rank, stable partition by owner rank of the
+    vertex, ONE all-to-all per stream array, join per vertex range.  Every rank ends with the vertices it owns; the others
+    are empty in its CSR.  Results equal the one-GPU build because the rank-major receive order is the global read order."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    job.load_block(block, rank, world)
+    job.extract(params)
+    if world == 1:
+        return job.join(params)
+    counts = job.partition(world)                                  # [2][world]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    mine = torch.from_numpy(counts.reshape(-1)).to(dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    allc = torch.stack(gathered).cpu().numpy().reshape(world, 2, world)
+    nt, tptr, ne, eptr = job.stream_pointers()
+    received = []
+    for which, (n, ptrs) in enumerate(((nt, tptr), (ne, eptr))):
+        send, recv = exchange_plan(allc[:, which, :], rank)
+        outs = []
+        for p in ptrs:
+            src = _device_tensor(p, n, dev)
+            dst = torch.empty(int(sum(recv)), dtype=torch.int32, device=dev)
+            dist.all_to_all_single(dst, src, output_split_sizes=recv, input_split_sizes=send, group=group)
+            outs.append(dst)
+        received.append(outs)
+    torch.cuda.synchronize()
+    job.import_streams(received[0][0].numel(), [t.data_ptr() for t in received[0]],
+                       received[1][0].numel(), [t.data_ptr() for t in received[1]])
+    return job.join(params)

@@ -16,8 +16,8 @@ def lib():
     return L.load()
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "ag2_b200.h")).read()
+def declared_symbols(header="ag2_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(ag2_[a-z0-9_]+)\s*\(", text)))
 
@@ -29,6 +29,28 @@ def test_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), f"{n} declared in include/ag2_b200.h but not exported"
     from aligngraph2_b200.lib import EXPORTS
     assert sorted(EXPORTS) == names
+
+
+def test_exports_every_declared_pagraph_symbol(lib):
+    names = declared_symbols("ag2_pagraph.h")
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ag2_pagraph.h but not exported"
+    from aligngraph2_b200.pagraph import EXPORTS, ALN_DTYPE, Params, Stats
+    assert sorted(EXPORTS) == names
+    assert ALN_DTYPE.itemsize == 72 and C.sizeof(Params) == 48 and C.sizeof(Stats) == 128
+
+
+def test_pagraph_refuses_without_gpu(lib, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from aligngraph2_b200 import pagraph
+    from aligngraph2_b200.lib import Ag2Error
+    h = C.c_void_p()
+    assert pagraph._L().ag2_pg_create(0, C.byref(h)) == -1   # AG2_ENODEV
+    with pytest.raises(Ag2Error):
+        pagraph.Job("a", "b", "c", str(tmp_path), "d")
 
 
 def test_struct_layouts_match_header(lib):
