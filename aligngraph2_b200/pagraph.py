@@ -150,6 +150,14 @@ class Job:
     def dump(self, block: int, path: str, append: bool = False) -> None:
         self._check(self.L.ag2_pg_job_dump(self.h, block, path.encode(), 1 if append else 0), "ag2_pg_job_dump")
 
+    def codes(self) -> np.ndarray:
+        out = np.zeros(max(self.stats().n_vertices, 1), np.uint64)
+        self._check(self.L.ag2_pg_fetch_codes(self.pg, out.ctypes.data, len(out)), "ag2_pg_fetch_codes")
+        return out[:self.stats().n_vertices]
+
+    def block_ref(self, block: int) -> str:
+        return self.L.ag2_pg_job_block_ref(self.h, block).decode()
+
     def graph(self) -> Graph:
         s = self.stats()
         nv = s.n_vertices
@@ -212,6 +220,29 @@ def _device_tensor(ptr: int, n: int, device):
     return torch.as_tensor(_Arr(), device=device)
 
 
+def exchange_streams(arrays, counts, group=None):
+    """The one exchange step of the graph build: every rank holds its streams already partitioned by owner rank
+    (`counts[o]` items for owner o, same split for every array of the stream); one all-to-all per array delivers to
+    each owner the items of its vertex range from all ranks, concatenated in RANK order -- which is the global read order,
+    because reads are sharded contiguously.  Works on any backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = arrays[0].device
+    mine = torch.as_tensor(np.asarray(counts, dtype=np.int64), device=dev)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    allc = torch.stack(gathered).cpu().numpy()
+    send, recv = exchange_plan(allc, rank)
+    out = []
+    for src in arrays:
+        dst = torch.empty(int(sum(recv)), dtype=src.dtype, device=dev)
+        dist.all_to_all_single(dst, src, output_split_sizes=recv, input_split_sizes=send, group=group)
+        out.append(dst)
+    return out
+
+
 def build_distributed(job: Job, block: int, params: Params, group=None) -> Stats:
     """Reads sharded over the ranks of the (NCCL) process group: extract per rank, stable partition by owner rank of the
     vertex, ONE all-to-all per stream array, join per vertex range.  Every rank ends with the vertices it owns; the others
@@ -226,22 +257,54 @@ def build_distributed(job: Job, block: int, params: Params, group=None) -> Stats
         return job.join(params)
     counts = job.partition(world)                                  # [2][world]
     dev = torch.device("cuda", torch.cuda.current_device())
-    mine = torch.from_numpy(counts.reshape(-1)).to(dev)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine, group=group)
-    allc = torch.stack(gathered).cpu().numpy().reshape(world, 2, world)
     nt, tptr, ne, eptr = job.stream_pointers()
-    received = []
-    for which, (n, ptrs) in enumerate(((nt, tptr), (ne, eptr))):
-        send, recv = exchange_plan(allc[:, which, :], rank)
-        outs = []
-        for p in ptrs:
-            src = _device_tensor(p, n, dev)
-            dst = torch.empty(int(sum(recv)), dtype=torch.int32, device=dev)
-            dist.all_to_all_single(dst, src, output_split_sizes=recv, input_split_sizes=send, group=group)
-            outs.append(dst)
-        received.append(outs)
+    tup = exchange_streams([_device_tensor(p, nt, dev) for p in tptr], counts[0], group)
+    edg = exchange_streams([_device_tensor(p, ne, dev) for p in eptr], counts[1], group)
     torch.cuda.synchronize()
-    job.import_streams(received[0][0].numel(), [t.data_ptr() for t in received[0]],
-                       received[1][0].numel(), [t.data_ptr() for t in received[1]])
+    job.import_streams(tup[0].numel(), [t.data_ptr() for t in tup], edg[0].numel(), [t.data_ptr() for t in edg])
     return job.join(params)
+
+
+def gather_graph(job: Job, group=None) -> Graph:
+    """The all-gather that merges the per-GPU vertex tables before the traversal: every rank receives the
+    CSR pieces of all ranks.  Owner ranges ascend with the rank, so the merged payload is the rank-order concatenation and
+    the merged per-vertex sizes are the element-wise sums."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    g = job.graph()
+    if world == 1:
+        return g
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def gather(a: np.ndarray) -> list:
+        n = torch.tensor([a.size], dtype=torch.int64, device=dev)
+        sizes = [torch.empty_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=group)
+        sizes = [int(x.item()) for x in sizes]
+        pad = torch.zeros(max(max(sizes), 1), dtype=torch.int64, device=dev)
+        pad[:a.size] = torch.from_numpy(a.astype(np.int64)).to(dev)
+        outs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(outs, pad, group=group)
+        return [o[:k].cpu().numpy() for o, k in zip(outs, sizes)]
+
+    pos_n = sum(gather(np.diff(g.pos_off)))
+    edge_n = sum(gather(np.diff(g.edge_off)))
+    cat = lambda a, dt: np.concatenate(gather(a)).astype(dt)
+    pos_off = np.concatenate(([0], np.cumsum(pos_n))).astype(np.int64)
+    edge_off = np.concatenate(([0], np.cumsum(edge_n))).astype(np.int64)
+    return Graph(pos_off, cat(g.ctg, np.uint32), cat(g.ref, np.uint32), cat(g.count, np.uint16),
+                 edge_off, cat(g.edge_to, np.uint32), cat(g.edge_step, np.int32))
+
+
+def graph_dump_text(graph: Graph, codes: np.ndarray, block: int, ref_name: str) -> bytes:
+    """The dump format of ag2_pg_job_dump from a Graph held on the host (used with gather_graph)."""
+    out = [f"#config {block} {ref_name}\n"]
+    po, eo = graph.pos_off, graph.edge_off
+    for v in np.nonzero((np.diff(po) > 0) | (np.diff(eo) > 0))[0]:
+        pos = " ".join(f"{graph.ctg[i]},{graph.ref[i]},{graph.count[i]}" for i in range(po[v], po[v + 1]))
+        edg = " ".join(f"{graph.edge_to[i]},{graph.edge_step[i]}" for i in range(eo[v], eo[v + 1]))
+        line = f"V {v} {codes[v]} P {po[v + 1] - po[v]}" + (" " + pos if pos else "") + f" E {eo[v + 1] - eo[v]}" + (" " + edg if edg else "")
+        out.append(line + "\n")
+    return "".join(out).encode()

@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--cpu-sample-per-core", type=int, default=1000, help="reads per host core in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pagraph-reads", type=int, default=4000, help="reads of the A-Bruijn build stage line (0 = skip)")
+    ap.add_argument("--pagraph-k", type=int, default=14)
     return ap.parse_args()
 
 
@@ -155,6 +157,67 @@ def cpu_baseline(ref, bases, off, strand, loc1, loc2, n_sample: int, cores: int)
     return {"value": aligned / busy / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"first {n_sample} reads of the workload ({aligned / 1e6:.1f} Mbp aligned), extend stage only, "
                       f"{cores} processes x 1 thread, slowest worker {busy:.1f} s (pool wall {wall:.1f} s)"}
+
+
+def pagraph_stage(args, local: int):
+    """BASELINE configs[3] in small: the A-Bruijn graph build on pre-aligned synthetic reads.
+    Not the headline metric; reported as stages.pagraph with its own algorithmic-bytes figure (SURVEY 8d:
+    80 B per vertex tuple + 100 B per edge tuple) and the reference classes (or the port) on one host core beside it."""
+    import shutil
+    import tempfile
+    import torch
+    from aligngraph2_b200 import pagraph, synth_pg
+    d = tempfile.mkdtemp(prefix="ag2_pg_")
+    try:
+        n = args.pagraph_reads
+        info = synth_pg.make_input_set(d, args.seed, max(400_000, n * 40), n, tlen=args.tlen, n_ctg=8)
+        words = synth_pg.solid_words_from_reads(d, args.pagraph_k, 0.2, local)
+        j = lambda x: os.path.join(d, x)
+        job = pagraph.Job(j("solid.bin"), j("ctg.fasta"), j("ref.fasta"), d, j("c2r.ref"), device=local)
+        p = pagraph.default_params(10, 2)
+        job.load_block(0)
+        job.build(p)                                   # warm-up
+        torch.cuda.synchronize()
+        reps, t0 = 3, time.perf_counter()
+        for _ in range(reps):
+            st = job.build(p)
+        torch.cuda.synchronize()
+        build_ms = (time.perf_counter() - t0) * 1e3 / reps
+        t0 = time.perf_counter()
+        job.load_block(0)                              # files -> host parse -> H2D
+        st = job.build(p)
+        g = job.graph()                                # D2H of the CSR
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        sd = st.as_dict()
+        tuples, edges_raw = sum(sd["tuples"]), sum(sd["edges_raw"])
+        alg_bytes = 80.0 * tuples + 100.0 * edges_raw
+        out = {"workload": f"{n} synthetic pre-aligned CLR reads ({args.tlen} bp templates) vs 8 contigs + 5%-diverged reference, "
+                           f"k={args.pagraph_k}, epsilon=10, -v 2", "read_bases": info["read_bases"], "columns": info["columns"],
+               "vertices": sd["n_vertices"], "solid_kmers": int(len(words) - 1), "tuples": tuples, "edges_raw": edges_raw,
+               "positions": sd["positions"], "edges": sd["edges"], "build_ms": build_ms, "extract_ms": sd["extract_ms"],
+               "join_ms": sd["join_ms"], "launches": sd["launches"], "e2e_ms": e2e_ms,
+               "read_gbp_per_s": info["read_bases"] / (build_ms * 1e-3) / 1e9,
+               "e2e_read_gbp_per_s": info["read_bases"] / (e2e_ms * 1e-3) / 1e9,
+               "algorithmic_GBps": alg_bytes / (build_ms * 1e-3) / 1e9,
+               "d2h_bytes": int(g.ctg.nbytes + g.ref.nbytes + g.count.nbytes + g.edge_to.nbytes + g.edge_step.nbytes + 2 * g.pos_off.nbytes)}
+        job.close()
+        # the CPU beside it: the unmodified reference classes when built here, else the port; one core (-t 1 is the only
+        # deterministic setting of the reference)
+        from oracle import binding
+        t0 = time.perf_counter()
+        if os.path.exists(binding.REF_PAGRAPH_DUMP):
+            subprocess.run([binding.REF_PAGRAPH_DUMP, "1", "solid.bin", "ctg.fasta", "ref.fasta", ".", "c2r.ref", "10", "2", "cpu.txt"],
+                           cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            kind = "reference"
+        else:
+            binding.pagraph_dump(d, "cpu.txt", 10, 2)
+            kind = "port"
+        cpu_s = time.perf_counter() - t0
+        out["cpu"] = {"kind": kind, "cores": 1, "seconds": cpu_s, "read_gbp_per_s": info["read_bases"] / cpu_s / 1e9,
+                      "note": "whole process: file parsing + graph build + dump of the table, same input set"}
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def cbar_guard(st) -> float:
@@ -343,7 +406,13 @@ def main():
                                "candidates); ag2_map_reads = the whole per-read path (seed, extend every candidate, rescue, second pass, "
                                "output choice; -n 10 -b 1), its Gbp/s estimated as DP cells / cells-per-aligned-base of the extend-only run"})
 
-    # ---- roofline of the dominant kernel (xdrop_chains_kernel) ----
+    if rank == 0 and world == 1 and args.pagraph_reads > 0:
+        try:
+            stages["pagraph"] = pagraph_stage(args, local)
+        except Exception as e:  # the headline line must still print
+            stages["pagraph"] = {"error": repr(e)}
+
+    # ---- roofline of the dominant kernel (xdrop_lane_kernel) ----
     peak, peak_src = peaks()
     cbar = st["cells"] / max(1, st["aligned"])
     b_alg = 3.0 * cbar + 3.6                      # bytes per aligned base, SURVEY.md 8(d)

@@ -118,3 +118,46 @@ def test_read_sharded_ranks_cover_the_graph(small):
         job.close()
     got = open(out, "rb").read()
     assert got == want, _explain(got, want)
+
+
+def test_two_gpus_nccl_exchange(small):
+    """Reads sharded over 2 GPUs, NCCL all-to-all of the vertex tuples by owner, all-gather of the merged tables:
+    the dump rank 0 writes equals the reference's.  Needs a 2-GPU box (gpurun --gpus 2)."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from aligngraph2_b200 import build
+    build.build()
+    j = lambda n: os.path.join(small, n)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", "-m", "aligngraph2_b200.pagraph_dist_main", "-k", j("solid.bin"), "-c", j("ctg.fasta"),
+           "-R", j("ref.fasta"), "-p", small, "-a", j("c2r.ref"), "-o", j("dist.txt"), "--epsilon", "10", "-v", "2"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    got = open(j("dist.txt"), "rb").read()
+    want = open(j("graph.txt"), "rb").read()
+    assert got == want, _explain(got, want)
+
+
+def test_synthetic_set_with_gpu_kmer_counter_equals_oracle(tmp_path):
+    """A bigger, generated input set (aligngraph2_b200.synth_pg), solid k-mers from this package's kmer_counter kernels
+    (row B1), k = 12: GPU graph == oracle graph."""
+    from aligngraph2_b200 import pagraph, synth_pg
+    from oracle import binding
+    binding.build(ref=False)
+    d = str(tmp_path)
+    synth_pg.make_input_set(d, 77, 600_000, 1500, tlen=5000, n_ctg=5)
+    words = synth_pg.solid_words_from_reads(d, 12, 0.2, 0)
+    assert words[0] == 12 and len(words) > 1000
+    want = binding.pagraph_dump(d, "orc.txt", eps=10, cov=2)
+    j = lambda n: os.path.join(d, n)
+    job = pagraph.Job(j("solid.bin"), j("ctg.fasta"), j("ref.fasta"), d, j("c2r.ref"))
+    job.load_block(0)
+    st = job.build(pagraph.default_params(10, 2))
+    job.dump(0, j("gpu.txt"))
+    job.close()
+    got = open(j("gpu.txt"), "rb").read()
+    assert got == want, _explain(got, want)
+    assert st.positions > 10000 and st.edges > 10000
