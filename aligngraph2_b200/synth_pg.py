@@ -4,7 +4,7 @@ The reference pipeline gets its three `.ref` alignment files from aligners (meca
 bench sizes that is hours of CPU, so this generator writes the alignments it KNOWS instead: every read is a noisy copy of
 a genome window (the CLR error profile of synth.py), the contigs are genome windows, the reference is a 5 %-diverged copy
 of the genome with recorded edits, and the alignment columns are composed from those edit records.  The files are
-ordinary pagraph inputs (the oracle and the reference binary read them too); the generator is not part of the parity
+ordinary pagraph inputs (the CPU checker and the reference binary read them too); the generator is not part of the parity
 contract.
 """
 from __future__ import annotations
