@@ -5,6 +5,7 @@
 #include "../../include/ag2_b200.h"
 #include "xdrop_device.cuh"
 #include "xdrop_lane.cuh"
+#include "xdrop_pair.cuh"
 #include "index_kernels.cuh"
 #include "map_kernels.cuh"
 #include "kmer_kernels.cuh"
@@ -145,6 +146,17 @@ __global__ void __launch_bounds__(kLaneThreads) xdrop_lane_kernel(LaneArgs g)
     lane_kernel_body(g, sm, tid, scratch);
 }
 
+// Pair path (xdrop_pair.cuh): two directions per thread in packed 16-bit arithmetic, 64 directions in lock step
+// per warp.  The dominant kernel; the lane kernel above restarts the directions it hands over.
+__global__ void __launch_bounds__(kPairThreads, 8) xdrop_pair_kernel(LaneArgs g)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    PairSmem &sm = *reinterpret_cast<PairSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    uint8_t *scratch = g.scratch + (size_t)blockIdx.x * kPairCtaScratch; // the CTA's: traceback of its 128 directions interleaved
+    pair_kernel_body(g, sm, tid, scratch);
+}
+
 // One warp per record: the two directions' workspace areas -> dense strings; fills aln_off.
 __global__ void assemble_kernel(Record *rec, const ExtGeom *geom, const ChainResult *res, const uint32_t *meta,
                                 const int64_t *dense_off, int64_t dense_base, int64_t first, int64_t n, const char *ws_q,
@@ -260,14 +272,15 @@ struct ag2_ctx {
     DevBuf ws_q, ws_t;                  // workspace strings (one chunk of candidates)
     DevBuf out_q, out_t;                // dense output strings
     int64_t out_total = 0;
-    DevBuf tb, tb_wide;
-    DevBuf wide_queue;
+    DevBuf tb, tb_wide, tb_pair;
+    DevBuf wide_queue, lane_queue;
     DevBuf scalars;                     // ChainCounters + work counters + totals
     size_t ws_limit = (size_t)24 << 30; // bytes per workspace string per chunk (resident runs: one chunk, no drain tails)
     size_t ws_limit_streamed = (size_t)3 << 30; // chunk size when results stream to host buffers while the next chunk computes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done = nullptr;
     bool ran = false;
+    int64_t stats_lane_chains = 0;      // directions the pair kernel handed to the lane kernel (last run)
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> chain_events;
@@ -278,8 +291,8 @@ namespace {
 
 struct Scalars {
     ChainCounters ctr;
-    unsigned long long next_fast, next_wide;
-    unsigned int wide_count, pad;
+    unsigned long long next_fast, next_wide, next_pair;
+    unsigned int wide_count, lane_count;
     unsigned long long aligned, columns;
 };
 
@@ -410,7 +423,7 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
                      &ctx->km_out, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
-                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->wide_queue, &ctx->scalars};
+                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->scalars};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->chain_events) {
@@ -535,7 +548,16 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     RESERVE(ctx->ok_len, (size_t)n * 8);
     RESERVE(ctx->dense_off, (size_t)(n + 1) * 8);
     RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
+    RESERVE(ctx->lane_queue, (size_t)n * 2 * 4);
 
+    // pair kernel: the band window of 128 directions per CTA in shared memory
+    int pocc = 0;
+    const size_t pair_smem = sizeof(PairSmem);
+    CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, xdrop_pair_kernel, kPairThreads, pair_smem));
+    if (pocc < 1) pocc = 1;
+    const int pair_grid = ctx->sm_count * pocc;
+    RESERVE(ctx->tb_pair, kPairCtaScratch * (size_t)pair_grid);
     // lane kernel: as many CTAs per SM as shared memory allows (band + target block per thread)
     int occ = 0;
     const size_t lane_smem = sizeof(LaneSmem);
@@ -550,7 +572,10 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
 
     const PackedSeqs sq = seqs_of(ctx);
     Scalars *sc = (Scalars *)ctx->scalars.p;
-    if (fresh_stats) CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+    if (fresh_stats) {
+        CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+        ctx->stats_lane_chains = 0;
+    }
     extend_setup_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(d_cand, n, sq, ctx->n_reads,
                                                                          (ExtGeom *)ctx->geom.p, (int64_t *)ctx->caps.p,
                                                                          (int64_t *)ctx->nmeta.p);
@@ -600,7 +625,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         const int64_t lo = chunks[ci].first, cn = chunks[ci].second - chunks[ci].first;
         set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p,
                                                                            (const int64_t *)ctx->meta_prefix.p, lo, cn);
-        CK(cudaMemsetAsync(&sc->next_fast, 0, 2 * sizeof(unsigned long long) + sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(&sc->next_fast, 0, 3 * sizeof(unsigned long long) + 2 * sizeof(unsigned int), st));
         LaneArgs a = {};
         a.seqs = sq;
         a.cand = d_cand + lo;
@@ -609,21 +634,39 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         a.meta = (uint32_t *)ctx->meta.p;
         a.ws_q = (char *)ctx->ws_q.p;
         a.ws_t = (char *)ctx->ws_t.p;
-        a.scratch = (uint8_t *)ctx->tb.p;
-        a.n_chains = 2 * cn;
-        a.next = &sc->next_fast;
-        a.wide_queue = (int32_t *)ctx->wide_queue.p;
-        a.wide_count = &sc->wide_count;
         a.counters = &sc->ctr;
+        // pair kernel over all directions of the chunk; what it hands over goes to the lane queue
+        LaneArgs pa = a;
+        pa.scratch = (uint8_t *)ctx->tb_pair.p;
+        pa.n_chains = 2 * cn;
+        pa.queue = nullptr;
+        pa.next = &sc->next_pair;
+        pa.wide_queue = (int32_t *)ctx->lane_queue.p;
+        pa.wide_count = &sc->lane_count;
         CK(cudaEventRecord(ctx->chain_events[ci].first, st));
-        xdrop_lane_kernel<<<lane_grid, kLaneThreads, lane_smem, st>>>(a);
+        xdrop_pair_kernel<<<pair_grid, kPairThreads, pair_smem, st>>>(pa);
         CK(cudaEventRecord(ctx->chain_events[ci].second, st));
         CK(cudaGetLastError());
-        // directions that left the lane path (band > 120 columns, or reservation exceeded): wide kernel
-        unsigned int n_wide = 0;
-        CK(cudaMemcpyAsync(&n_wide, &sc->wide_count, sizeof n_wide, cudaMemcpyDeviceToHost, st));
+        unsigned int n_lane = 0, n_wide = 0;
+        CK(cudaMemcpyAsync(&n_lane, &sc->lane_count, sizeof n_lane, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         launches += 2;
+        ctx->stats_lane_chains += n_lane;
+        if (n_lane > 0) {
+            // directions the pair window could not hold (or with a target block under 32 bases): lane kernel, restarted
+            a.scratch = (uint8_t *)ctx->tb.p;
+            a.n_chains = n_lane;
+            a.queue = (const int32_t *)ctx->lane_queue.p;
+            a.next = &sc->next_fast;
+            a.wide_queue = (int32_t *)ctx->wide_queue.p;
+            a.wide_count = &sc->wide_count;
+            xdrop_lane_kernel<<<lane_grid, kLaneThreads, lane_smem, st>>>(a);
+            CK(cudaGetLastError());
+            // directions that left the lane path too (band > 120 columns, or reservation exceeded): wide kernel
+            CK(cudaMemcpyAsync(&n_wide, &sc->wide_count, sizeof n_wide, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            ++launches;
+        }
         if (n_wide > 0) {
             ChainArgs w = {};
             w.seqs = sq;
@@ -688,6 +731,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     s.columns = (int64_t)hs.columns;
     s.launches = (fresh_stats ? 0 : s.launches) + launches;
     if (fresh_stats) s.kernel_ms = 0;
+    s.lane_chains = ctx->stats_lane_chains;
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx->chain_events[ci].first, ctx->chain_events[ci].second));

@@ -94,6 +94,9 @@ struct ChainCounters {
     unsigned long long cells, rows, blocks, interior, wide;
 };
 
+// ASCII of a code 0..3 (ACGT) or 4 ('-'), computed: an indexed read of a string literal is a global load
+__device__ __forceinline__ char code_char(int c) { return (char)(c < 4 ? (0x54474341u >> (8 * c)) & 0xffu : 0x2du); }
+
 __device__ __forceinline__ int get2(const uint32_t *p, int64_t i)
 {
     return (int)((p[i >> 4] >> (2 * (int)(i & 15))) & 3u);
@@ -479,8 +482,8 @@ __device__ bool run_chain(const ChainArgs &g, int64_t chain, WarpSmem &sm, uint8
             const unsigned tm = __ballot_sync(kFull, on && op != kOpGapB);
             const unsigned lt = (1u << lane) - 1u;
             if (on) {
-                const char qc = op != kOpGapA ? "ACGT"[sm.A[qi + __popc(qm & lt)]] : '-';
-                const char tc = op != kOpGapB ? "ACGT"[sm.B[ti + __popc(tm & lt)]] : '-';
+                const char qc = op != kOpGapA ? code_char(sm.A[qi + __popc(qm & lt)]) : '-';
+                const char tc = op != kOpGapB ? code_char(sm.B[ti + __popc(tm & lt)]) : '-';
                 const int64_t pos = forward ? mid + ncols + col : mid - 1 - (ncols + col);
                 g.ws_q[pos] = qc;
                 g.ws_t[pos] = tc;

@@ -60,6 +60,7 @@ struct LaneArgs {
     char *ws_q, *ws_t;
     uint8_t *scratch;        // kLaneScratch bytes per resident thread
     int64_t n_chains;
+    const int32_t *queue;    // nullptr: chains 0..n_chains-1; else chain ids to run
     unsigned long long *next;
     int32_t *wide_queue;
     unsigned int *wide_count;
@@ -117,16 +118,37 @@ __device__ __forceinline__ uint32_t spread_bits16(uint32_t m) // 16 bits -> 16 t
     return x | (x << 1);
 }
 
-// 16 "not upper-case ACGT" bits in extension order (for the reverse strand's complement)
+// 16 "not upper-case ACGT" bits in extension order (for the reverse strand's complement): bit i = position p0 + dir * i,
+// positions below 0 read as 0
+__device__ __forceinline__ uint32_t load16_bits(const uint32_t *bits, int64_t s) // bit j = position s + j
+{
+    const int64_t w = s >> 5;
+    const int sh = (int)(s & 31);
+    uint32_t r = bits[w] >> sh;
+    if (sh > 16) r |= bits[w + 1] << (32 - sh);
+    return r & 0xffffu;
+}
 __device__ __forceinline__ uint32_t fetch16_bits(const uint32_t *bits, int64_t off, int64_t p0, int dir)
 {
-    uint32_t r = 0;
-    // rare path (reverse strand only): 16 single-bit reads
-    for (int i = 0; i < 16; ++i) {
-        const int64_t p = p0 + (int64_t)dir * i;
-        if (p >= 0) r |= (uint32_t)get1(bits, off + p) << i;
+    if (dir > 0) {
+        if (p0 >= 0) return load16_bits(bits, off + p0);
+        if (p0 <= -16) return 0;
+        return load16_bits(bits, off) << (int)(-p0) & 0xffffu;
     }
-    return r;
+    if (p0 < 0) return 0;
+    int64_t s = p0 - 15;
+    int drop = 0;
+    if (s < 0) {
+        drop = (int)(-s);
+        s = 0;
+    }
+    const uint32_t x = load16_bits(bits, off + s);        // bit j = position s + j
+    uint32_t r = x;                                        // reverse the 16 bits
+    r = ((r >> 1) & 0x5555u) | ((r & 0x5555u) << 1);
+    r = ((r >> 2) & 0x3333u) | ((r & 0x3333u) << 2);
+    r = ((r >> 4) & 0x0f0fu) | ((r & 0x0f0fu) << 4);
+    r = ((r >> 8) & 0x00ffu) | ((r & 0x00ffu) << 8);      // bit k = position s + 15 - k
+    return r >> drop;                                      // bit i = position p0 - i
 }
 
 struct LaneBlock {
@@ -270,8 +292,8 @@ __device__ int lane_walk(const LaneSmem &sm, int tid, const uint32_t *__restrict
             m = (qc == tc) ? m + 1 : 0;
             if (m == kTailMatch) scanning = false;
         }
-        wq[n] = "ACGT-"[qc];
-        wt[n] = "ACGT-"[tc];
+        wq[n] = code_char(qc);
+        wt[n] = code_char(tc);
         ++n;
     }
     qcnt = q;
@@ -326,6 +348,36 @@ __device__ __forceinline__ void lane_start_chain(const LaneArgs &g, int64_t chai
     s.meta_end = s.meta + (forward ? s.ge.nmetaR : s.ge.nmetaL);
 }
 
+// align_ex's bookkeeping after one block's walk (:334-357): metadata word, consumed counts, next block origin.
+// Returns 0 = chain continues, 1 = chain finished.
+__device__ __forceinline__ int lane_block_tail(const LaneArgs &g, LaneChain &s, int qblk, int tblk, bool last_block, int ae, int be,
+                                               int nops, int qcnt, int tcnt, int acnt, bool trim_ok, int first_op, int op_after)
+{
+    const bool full_map = (qblk - ae <= kFullMapSlack) || (tblk - be <= kFullMapSlack); // (:334-335)
+    const bool stop = !full_map || last_block;
+    int skip = 0;
+    if (!stop) {
+        if (!trim_ok) { // (:349) the block's columns are dropped and the direction ends
+            g.meta[s.meta + s.nblocks++] = (uint32_t)nops | ((uint32_t)nops << 16);
+            return 1;
+        }
+        skip = acnt;
+    }
+    g.meta[s.meta + s.nblocks++] = (uint32_t)nops | ((uint32_t)skip << 16);
+    s.seg += nops;
+    if (nops - skip > 0) {
+        s.last_op = skip ? op_after : first_op;
+        s.ncols += nops - skip;
+        s.qcons += skip ? ae - qcnt : ae;
+        s.tcons += skip ? be - tcnt : be;
+    }
+    if (stop) return 1;
+    s.qidx += ae - qcnt; // (:354-355)
+    s.tidx += be - tcnt;
+    return 0;
+}
+
+
 // One block of align_ex for the lane's chain.  Returns 0 = chain continues, 1 = chain finished,
 // 2 = hand the chain to the wide path.
 __device__ int lane_block(const LaneArgs &g, LaneChain &s, LaneSmem &sm, int tid, uint8_t *scratch)
@@ -373,28 +425,7 @@ __device__ int lane_block(const LaneArgs &g, LaneChain &s, LaneSmem &sm, int tid
     bool trim_ok;
     const int nops = lane_walk(sm, tid, qcodes, tb, ae, be, g.ws_q + s.seg, g.ws_t + s.seg, cap, qcnt, tcnt, acnt, trim_ok,
                                first_op, op_after);
-    const bool full_map = (qblk - ae <= kFullMapSlack) || (tblk - be <= kFullMapSlack); // (:334-335)
-    const bool stop = !full_map || last_block;
-    int skip = 0;
-    if (!stop) {
-        if (!trim_ok) { // (:349) the block's columns are dropped and the direction ends
-            g.meta[s.meta + s.nblocks++] = (uint32_t)nops | ((uint32_t)nops << 16);
-            return 1;
-        }
-        skip = acnt;
-    }
-    g.meta[s.meta + s.nblocks++] = (uint32_t)nops | ((uint32_t)skip << 16);
-    s.seg += nops;
-    if (nops - skip > 0) {
-        s.last_op = skip ? op_after : first_op;
-        s.ncols += nops - skip;
-        s.qcons += skip ? ae - qcnt : ae;
-        s.tcons += skip ? be - tcnt : be;
-    }
-    if (stop) return 1;
-    s.qidx += ae - qcnt; // (:354-355)
-    s.tidx += be - tcnt;
-    return 0;
+    return lane_block_tail(g, s, qblk, tblk, last_block, ae, be, nops, qcnt, tcnt, acnt, trim_ok, first_op, op_after);
 }
 
 // Body of xdrop_lane_kernel: a thread keeps pulling directions from the queue and advances its
@@ -409,7 +440,7 @@ __device__ void lane_kernel_body(const LaneArgs &g, LaneSmem &sm, int tid, uint8
         if (s.chain < 0 && !drained) {
             const unsigned long long t = atomicAdd(g.next, 1ull);
             if ((int64_t)t < g.n_chains) {
-                lane_start_chain(g, (int64_t)t, s);
+                lane_start_chain(g, g.queue ? (int64_t)g.queue[t] : (int64_t)t, s);
                 if (!s.ge.valid) {
                     const ChainResult out = {0, 0, 0, -1, 0, 0, 0, 0};
                     g.res[s.chain] = out;

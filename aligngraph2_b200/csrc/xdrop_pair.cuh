@@ -1,0 +1,631 @@
+// xdrop_pair.cuh -- the "pair" path of the X-drop extension: every thread runs TWO extension directions at once, one
+// in each 16-bit half of its registers, and all 64 directions of a warp advance through the DP in lock step without a
+// single data-dependent branch inside a row.
+//
+// What is computed is xdrop_align (MC/xdrop_gapalign.cpp:11-213) cell by cell, in the reference's row-major order:
+// the running best, the X-drop test against it, the un-decayed horizontal gap across pruned cells (:109-112) and the
+// stale vertical gap of a pruned interior cell (:111) are kept as they are.  What is designed is the form:
+//
+//   * scores are binary16 integers offset by +1024 (exact up to 2048; a block scores <= 720): HADD2 on the FMA pipe,
+//     HMNMX2 / HSET2 (compare -> 16-bit mask) / LOP3 on the ALU pipe, two directions per instruction (h2ops.cuh);
+//   * one 16-bit word v per column holds the column state: v > 0 live (h = v, e = v - 1, the only case the reference's
+//     parameters produce, :58-59, :122/:135, :148-149), v < 0 pruned inside the band (h = MIN, e = |v| - 1 kept), v = 0
+//     outside the band or the sentinel column (:161-162).  Everything at or below zero is "MIN": real scores are
+//     >= 1024 - 62, and MIN only ever takes part in comparisons it loses;
+//   * the band lives in a window of kPairSlots columns [base, base + kPairSlots) in shared memory, base a multiple of
+//     8 that follows the band's first column (checked every 4 rows); a row is a loop over groups of 8 slots, every slot
+//     the same straight-line code.  Cells left of the band, right of it, the row-end extension (:147-153) and the
+//     sentinel are not special cases: a slot is a "standard" cell when it is below nD = last live slot of the previous
+//     row + 2, an "extension" cell (no diagonal, no vertical gap, live only if its left neighbour is) above it, and the
+//     leading cells that leave the band (:110) are cleared by a running mask;
+//   * the reference never lets the band reach column N (:147 `b_size < N`): columns >= N can become live here, but the
+//     target codes from position N - 1 on are forced to mismatch, so those cells stay strictly below the best score,
+//     feed nothing back (the recurrence only looks left and up) and are clipped from the band end every row;
+//   * traceback: 4 bits per cell as on the lane path, one 32-bit word per 8 slots, rows relative to the window base;
+//     the rows at which the base moved are logged for the walk.
+//
+// A direction this path cannot hold (window overflow, a target block shorter than 32, reservation exceeded) is handed
+// to the lane kernel (xdrop_lane.cuh), which restarts it; behind that stands the wide kernel.
+#pragma once
+
+#include "h2ops.cuh"
+#include "xdrop_lane.cuh"
+
+namespace ag2 {
+
+constexpr int kPairThreads = 64;                   // threads per CTA (128 directions)
+constexpr int kPairSlots = 88;                     // window width in columns (band + lead fits in 99.98 % of the blocks of CLR reads)
+constexpr int kPairGroups = kPairSlots / 8;
+constexpr int kPairQuads = (kPairGroups + 3) / 4;  // a traceback row = kPairQuads pieces of 16 bytes (4 groups = 32 columns each)
+constexpr int kPairMainGroups = 8;                 // the walk fetches the first 8 groups of a row (64 columns); the rest on demand
+constexpr int kPairQuadStride = 2 * kPairThreads * 16; // the CTA's 128 directions side by side: a warp stores 512 contiguous bytes
+constexpr int kPairRowStride = kPairQuads * kPairQuadStride;
+constexpr size_t kPairTbCta = (size_t)(kMaxBlk + 2) * kPairRowStride; // traceback of one CTA
+constexpr int kPairLogBytes = 256;                 // rows at which the window base moved (u16), <= 92 entries
+constexpr int kPairSeqBytes = 192;                 // kSeqWords (46) words, padded
+constexpr int kPairAux = kPairLogBytes + 2 * kPairSeqBytes; // per direction
+constexpr size_t kPairCtaScratch = kPairTbCta + (size_t)2 * kPairThreads * kPairAux;
+constexpr int kPairOff = 1024;                     // score offset
+constexpr int kPairMinN = 32;                      // shortest target block this path takes
+
+struct PairSmem {
+    uint32_t v[kPairSlots / 4][kPairThreads][4];   // slot j of both directions: v[j >> 2][tid][j & 3]
+    uint32_t tg[kPairGroups][kPairThreads];        // 8 target codes of group g (2 bits each), per half
+    uint32_t ph[kPairGroups][kPairThreads];        // forced-mismatch bits (even bit positions), per half
+};
+
+// Views into the CTA's scratch for one direction (hh = 0 / 1: low / high half of thread tid).  Traceback: piece q of row a
+// is the 16 bytes at tb + (a * kPairQuads + q) * kPairQuadStride -- the directions of a warp are adjacent, so the lock-step DP
+// writes whole 512-byte runs.
+struct PairScratch {
+    uint8_t *tb;
+    uint16_t *log;
+    uint32_t *qcodes;
+    uint32_t *tcodes;
+};
+__device__ __forceinline__ PairScratch pair_scratch(uint8_t *cta, int tid, int hh)
+{
+    PairScratch s;
+    const int col = hh * kPairThreads + tid;
+    s.tb = cta + (size_t)col * 16;
+    uint8_t *aux = cta + kPairTbCta + (size_t)col * kPairAux;
+    s.log = reinterpret_cast<uint16_t *>(aux);
+    s.qcodes = reinterpret_cast<uint32_t *>(aux + kPairLogBytes);
+    s.tcodes = reinterpret_cast<uint32_t *>(aux + kPairLogBytes + kPairSeqBytes);
+    return s;
+}
+
+// 8 two-bit target codes at positions p0 .. p0+7 (p0 a multiple of 8), and the forced-mismatch bits for p >= limit
+__device__ __forceinline__ uint32_t pair_tg16(const uint32_t *tcodes, int p0)
+{
+    const int w = p0 >> 4;
+    if (w >= kSeqWords) return 0;
+    return (tcodes[w] >> (16 * ((p0 >> 3) & 1))) & 0xffffu;
+}
+__device__ __forceinline__ uint32_t pair_ph16(int p0, int limit)
+{
+    const int n = min(max(limit - p0, 0), 8);
+    return (0x5555u << (2 * n)) & 0xffffu;
+}
+
+// Shared-memory loads the compiler must leave where they are written (volatile): the next group's operands are requested
+// before the current group's arithmetic, a whole group ahead of their use.
+__device__ __forceinline__ void pair_lds4(const uint32_t *p, uint32_t (&d)[4])
+{
+#ifdef AG2_EMU
+    d[0] = p[0]; d[1] = p[1]; d[2] = p[2]; d[3] = p[3];
+#else
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+                 : "r"((unsigned)__cvta_generic_to_shared(p)));
+#endif
+}
+__device__ __forceinline__ uint32_t pair_lds1(const uint32_t *p)
+{
+#ifdef AG2_EMU
+    return *p;
+#else
+    uint32_t d;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return d;
+#endif
+}
+
+__device__ __forceinline__ void pair_store16(uint8_t *p, const uint32_t (&w)[4])
+{
+#ifdef AG2_EMU
+    memcpy(p, w, 16);
+#else
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+#endif
+}
+
+struct PairCarry {
+    h2 diag, hgap, best, thr, be, lastj;
+    uint32_t Ms, Mlp, Mlead, cnt;
+};
+
+// One DP cell of both directions.  K = slot within the group.
+template <int K>
+__device__ __forceinline__ void pair_slot(uint32_t &v, PairCarry &c, const h2 nDg, const h2 Jg, const uint32_t mmw, uint32_t &acc)
+{
+    constexpr int kq = K & 3;
+    constexpr uint32_t C1 = 0x00010001u << (4 * kq), C3 = 0x00030003u << (4 * kq), C4 = 0x00040004u << (4 * kq),
+                       CF = 0x000f000fu << (4 * kq);
+    const h2 Jc = h2_add(Jg, H2C(K));
+    const h2 mt = ((mmw << (15 - 2 * K)) & kH2Sign) ^ H2C(1);
+    const h2 nd = h2_add(v, mt);                           // h(a-1, b) + match(a, b+1's target base): the next slot's diagonal
+    const uint32_t Ms = c.Ms;                              // this slot is a standard cell (column < nD)
+    const uint32_t Me = h2_gt(nDg, H2C(K + 1));            // the next one is: this slot's vertical gap is valid
+    c.Ms = Me;
+    const h2 e = h2_add(h2_abs(v), H2C(-1)) & Me;          // e(a-1, b)
+    const h2 dg = c.diag & Ms;                             // h(a-1, b-1) + match
+    const h2 m1 = h2_max(dg, e);
+    const h2 sc = h2_max(m1, c.hgap);                      // (:95-107)
+    const uint32_t Ml = h2_ge(sc, c.thr) & (Ms | c.Mlp);   // not pruned (:109); extension cells need a live left neighbour
+    const uint32_t P1 = h2_lt(dg, e);                      // SCRIPT_GAP_IN_B beats the diagonal
+    const uint32_t P2 = h2_lt(m1, c.hgap);                 // SCRIPT_GAP_IN_A beats both
+    const uint32_t PA = h2_eq(e, sc);                      // kExtA (:121-126)
+    const uint32_t PB = h2_eq(c.hgap, sc);                 // kExtB (:129-133)
+    const uint32_t tA = (P2 & C1) | (P1 & ~P2 & ~C1);      // bit 0: gap in A, bit 1: gap in B
+    const uint32_t tB = ((PA & C4) | (PB & ~C4)) & Ml & Ms; // bits 2,3: flags, unpruned standard cells only
+    acc |= ((tA & C3) | (tB & ~C3)) & CF;
+    const uint32_t Mnew = h2_gt(sc, c.best);
+    c.best = h2_max(c.best, sc);
+    c.thr = h2_add(c.best, H2C(-kXdrop));
+    c.be = h2_sel(Mnew, Jc, c.be);
+    c.lastj = h2_sel(Ml, Jc, c.lastj);
+    c.hgap = h2_sel(Ml, h2_add(sc, H2C(-1)), c.hgap);      // not decayed across pruned cells
+    c.Mlead &= ~Ml;                                        // still in the run of leading pruned cells (:110)
+    c.cnt = vadd2(c.cnt, c.Mlead);
+    v = h2_sel(Ml, sc, (v | kH2Sign) & ~c.Mlead);          // live / pruned inside the band / left the band
+    c.diag = nd;
+    c.Mlp = Ml;
+}
+
+struct PairIO {
+    int M[2], N[2];          // block sizes per direction (M = 0: no block)
+    // results
+    int ae[2], be[2], nshift[2], bail[2];
+    unsigned cells[2], rows[2];
+};
+
+// xdrop_align forward pass of both directions of the thread; the warp runs max(M) rows.
+__device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, const PairScratch &s1, PairIO &io)
+{
+    const int M0 = io.M[0], M1 = io.M[1], N0 = io.N[0], N1 = io.N[1];
+    // row 0 (:53-67): columns 0..30 hold -j (N >= 32 here); the band ends at column 30, no sentinel yet
+    {
+        const uint32_t on = (M0 > 0 ? 0xffffu : 0u) | (M1 > 0 ? 0xffff0000u : 0u);
+        for (int q = 0; q < kPairSlots / 4; ++q) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = 4 * q + i;
+                sm.v[q][tid][i] = j <= kXdrop ? h2_from_ints(kPairOff - j, kPairOff - j) & on : 0u;
+            }
+        }
+        for (int g = 0; g < kPairGroups; ++g) {
+            sm.tg[g][tid] = pair_tg16(s0.tcodes, 8 * g) | (pair_tg16(s1.tcodes, 8 * g) << 16);
+            sm.ph[g][tid] = pair_ph16(8 * g, N0 - 1) | (pair_ph16(8 * g, N1 - 1) << 16);
+        }
+    }
+    const int rows_max = __reduce_max_sync(kFull, max(M0, M1));
+    const h2 Mh = h2_from_ints(M0, M1);
+    int base0 = 0, base1 = 0, nsh0 = 0, nsh1 = 0;
+    h2 nrelm1 = h2_from_ints(N0 - 1, N1 - 1);      // N - 1 - base
+    h2 nD = h2_from_ints(M0 > 0 ? kXdrop + 1 : 0, M1 > 0 ? kXdrop + 1 : 0);
+    h2 frelh = 0, ah = 0, ae = 0;
+    uint32_t alive = (M0 > 0 ? 0xffffu : 0u) | (M1 > 0 ? 0xffff0000u : 0u);
+    PairCarry c;
+    c.best = H2C(kPairOff);
+    c.thr = H2C(kPairOff - kXdrop);
+    c.be = 0;
+    unsigned cells0 = 0, cells1 = 0, rows2 = 0;
+    uint32_t aw0 = 0, aw1 = 0, an0 = s0.qcodes[0], an1 = s1.qcodes[0], bail = 0;
+
+    for (int a = 1; a <= rows_max; ++a) {
+        if ((a & 3) == 0) {
+            // move the window of a direction whose band start has advanced by 8 columns or more
+            const uint32_t Msh = h2_ge(frelh, H2C(8));
+            if (__any_sync(kFull, Msh != 0)) {
+                for (int q = 0; q < kPairSlots / 4; ++q) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t up = q + 2 < kPairSlots / 4 ? sm.v[q + 2][tid][i] : 0u;
+                        sm.v[q][tid][i] = h2_sel(Msh, up, sm.v[q][tid][i]);
+                    }
+                }
+                if (Msh & 0xffffu) {
+                    base0 += 8;
+                    s0.log[nsh0++] = (uint16_t)a;
+                }
+                if (Msh >> 16) {
+                    base1 += 8;
+                    s1.log[nsh1++] = (uint16_t)a;
+                }
+                for (int g = 0; g < kPairGroups; ++g) {
+                    uint32_t tn, pn;
+                    if (g + 1 < kPairGroups) {
+                        tn = sm.tg[g + 1][tid];
+                        pn = sm.ph[g + 1][tid];
+                    } else {
+                        tn = pair_tg16(s0.tcodes, base0 + 8 * g) | (pair_tg16(s1.tcodes, base1 + 8 * g) << 16);
+                        pn = pair_ph16(base0 + 8 * g, N0 - 1) | (pair_ph16(base1 + 8 * g, N1 - 1) << 16);
+                    }
+                    sm.tg[g][tid] = h2_sel(Msh, tn, sm.tg[g][tid]);
+                    sm.ph[g][tid] = h2_sel(Msh, pn, sm.ph[g][tid]);
+                }
+                const h2 m8 = Msh & H2C(-8);
+                frelh = h2_add(frelh, m8);
+                nD = h2_add(nD, m8);
+                nrelm1 = h2_add(nrelm1, m8);
+                c.be = h2_add(c.be, m8);
+            }
+        }
+        // row start
+        if (((a - 1) & 15) == 0) { // next 16 query codes: fetched 16 rows ago, the ones after them are requested now
+            const int w = ((a - 1) >> 4) + 1;
+            aw0 = an0;
+            aw1 = an1;
+            an0 = w < kSeqWords ? s0.qcodes[w] : 0u;
+            an1 = w < kSeqWords ? s1.qcodes[w] : 0u;
+        }
+        const uint32_t acrep = ((aw0 & 3u) * 0x5555u) | ((aw1 & 3u) * 0x55550000u);
+        aw0 >>= 2;
+        aw1 >>= 2;
+        ah = h2_add(ah, H2C(1));
+        const uint32_t run = h2_le(ah, Mh) & alive;
+        if (!__any_sync(kFull, run != 0)) break;
+        {   // counters: cells of this row = band end - band start (:84), rows
+            const h2 wdt = h2_add(h2_min(nD, h2_add(nrelm1, H2C(1))), frelh ^ kH2Sign) & run;
+            const uint32_t wi = h2_add(wdt, H2C(1024)) & 0x03ff03ffu;
+            cells0 += wi & 0xffffu;
+            cells1 += wi >> 16;
+            rows2 = vadd2(rows2, run & 0x00010001u);
+        }
+        const h2 nDe = nD & run;
+        const h2 best0 = c.best;
+        c.diag = 0;
+        c.hgap = 0;
+        c.Mlead = 0xffffffffu;
+        c.Mlp = 0;
+        c.cnt = 0;
+        c.lastj = H2C(-1);
+        c.Ms = h2_gt(nDe, 0u);
+        h2 Jg = 0, nDg = nDe;
+        uint8_t *row0 = s0.tb + (size_t)a * kPairRowStride, *row1 = s1.tb + (size_t)a * kPairRowStride;
+        uint32_t t0[4] = {0, 0, 0, 0}, t1[4] = {0, 0, 0, 0}; // traceback words of the current piece (4 groups) per direction
+        // groups that hold standard cells of some direction of the warp run without asking; after them one group at a
+        // time while a direction still has a live cell to extend from (:147-153)
+        int g_std;
+        {
+            const int n0 = h2_lo_int(nDe), n1 = h2_hi_int(nDe);
+            g_std = min(__reduce_max_sync(kFull, (max(n0, n1) + 7) >> 3), kPairGroups);
+        }
+        int g = 0;
+        bool more = g_std > 0;
+        // operands of the next group are fetched from shared memory while the current one computes
+        uint32_t va[4], vb[4], tgw, phw;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            va[i] = sm.v[0][tid][i];
+            vb[i] = sm.v[1][tid][i];
+        }
+        tgw = sm.tg[0][tid];
+        phw = sm.ph[0][tid];
+        while (more) {
+            const int gn = min(g + 1, kPairGroups - 1);
+            uint32_t na[4], nb[4];
+            pair_lds4(&sm.v[2 * gn][tid][0], na);
+            pair_lds4(&sm.v[2 * gn + 1][tid][0], nb);
+            const uint32_t ntg = pair_lds1(&sm.tg[gn][tid]), nph = pair_lds1(&sm.ph[gn][tid]);
+            const uint32_t x = tgw ^ acrep;
+            const uint32_t mmw = x | (x >> 1) | phw; // bit 2k of each half: slot k mismatches
+            uint32_t acc0 = 0, acc1 = 0;
+            pair_slot<0>(va[0], c, nDg, Jg, mmw, acc0);
+            pair_slot<1>(va[1], c, nDg, Jg, mmw, acc0);
+            pair_slot<2>(va[2], c, nDg, Jg, mmw, acc0);
+            pair_slot<3>(va[3], c, nDg, Jg, mmw, acc0);
+            pair_slot<4>(vb[0], c, nDg, Jg, mmw, acc1);
+            pair_slot<5>(vb[1], c, nDg, Jg, mmw, acc1);
+            pair_slot<6>(vb[2], c, nDg, Jg, mmw, acc1);
+            pair_slot<7>(vb[3], c, nDg, Jg, mmw, acc1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                sm.v[2 * g][tid][i] = va[i];
+                sm.v[2 * g + 1][tid][i] = vb[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                t0[i] = t0[i + 1];
+                t1[i] = t1[i + 1];
+            }
+            t0[3] = (acc0 & 0xffffu) | (acc1 << 16);
+            t1[3] = (acc0 >> 16) | (acc1 & 0xffff0000u);
+            ++g;
+            if ((g & 3) == 0) { // a piece is complete: one 16-byte store per direction, coalesced over the warp
+                pair_store16(row0 + (size_t)((g >> 2) - 1) * kPairQuadStride, t0);
+                pair_store16(row1 + (size_t)((g >> 2) - 1) * kPairQuadStride, t1);
+            }
+            Jg = h2_add(Jg, H2C(8));
+            nDg = h2_add(nDg, H2C(-8));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                va[i] = na[i];
+                vb[i] = nb[i];
+            }
+            tgw = ntg;
+            phw = nph;
+            if (g < g_std) continue;
+            more = __any_sync(kFull, (c.Ms | c.Mlp) != 0);
+            if (g >= kPairGroups) break;
+        }
+        if (g & 3) { // the row's last, partial piece
+            for (int r = g & 3; r < 4; ++r) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    t0[i] = t0[i + 1];
+                    t1[i] = t1[i + 1];
+                }
+            }
+            pair_store16(row0 + (size_t)(g >> 2) * kPairQuadStride, t0);
+            pair_store16(row1 + (size_t)(g >> 2) * kPairQuadStride, t1);
+        }
+        if (more) bail |= c.Ms | c.Mlp; // the window is too narrow for this direction
+        // row end (:142-164): the next band ends one past the last live cell (the sentinel), clipped to column N - 1
+        const uint32_t any_live = h2_ge(c.lastj, 0u);
+        alive &= any_live | ~run;      // every cell pruned: the reference leaves the loop (:142)
+        nD = h2_sel(run, h2_add(h2_min(c.lastj, nrelm1), H2C(2)), nD);
+        frelh = h2_sel(run, h2_add(vadd2(vadd2(~c.cnt, 0x00010001u), H2C(1024)), H2C(-1024)), frelh); // -cnt leading cells left the band
+        ae = h2_sel(h2_ne(c.best, best0), ah, ae);
+    }
+    io.ae[0] = h2_lo_int(ae);
+    io.ae[1] = h2_hi_int(ae);
+    io.be[0] = base0 + h2_lo_int(c.be);
+    io.be[1] = base1 + h2_hi_int(c.be);
+    io.nshift[0] = nsh0;
+    io.nshift[1] = nsh1;
+    io.bail[0] = (bail & 0xffffu) != 0;
+    io.bail[1] = (bail >> 16) != 0;
+    io.cells[0] = cells0;
+    io.cells[1] = cells1;
+    io.rows[0] = rows2 & 0xffffu;
+    io.rows[1] = rows2 >> 16;
+}
+
+// 16-byte global -> shared copy that does not pass through registers (LDGSTS); per-thread completion
+__device__ __forceinline__ void pair_copy16_async(uint32_t *smem_dst, const uint8_t *gmem_src)
+{
+#ifdef AG2_EMU
+    memcpy(smem_dst, gmem_src, 16);
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void pair_copy_wait()
+{
+#ifndef AG2_EMU
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
+constexpr int kPairWalkRows = (kPairSlots / 4) / (kPairMainGroups / 4); // traceback rows per batch: what the band window holds
+static_assert(kPairMainGroups % 4 == 0 && kPairGroups <= 4 * kPairQuads && kPairWalkRows >= 4, "walk batches");
+
+// Traceback (:170-210) over the pair layout: row a holds the nibbles of columns base(a) .. base(a) + kPairSlots - 1, base(a) =
+// 8 x (number of logged window moves at rows <= a).  Otherwise lane_walk.  The rows live in HBM (the scratch of all resident
+// directions is far larger than L2) and a step depends on the previous one, so the walk fetches kPairWalkRows whole rows at a
+// time with asynchronous copies into the thread's band window, which is idle during the walk.  Called by the whole warp
+// (`active` = this lane has a direction to walk): the fetches are issued by all lanes together, then every lane steps through
+// its own batch -- a lane-private fetch loop would serialise the warp.
+__device__ int pair_walk(PairSmem &sm, int tid, uint8_t *cta_scratch, int hh, bool active, int nshift, int ae, int be, char *wq, char *wt,
+                         int cap, int &qcnt, int &tcnt, int &acnt, bool &trim_ok, int &first_op, int &op_after_trim)
+{
+    const PairScratch ps = pair_scratch(cta_scratch, tid, hh); // derived from register-held values, nothing read from local memory
+    int a = ae, b = be, n = 0, cur = kOpSub;
+    int m = 0, q = 0, t = 0, ac = 0;
+    bool scanning = true;
+    first_op = -1;
+    op_after_trim = -1;
+    // The block's codes and the window-move log are read one word AHEAD of the walk (it only moves towards the origin):
+    // the lanes of a warp cross word boundaries at different steps, and a load consumed right away would stall all of
+    // them for a memory latency at almost every step.
+    int qi = min(max(a - 1, 0) >> 4, kSeqWords - 1), ti = min(max(b - 1, 0) >> 4, kSeqWords - 1);
+    uint32_t qwv = 0, twv = 0, qwn = 0, twn = 0;
+    int ns = nshift;
+    int ns_row = 0, ns_next = 0; // rows of the last two window moves at or below the walk
+    if (active) {
+        qwv = ps.qcodes[qi];
+        twv = ps.tcodes[ti];
+        qwn = qi > 0 ? ps.qcodes[qi - 1] : 0u;
+        twn = ti > 0 ? ps.tcodes[ti - 1] : 0u;
+        ns_row = ns > 0 ? (int)ps.log[ns - 1] : 0;
+        ns_next = ns > 1 ? (int)ps.log[ns - 2] : 0;
+    }
+    bool walking = active && (a > 0 || b > 0) && n < cap;
+    for (;;) {
+        if (!__any_sync(kFull, walking)) break;
+        int a_lo = a;
+        if (walking && a > 0) { // fetch rows a_lo .. a
+            a_lo = max(1, a - (kPairWalkRows - 1));
+            const uint8_t *src = ps.tb + (size_t)a_lo * kPairRowStride;
+            const int nchunks = (a - a_lo + 1) * (kPairMainGroups / 4);
+            for (int c = 0; c < nchunks; c += kPairMainGroups / 4) {
+#pragma unroll
+                for (int q = 0; q < kPairMainGroups / 4; ++q) pair_copy16_async(&sm.v[c + q][tid][0], src + (size_t)q * kPairQuadStride);
+                src += kPairRowStride;
+            }
+        }
+        pair_copy_wait();
+        while (walking && (a == 0 || a >= a_lo)) {
+            int cell = kOpGapA; // row 0 is all SCRIPT_GAP_IN_A (:61)
+            if (a > 0) {
+                while (ns_row > a) {
+                    --ns;
+                    ns_row = ns_next;
+                    ns_next = ns > 1 ? (int)ps.log[ns - 2] : 0;
+                }
+                const int slot = b - 8 * ns, w = slot >> 3;
+                uint32_t word;
+                if (w < kPairMainGroups) {
+                    const int f = (a - a_lo) * kPairMainGroups + w;
+                    word = sm.v[f >> 2][tid][f & 3];
+                } else { // far right of the window: not part of the fetched rows
+                    word = *reinterpret_cast<const uint32_t *>(ps.tb + (size_t)a * kPairRowStride + (size_t)(w >> 2) * kPairQuadStride + 4 * (w & 3));
+                }
+                cell = (int)((word >> (4 * (slot & 7))) & 15u);
+            }
+            int nxt = cell & 3;
+            if (cur == kOpGapA && (cell & kExtA)) nxt = kOpGapA;
+            if (cur == kOpGapB && (cell & kExtB)) nxt = kOpGapB;
+            cur = nxt;
+            if (cur != kOpGapA) --a;
+            if (cur != kOpGapB) --b;
+            int qc = 4, tc = 4;
+            if (cur != kOpGapA) {
+                if ((a >> 4) != qi) { // a moved into the word below: take the prefetched one, fetch the next
+                    qi = a >> 4;
+                    qwv = qwn;
+                    qwn = qi > 0 ? ps.qcodes[qi - 1] : 0u;
+                }
+                qc = (int)((qwv >> (2 * (a & 15))) & 3u);
+            }
+            if (cur != kOpGapB) {
+                if ((b >> 4) != ti) {
+                    ti = b >> 4;
+                    twv = twn;
+                    twn = ti > 0 ? ps.tcodes[ti - 1] : 0u;
+                }
+                tc = (int)((twv >> (2 * (b & 15))) & 3u);
+            }
+            if (n == 0) first_op = cur;
+            if (!scanning && op_after_trim < 0) op_after_trim = cur;
+            if (scanning) { // trim_mismatch_end scans from the END of the block's alignment = walk start
+                ++ac;
+                if (cur != kOpGapA) ++q;
+                if (cur != kOpGapB) ++t;
+                m = (qc == tc) ? m + 1 : 0;
+                if (m == kTailMatch) scanning = false;
+            }
+            wq[n] = code_char(qc);
+            wt[n] = code_char(tc);
+            ++n;
+            walking = (a > 0 || b > 0) && n < cap;
+        }
+    }
+    qcnt = q;
+    tcnt = t;
+    acnt = ac;
+    trim_ok = !scanning && (n - 1 - ac) > 0;
+    return n;
+}
+
+struct PairBlk {
+    int qblk, tblk;
+    bool last_block;
+};
+
+// retrieve_next_aln_block (MC/gapalign.cpp:9-45) + staging of the block's codes in extension order
+__device__ void pair_prepare(const LaneArgs &g, const LaneChain &s, const PairScratch &ps, PairBlk &blk)
+{
+    const int qleft = s.qsize - s.qidx, tleft = s.tsize - s.tidx;
+    if (qleft < kBlk + kBlkSlack || tleft < kBlk + kBlkSlack) {
+        blk.qblk = min(qleft, stretch_0p2(tleft));
+        blk.tblk = min(tleft, stretch_0p2(qleft));
+        blk.last_block = true;
+    } else {
+        blk.qblk = kBlk;
+        blk.tblk = kBlk;
+        blk.last_block = false;
+    }
+    const int qw = (blk.qblk + 15) >> 4, tw = (blk.tblk + 16) >> 4;
+    const int qdir = s.c.strand == 0 ? s.inc : -s.inc;
+    for (int w = 0; w < qw; ++w) {
+        const int p = s.q0 + s.inc * (s.qidx + 16 * w);
+        const int64_t fp = s.c.strand == 0 ? p : (int64_t)s.rlen - 1 - p;
+        uint32_t v = fetch16(g.seqs.reads2, s.roff, s.rlen, fp, qdir);
+        if (s.c.strand != 0) v ^= ~spread_bits16(fetch16_bits(g.seqs.reads_irr, s.roff, fp, qdir));
+        ps.qcodes[w] = v;
+    }
+    for (int w = 0; w < tw && w < kSeqWords; ++w)
+        ps.tcodes[w] = fetch16(g.seqs.ref2, 0, g.seqs.ref_len, s.t0 + (int64_t)s.inc * (s.tidx + 16 * w), s.inc);
+}
+
+// Body of xdrop_pair_kernel.  Every thread holds two directions; the warp advances all of them by one block per round
+// (stage -> pair_dp in lock step -> per direction: walk and align_ex's bookkeeping), refilling finished ones from the queue.
+// g.wide_queue / g.wide_count receive the directions handed to the lane kernel.
+__device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8_t *scratch)
+{
+    LaneChain s[2];
+    s[0].chain = s[1].chain = -1;
+    const PairScratch ps[2] = {pair_scratch(scratch, tid, 0), pair_scratch(scratch, tid, 1)}; // scratch = the CTA's
+    unsigned long long cells = 0, rows = 0, blocks = 0, handed = 0;
+    bool drained = false;
+    for (;;) {
+        PairIO io;
+        PairBlk blk[2];
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) { // not unrolled: the chain state is indexed, so it lives in local memory, not in registers
+            io.M[h] = io.N[h] = 0;
+            io.ae[h] = io.be[h] = io.nshift[h] = io.bail[h] = 0;
+            io.cells[h] = io.rows[h] = 0;
+            if (s[h].chain < 0 && !drained) {
+                const unsigned long long t = atomicAdd(g.next, 1ull);
+                if ((int64_t)t < g.n_chains) {
+                    lane_start_chain(g, g.queue ? (int64_t)g.queue[t] : (int64_t)t, s[h]);
+                    if (!s[h].ge.valid) {
+                        const ChainResult out = {0, 0, 0, -1, 0, 0, 0, 0};
+                        g.res[s[h].chain] = out;
+                        s[h].chain = -1;
+                    }
+                } else {
+                    drained = true;
+                }
+            }
+            if (s[h].chain >= 0) {
+                pair_prepare(g, s[h], ps[h], blk[h]);
+                if (blk[h].qblk > 0 && blk[h].tblk > 0) {
+                    if (blk[h].tblk < kPairMinN) { // the reference's row 0 may reach column N here: lane kernel
+                        g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)s[h].chain;
+                        ++handed;
+                        s[h].chain = -1;
+                    } else {
+                        io.M[h] = blk[h].qblk;
+                        io.N[h] = blk[h].tblk;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(kFull, s[0].chain >= 0 || s[1].chain >= 0 || !drained)) break;
+        if (__any_sync(kFull, io.M[0] > 0 || io.M[1] > 0)) pair_dp(sm, tid, ps[0], ps[1], io);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) { // not unrolled: the chain state is indexed, so it lives in local memory, not in registers
+            LaneChain &c = s[h];
+            const bool have = c.chain >= 0;
+            const int ae = io.ae[h], be = io.be[h];
+            const int cap = have ? (int)min((int64_t)(2 * kMaxBlk), c.seg_end - c.seg) : 0;
+            const bool over = have && (io.bail[h] || ae + be > cap || c.meta + c.nblocks >= c.meta_end);
+#ifdef AG2_EXP_NOWALK
+            const bool walk = false;
+#else
+            const bool walk = have && !over;
+#endif
+            int qcnt, tcnt, acnt, first_op, op_after;
+            bool trim_ok;
+            const int64_t seg = walk ? c.seg : 0;
+            const int nops = pair_walk(sm, tid, scratch, h, walk, io.nshift[h], ae, be, g.ws_q + seg, g.ws_t + seg, cap, qcnt, tcnt, acnt,
+                                       trim_ok, first_op, op_after);
+            if (!have) continue;
+            int rc = 2;
+#ifdef AG2_EXP_NOWALK
+            if (have && !over) {
+#else
+            if (walk) {
+#endif
+                if (io.M[h] > 0) c.blocks += 1;
+                c.cells += io.cells[h];
+                c.rows += io.rows[h];
+                rc = lane_block_tail(g, c, blk[h].qblk, blk[h].tblk, blk[h].last_block, ae, be, nops, qcnt, tcnt, acnt, trim_ok,
+                                     first_op, op_after);
+            }
+            if (rc == 1) {
+                const ChainResult out = {c.ncols, c.qcons, c.tcons, c.last_op, c.nblocks, 0, 0, 0};
+                g.res[c.chain] = out;
+                cells += c.cells;
+                rows += c.rows;
+                blocks += c.blocks;
+                c.chain = -1;
+            } else if (rc == 2) {
+                g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)c.chain;
+                ++handed;
+                c.chain = -1;
+            }
+        }
+    }
+    atomicAdd(&g.counters->cells, cells);
+    atomicAdd(&g.counters->rows, rows);
+    atomicAdd(&g.counters->blocks, blocks);
+    (void)handed;
+}
+
+} // namespace ag2

@@ -420,7 +420,7 @@ def main():
     achieved = b_alg * st["aligned"] / kern_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": TRAFFIC_BYTES_PER_ALIGNED_BASE * st["aligned"], "traffic_note": TRAFFIC_NOTE,
-                "kernel": "xdrop_lane_kernel", "kernel_ms_per_launch": kernel_ms / args.steps,
+                "kernel": "xdrop_pair_kernel", "kernel_ms_per_launch": kernel_ms / args.steps,
                 "algorithmic_bytes_per_aligned_base": b_alg, "cells_per_aligned_base": cbar,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0}
 
@@ -436,7 +436,7 @@ def main():
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(st["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
-                "stats": {k: st[k] for k in ("cells", "rows", "blocks", "aligned", "columns", "wide_chains", "interior")}}
+                "stats": {k: st[k] for k in ("cells", "rows", "blocks", "aligned", "columns", "lane_chains", "wide_chains", "interior")}}
         print(json.dumps(line))
     dev.close()
     if world > 1:

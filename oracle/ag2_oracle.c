@@ -117,6 +117,11 @@ static inline int seq_at(const uint8_t *s, int i, int forward) /* MC/gapalign.h:
  *   - the last loop iteration reads B[b_size-1] even when that is index N (:85) -- the value is
  *     dead; here the read is skipped instead of performed out of bounds.
  */
+/* Band-geometry statistics for kernel design (test infrastructure only): [0] histogram of row widths,
+ * [1] per-block maximum row width, [2] per-block maximum of (band end - window base) for a window whose base
+ * follows `first` in steps of 8 columns, checked every 4 rows. */
+long orc_band_hist[3][256];
+
 int orc_xdrop_block(orc_xdrop *x, const uint8_t *A, int M, const uint8_t *B, int N, int forward,
                     int *ae_out, int *be_out, uint8_t *ops, int *nops, long *cells_out)
 {
@@ -153,8 +158,12 @@ int orc_xdrop_block(orc_xdrop *x, const uint8_t *A, int M, const uint8_t *B, int
         tb[i] = OP_GAP_A;
     }
     int bsize = i, first = 0, best = 0, ae = 0, be = 0;
+    int st_base = 0, st_maxw = 0, st_maxneed = bsize;
 
     for (int a = 1; a <= M; ++a) { /* :69-165 */
+        if ((a & 3) == 0 && first - st_base >= 8) st_base += 8;
+        if (bsize - first > st_maxw) st_maxw = bsize - first;
+        orc_band_hist[0][bsize - first > 255 ? 255 : bsize - first]++;
         const int ac = seq_at(A, a - 1, forward);
         uint8_t *row = tb + (long)a * stride;
         int diag = NEG_INF, hgap = NEG_INF, last = first, b;
@@ -205,7 +214,10 @@ int orc_xdrop_block(orc_xdrop *x, const uint8_t *A, int M, const uint8_t *B, int
             col[bsize].e = NEG_INF;
             ++bsize;
         }
+        if (bsize - st_base > st_maxneed) st_maxneed = bsize - st_base;
     }
+    orc_band_hist[1][st_maxw > 255 ? 255 : st_maxw]++;
+    orc_band_hist[2][st_maxneed > 255 ? 255 : st_maxneed]++;
 
     /* traceback (:170-210), expanded to one op per step */
     int a = ae, b = be, n = 0;

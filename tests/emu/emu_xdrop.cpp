@@ -4,6 +4,7 @@
 #define AG2_EMU 1
 #include "../../aligngraph2_b200/csrc/xdrop_device.cuh"
 #include "../../aligngraph2_b200/csrc/xdrop_lane.cuh"
+#include "../../aligngraph2_b200/csrc/xdrop_pair.cuh"
 
 #include <vector>
 
@@ -151,8 +152,8 @@ int emu_extend(int K, const char *ref, long ref_len, const char *read, int read_
 // setup_one -> lane_kernel_body (+ wide rerun of handed-over directions) -> finalize_one -> assemble_record.
 // reads: concatenated ASCII with offs[n+1]; cand: n x (read, strand, loc1, loc2).  Outputs per candidate:
 // rec[8] = ok qb qe sb se aln_len mode_left mode_right; strings concatenated into qaln/taln at aoff[i].
-int emu_lane_batch(const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
-                   int n, long *rec, long *aoff, char *qaln, char *taln, long *stats /* cells wide */)
+static int batch_impl(bool pair, const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
+                      int n, long *rec, long *aoff, char *qaln, char *taln, long *stats /* cells wide handed */)
 {
     std::vector<uint32_t> ref2((ref_len >> 4) + 8, 0), dummy((ref_len >> 5) + 8, 0);
     pack2(ref, ref_len, ref2, dummy, 0);
@@ -202,10 +203,35 @@ int emu_lane_batch(const char *ref, long ref_len, const char *reads, const long 
     a.wide_queue = wide_queue.data();
     a.wide_count = &wide_count;
     a.counters = &ctr;
-    warp_emu::run_warp([&]() {
-        const int lane = warp_emu::st().cur;
-        lane_kernel_body(a, lsm, lane, a.scratch + (size_t)lane * kLaneScratch);
-    });
+    unsigned int handed = 0;
+    if (pair) {
+        // pair path first (two directions per lane); what it hands over is restarted by the lane kernel body
+        static PairSmem psm;
+        std::vector<uint8_t> pscratch(kPairCtaScratch + 64);
+        std::vector<int32_t> lane_queue(2 * n + 1);
+        LaneArgs pa = a;
+        pa.scratch = (uint8_t *)(((uintptr_t)pscratch.data() + 15) & ~(uintptr_t)15);
+        pa.wide_queue = lane_queue.data();
+        pa.wide_count = &handed;
+        warp_emu::run_warp([&]() {
+            const int lane = warp_emu::st().cur;
+            pair_kernel_body(pa, psm, lane, pa.scratch);
+        });
+        if (handed) {
+            next = 0;
+            a.queue = lane_queue.data();
+            a.n_chains = handed;
+            warp_emu::run_warp([&]() {
+                const int lane = warp_emu::st().cur;
+                lane_kernel_body(a, lsm, lane, a.scratch + (size_t)lane * kLaneScratch);
+            });
+        }
+    } else {
+        warp_emu::run_warp([&]() {
+            const int lane = warp_emu::st().cur;
+            lane_kernel_body(a, lsm, lane, a.scratch + (size_t)lane * kLaneScratch);
+        });
+    }
     // wide rerun
     if (wide_count) {
         static WarpSmem sm;
@@ -250,7 +276,21 @@ int emu_lane_batch(const char *ref, long ref_len, const char *reads, const long 
     }
     stats[0] = (long)ctr.cells;
     stats[1] = (long)wide_count;
+    stats[2] = (long)handed;
     return 0;
+}
+
+int emu_lane_batch(const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
+                   int n, long *rec, long *aoff, char *qaln, char *taln, long *stats)
+{
+    return batch_impl(false, ref, ref_len, reads, offs, n_reads, cand, n, rec, aoff, qaln, taln, stats);
+}
+
+// The pair path (xdrop_pair.cuh) for a batch: pair kernel body -> lane kernel body for what it hands over -> wide rerun.
+int emu_pair_batch(const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
+                   int n, long *rec, long *aoff, char *qaln, char *taln, long *stats)
+{
+    return batch_impl(true, ref, ref_len, reads, offs, n_reads, cand, n, rec, aoff, qaln, taln, stats);
 }
 
 } // extern "C"

@@ -57,7 +57,7 @@ def test_struct_layouts_match_header(lib):
     from aligngraph2_b200.lib import CANDIDATE_DTYPE, RECORD_DTYPE, ExtendStats
     assert CANDIDATE_DTYPE.itemsize == 24
     assert RECORD_DTYPE.itemsize == 56
-    assert C.sizeof(ExtendStats) == 72
+    assert C.sizeof(ExtendStats) == 80
 
 
 def test_version_and_no_cpu_fallback(lib):

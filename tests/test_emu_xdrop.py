@@ -23,12 +23,14 @@ def emu():
     L.emu_extend.argtypes = [C.c_int, C.c_char_p, C.c_long, C.c_char_p, C.c_int, C.c_int, C.c_long, C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p]
     L.emu_lane_batch.argtypes = [C.c_char_p, C.c_long, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    L.emu_pair_batch.argtypes = L.emu_lane_batch.argtypes
     return L
 
 
-def emu_lane_batch(L, ref, reads, cands):
+def emu_lane_batch(L, ref, reads, cands, pair=False):
     """The lane path (xdrop_lane.cuh) for a batch: setup -> lane kernel body (one emulated warp, queue
-    refill) -> wide rerun -> finalize -> assemble."""
+    refill) -> wide rerun -> finalize -> assemble.  pair=True: the pair path (xdrop_pair.cuh) in front of it;
+    the third return value is then (wide, handed to the lane kernel)."""
     offs = np.zeros(len(reads) + 1, dtype=np.int64)
     np.cumsum([len(r) for r in reads], out=offs[1:])
     cat = b"".join(reads)
@@ -38,8 +40,8 @@ def emu_lane_batch(L, ref, reads, cands):
     aoff = np.zeros(n, dtype=np.int64)
     cap = int(offs[-1]) * 3 + 100000
     qa, ta = C.create_string_buffer(cap), C.create_string_buffer(cap)
-    st = np.zeros(2, dtype=np.int64)
-    L.emu_lane_batch(ref, len(ref), cat, offs.ctypes.data, len(reads), c.ctypes.data, n, rec.ctypes.data,
+    st = np.zeros(3, dtype=np.int64)
+    (L.emu_pair_batch if pair else L.emu_lane_batch)(ref, len(ref), cat, offs.ctypes.data, len(reads), c.ctypes.data, n, rec.ctypes.data,
                      aoff.ctypes.data, qa, ta, st.ctypes.data)
     out = []
     for i in range(n):
@@ -48,7 +50,7 @@ def emu_lane_batch(L, ref, reads, cands):
         out.append(dict(ok=int(r[0]), qb=int(r[1]), qe=int(r[2]), sb=int(r[3]), se=int(r[4]), aln_size=ln,
                         qaln=qa.raw[a:a + ln] if r[0] else b"", taln=ta.raw[a:a + ln] if r[0] else b"",
                         modes=(int(r[6]), int(r[7]))))
-    return out, int(st[0]), int(st[1])
+    return out, int(st[0]), ((int(st[1]), int(st[2])) if pair else int(st[1]))
 
 
 def emu_block(L, K, A, B):
@@ -115,13 +117,13 @@ def test_emulated_extend_matches_golden(emu):
             assert e["qaln"] == r["qaln"].tobytes() and e["taln"] == r["taln"].tobytes()
 
 
-def test_emulated_lane_path_matches_oracle(emu, oracle):
+def _stress_batch(oracle, seed, n):
     # more directions than lanes (queue refill), ragged reads, both strands, soft-masked / N bases,
     # seeds at the read ends, and unrelated extensions whose band leaves the lane window (wide rerun)
-    rng = np.random.default_rng(21)
+    rng = np.random.default_rng(seed)
     ref = synth.make_reference(rng, 40_000)
     reads, cands, exp, cells = [], [], [], 0
-    for i in range(40):
+    for i in range(n):
         tl = int(rng.integers(60, 2600))
         rd, start, ops = synth.make_read(rng, ref, tl, False)
         cnt = np.ones(tl, dtype=np.int64)
@@ -151,11 +153,47 @@ def test_emulated_lane_path_matches_oracle(emu, oracle):
         a = oracle.extend(ref.tobytes(), synth.orient(given, strand), loc1, loc2)
         exp.append(a)
         cells += a["cells"]
-    got, got_cells, wide = emu_lane_batch(emu, ref.tobytes(), reads, cands)
+    return ref, reads, cands, exp, cells
+
+
+def _check(exp, got):
     for a, b in zip(exp, got):
         assert a["ok"] == b["ok"]
         if a["ok"]:
             for k in ("qb", "qe", "sb", "se", "aln_size", "qaln", "taln"):
                 assert a[k] == b[k], k
+
+
+def test_emulated_lane_path_matches_oracle(emu, oracle):
+    ref, reads, cands, exp, cells = _stress_batch(oracle, 21, 40)
+    got, got_cells, wide = emu_lane_batch(emu, ref.tobytes(), reads, cands)
+    _check(exp, got)
     assert got_cells == cells
     assert wide > 0, "no direction was handed to the wide path: that hand-over is part of this test"
+
+
+def test_emulated_pair_path_matches_oracle(emu, oracle):
+    # the pair path (two directions per lane, packed 16-bit DP) in front of the lane path: same stress batch, more
+    # directions than the 64 the emulated warp holds (refill), target blocks shorter than 32 and unrelated extensions
+    # (handed to the lane kernel, then to the wide kernel)
+    ref, reads, cands, exp, cells = _stress_batch(oracle, 22, 80)
+    got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
+    _check(exp, got)
+    assert got_cells == cells
+    assert handed > 0 and handed < len(cands), "the pair kernel must keep most directions and hand some over"
+
+
+def test_emulated_pair_path_long_reads(emu, oracle):
+    # full-length blocks (500 x 500), window moves, several blocks per direction
+    d = synth.make_batch_torch(77, 150_000, 24, 4000)
+    ref, bases, off = d["ref"].numpy(), d["bases"].numpy(), d["offsets"].numpy()
+    reads = [bases[off[i]:off[i + 1]].tobytes() for i in range(24)]
+    cands = [(i, int(d["strand"][i]), int(d["loc1"][i]), int(d["loc2"][i])) for i in range(24)]
+    exp, cells = [], 0
+    for i in range(24):
+        a = oracle.extend(ref.tobytes(), synth.orient(reads[i], cands[i][1]), cands[i][2], cands[i][3])
+        exp.append(a)
+        cells += a["cells"]
+    got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
+    _check(exp, got)
+    assert got_cells == cells
