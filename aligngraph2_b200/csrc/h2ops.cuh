@@ -58,10 +58,20 @@ inline int dec(uint32_t b) // exact: every value in play is an integer
     }
     return sign * v;
 }
-inline uint32_t enc(int x)
+inline uint32_t enc(int x) // round to nearest even above 2048, like the hardware (such values only ever meet a factor 0)
 {
-    if (x > 2048 || x < -2048) { fprintf(stderr, "h2emu: %d out of the exact range\n", x); abort(); }
-    return h16_bits(x);
+    if (x <= 2048 && x >= -2048) return h16_bits(x);
+    const uint32_t sign = x < 0 ? 0x8000u : 0u;
+    uint32_t m = x < 0 ? (uint32_t)(-x) : (uint32_t)x;
+    int e = 0;
+    for (uint32_t t = m; t > 1; t >>= 1) ++e;
+    const int sh = e - 10;
+    uint32_t q = m >> sh;
+    const uint32_t rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+    if (rem > half || (rem == half && (q & 1u))) ++q;
+    if (q == 2048u) { q = 1024u; ++e; }
+    if (e > 15) { fprintf(stderr, "h2emu: %d overflows binary16\n", x); abort(); }
+    return sign | ((uint32_t)(e + 15) << 10) | (q & 0x3ffu);
 }
 inline bool neg0(uint32_t b) { return (b & 0xffffu) == 0x8000u; }
 template <typename F>
@@ -74,6 +84,10 @@ inline uint32_t map2(uint32_t a, uint32_t b, F f)
 inline h2 h2_add(h2 a, h2 b)
 {
     return h2emu::map2(a, b, [](uint32_t x, uint32_t y) { return h2emu::enc(h2emu::dec(x) + h2emu::dec(y)); });
+}
+inline h2 h2_sub(h2 a, h2 b)
+{
+    return h2emu::map2(a, b, [](uint32_t x, uint32_t y) { return h2emu::enc(h2emu::dec(x) - h2emu::dec(y)); });
 }
 inline h2 h2_max(h2 a, h2 b)
 {
@@ -96,6 +110,22 @@ AG2_H2_CMP(h2_le, <=)
 AG2_H2_CMP(h2_eq, ==)
 AG2_H2_CMP(h2_ne, !=)
 #undef AG2_H2_CMP
+#define AG2_H2_CMPF(name, op)                                                                                        \
+    inline h2 name(h2 a, h2 b)                                                                                       \
+    {                                                                                                                \
+        return h2emu::map2(a, b, [](uint32_t x, uint32_t y) { return h2emu::dec(x) op h2emu::dec(y) ? 0x3c00u : 0u; }); \
+    }
+AG2_H2_CMPF(h2_gtf, >)
+AG2_H2_CMPF(h2_ltf, <)
+AG2_H2_CMPF(h2_eqf, ==)
+#undef AG2_H2_CMPF
+inline h2 h2_fma(h2 a, h2 b, h2 c) // exact only: every product and sum in play is a small integer
+{
+    const int lo = h2emu::dec(a) * h2emu::dec(b) + h2emu::dec(c), hi = h2emu::dec(a >> 16) * h2emu::dec(b >> 16) + h2emu::dec(c >> 16);
+    return h2emu::enc(lo) | (h2emu::enc(hi) << 16);
+}
+inline h2 h2_mul(h2 a, h2 b) { return h2_fma(a, b, 0u); }
+inline uint32_t h2_opaque(uint32_t x) { return x; }
 inline uint32_t vadd2(uint32_t a, uint32_t b) { return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16); }
 inline h2 h2_from_ints(int lo, int hi) { return h2emu::enc(lo) | (h2emu::enc(hi) << 16); }
 inline int h2_lo_int(h2 a) { return h2emu::dec(a); }
@@ -104,6 +134,7 @@ inline int h2_hi_int(h2 a) { return h2emu::dec(a >> 16); }
 __device__ __forceinline__ __half2 h2_as(h2 a) { return *reinterpret_cast<__half2 *>(&a); }
 __device__ __forceinline__ h2 h2_bits(__half2 a) { return *reinterpret_cast<h2 *>(&a); }
 __device__ __forceinline__ h2 h2_add(h2 a, h2 b) { return h2_bits(__hadd2(h2_as(a), h2_as(b))); }
+__device__ __forceinline__ h2 h2_sub(h2 a, h2 b) { return h2_bits(__hsub2(h2_as(a), h2_as(b))); }
 __device__ __forceinline__ h2 h2_max(h2 a, h2 b) { return h2_bits(__hmax2(h2_as(a), h2_as(b))); }
 __device__ __forceinline__ h2 h2_min(h2 a, h2 b) { return h2_bits(__hmin2(h2_as(a), h2_as(b))); }
 __device__ __forceinline__ h2 h2_abs(h2 a) { return h2_bits(__habs2(h2_as(a))); }
@@ -113,6 +144,18 @@ __device__ __forceinline__ uint32_t h2_lt(h2 a, h2 b) { return __hlt2_mask(h2_as
 __device__ __forceinline__ uint32_t h2_le(h2 a, h2 b) { return __hle2_mask(h2_as(a), h2_as(b)); }
 __device__ __forceinline__ uint32_t h2_eq(h2 a, h2 b) { return __heq2_mask(h2_as(a), h2_as(b)); }
 __device__ __forceinline__ uint32_t h2_ne(h2 a, h2 b) { return __hne2_mask(h2_as(a), h2_as(b)); }
+// compares with a 1.0 / 0.0 result per half: the mask form for selects done as a*g + b on the FMA pipe
+__device__ __forceinline__ h2 h2_gtf(h2 a, h2 b) { return h2_bits(__hgt2(h2_as(a), h2_as(b))); }
+__device__ __forceinline__ h2 h2_ltf(h2 a, h2 b) { return h2_bits(__hlt2(h2_as(a), h2_as(b))); }
+__device__ __forceinline__ h2 h2_eqf(h2 a, h2 b) { return h2_bits(__heq2(h2_as(a), h2_as(b))); }
+__device__ __forceinline__ h2 h2_fma(h2 a, h2 b, h2 c) { return h2_bits(__hfma2(h2_as(a), h2_as(b), h2_as(c))); }
+__device__ __forceinline__ h2 h2_mul(h2 a, h2 b) { return h2_bits(__hmul2(h2_as(a), h2_as(b))); }
+// a constant the compiler must keep in a register (LOP3 takes one immediate; a second constant has to be a register)
+__device__ __forceinline__ uint32_t h2_opaque(uint32_t x)
+{
+    asm volatile("" : "+r"(x));
+    return x;
+}
 __device__ __forceinline__ uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 __device__ __forceinline__ h2 h2_from_ints(int lo, int hi) { return h2_bits(__halves2half2(__int2half_rn(lo), __int2half_rn(hi))); }
 __device__ __forceinline__ int h2_lo_int(h2 a) { return __half2int_rn(__low2half(h2_as(a))); }

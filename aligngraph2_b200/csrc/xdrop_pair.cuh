@@ -123,44 +123,75 @@ __device__ __forceinline__ void pair_store16(uint8_t *p, const uint32_t (&w)[4])
 struct PairCarry {
     h2 diag, hgap, best, thr, be, lastj;
     uint32_t Ms, Mlp, Mlead, cnt;
+    uint32_t one; // binary16 1.0 in both halves, held in a register
 };
 
-// One DP cell of both directions.  K = slot within the group.
-template <int K>
+// One DP cell of both directions.  K = slot within the group.  IN = the group is interior for every running direction of
+// the warp (all 8 slots and the one after them are standard cells, the leading run is over): the boundary masks drop out.
+// Instruction budget (the kernel is bound by the ALU pipe, where HSET2 / HMNMX2 / LOP3 issue, at one warp instruction per
+// two cycles; HADD2 / HFMA2 / IMAD issue on the FMA pipe): selects keyed on a compare are done as g * (a - b) + b with the
+// compare's 1.0 / 0.0 form wherever the operands stay exact, and the traceback nibble is summed, not assembled.
+// Nibble: bit 0 "gap in A beats the rest", bit 1 "gap in B beats the diagonal" (the walk gives bit 0 priority), bit 2 kExtA,
+// bit 3 kExtB; slot k of a group sits at bits 16 * (k / 4) + 4 * (3 - k % 4) of the group's word.
+template <int K, bool IN>
 __device__ __forceinline__ void pair_slot(uint32_t &v, PairCarry &c, const h2 nDg, const h2 Jg, const uint32_t mmw, uint32_t &acc)
 {
-    constexpr int kq = K & 3;
-    constexpr uint32_t C1 = 0x00010001u << (4 * kq), C3 = 0x00030003u << (4 * kq), C4 = 0x00040004u << (4 * kq),
-                       CF = 0x000f000fu << (4 * kq);
     const h2 Jc = h2_add(Jg, H2C(K));
-    const h2 mt = ((mmw << (15 - 2 * K)) & kH2Sign) ^ H2C(1);
-    const h2 nd = h2_add(v, mt);                           // h(a-1, b) + match(a, b+1's target base): the next slot's diagonal
-    const uint32_t Ms = c.Ms;                              // this slot is a standard cell (column < nD)
-    const uint32_t Me = h2_gt(nDg, H2C(K + 1));            // the next one is: this slot's vertical gap is valid
-    c.Ms = Me;
-    const h2 e = h2_add(h2_abs(v), H2C(-1)) & Me;          // e(a-1, b)
-    const h2 dg = c.diag & Ms;                             // h(a-1, b-1) + match
+    const h2 mt = ((mmw << (15 - 2 * K)) & kH2Sign) | c.one;   // +1 match, -1 mismatch
+    const h2 nd = h2_add(v, mt);                           // h(a-1, b) + match: the next slot's diagonal
+    h2 e = h2_add(h2_abs(v), H2C(-1));                     // e(a-1, b)
+    h2 dg = c.diag;                                        // h(a-1, b-1) + match
+    uint32_t Ms = 0xffffffffu;
+    if (!IN) {
+        Ms = c.Ms;                                         // this slot is a standard cell (column < nD)
+        const uint32_t Me = h2_gt(nDg, H2C(K + 1));        // the next one is: this slot's vertical gap is valid
+        c.Ms = Me;
+        e &= Me;
+        dg &= Ms;
+    }
     const h2 m1 = h2_max(dg, e);
     const h2 sc = h2_max(m1, c.hgap);                      // (:95-107)
-    const uint32_t Ml = h2_ge(sc, c.thr) & (Ms | c.Mlp);   // not pruned (:109); extension cells need a live left neighbour
-    const uint32_t P1 = h2_lt(dg, e);                      // SCRIPT_GAP_IN_B beats the diagonal
-    const uint32_t P2 = h2_lt(m1, c.hgap);                 // SCRIPT_GAP_IN_A beats both
-    const uint32_t PA = h2_eq(e, sc);                      // kExtA (:121-126)
-    const uint32_t PB = h2_eq(c.hgap, sc);                 // kExtB (:129-133)
-    const uint32_t tA = (P2 & C1) | (P1 & ~P2 & ~C1);      // bit 0: gap in A, bit 1: gap in B
-    const uint32_t tB = ((PA & C4) | (PB & ~C4)) & Ml & Ms; // bits 2,3: flags, unpruned standard cells only
-    acc |= ((tA & C3) | (tB & ~C3)) & CF;
-    const uint32_t Mnew = h2_gt(sc, c.best);
+    uint32_t Ml = h2_ge(sc, c.thr);                        // not pruned (:109)
+    if (!IN) Ml &= Ms | c.Mlp;                             // extension cells need a live left neighbour
+    const h2 gl = Ml & c.one;                              // 1.0 where live
+    const h2 gls = IN ? gl : (Ml & Ms & c.one);            // 1.0 where a live standard cell
+    // traceback nibble (+1024 to read it off the mantissa)
+    const h2 P1 = h2_ltf(dg, e), P2 = h2_ltf(m1, c.hgap);
+    const h2 PA = h2_eqf(e, sc), PB = h2_eqf(c.hgap, sc);  // kExtA (:121-126), kExtB (:129-133): unpruned cells only
+    const h2 fl = h2_mul(h2_fma(PB, H2C(2), PA), gls);
+    const h2 nib = h2_fma(fl, H2C(4), h2_fma(P1, H2C(2), h2_add(P2, H2C(1024))));
+    acc = acc * 16u + (nib & 0x000f000fu);
+    // running best (:114-118) and band bookkeeping
+    const h2 gnew = h2_gtf(sc, c.best);
     c.best = h2_max(c.best, sc);
     c.thr = h2_add(c.best, H2C(-kXdrop));
-    c.be = h2_sel(Mnew, Jc, c.be);
+    c.be = h2_fma(gnew, h2_sub(Jc, c.be), c.be);
     c.lastj = h2_sel(Ml, Jc, c.lastj);
-    c.hgap = h2_sel(Ml, h2_add(sc, H2C(-1)), c.hgap);      // not decayed across pruned cells
-    c.Mlead &= ~Ml;                                        // still in the run of leading pruned cells (:110)
-    c.cnt = vadd2(c.cnt, c.Mlead);
-    v = h2_sel(Ml, sc, (v | kH2Sign) & ~c.Mlead);          // live / pruned inside the band / left the band
+    c.hgap = h2_fma(gl, h2_sub(h2_add(sc, H2C(-1)), c.hgap), c.hgap); // not decayed across pruned cells
+    uint32_t dead = v | kH2Sign;                           // pruned inside the band: h = MIN, e kept
+    if (!IN) {
+        c.Mlead &= ~Ml;                                    // still in the run of leading pruned cells (:110)
+        c.cnt = vadd2(c.cnt, c.Mlead);
+        dead &= ~c.Mlead;                                  // left the band
+    }
+    v = h2_sel(Ml, sc, dead);
     c.diag = nd;
     c.Mlp = Ml;
+}
+
+template <bool IN>
+__device__ __forceinline__ void pair_group(uint32_t (&va)[4], uint32_t (&vb)[4], PairCarry &c, const h2 nDg, const h2 Jg, const uint32_t mmw,
+                                           uint32_t &acc0, uint32_t &acc1)
+{
+    pair_slot<0, IN>(va[0], c, nDg, Jg, mmw, acc0);
+    pair_slot<1, IN>(va[1], c, nDg, Jg, mmw, acc0);
+    pair_slot<2, IN>(va[2], c, nDg, Jg, mmw, acc0);
+    pair_slot<3, IN>(va[3], c, nDg, Jg, mmw, acc0);
+    pair_slot<4, IN>(vb[0], c, nDg, Jg, mmw, acc1);
+    pair_slot<5, IN>(vb[1], c, nDg, Jg, mmw, acc1);
+    pair_slot<6, IN>(vb[2], c, nDg, Jg, mmw, acc1);
+    pair_slot<7, IN>(vb[3], c, nDg, Jg, mmw, acc1);
+    if (IN) c.Ms = 0xffffffffu;
 }
 
 struct PairIO {
@@ -200,6 +231,7 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
     c.best = H2C(kPairOff);
     c.thr = H2C(kPairOff - kXdrop);
     c.be = 0;
+    c.one = h2_opaque(H2C(1));
     unsigned cells0 = 0, cells1 = 0, rows2 = 0;
     uint32_t aw0 = 0, aw1 = 0, an0 = s0.qcodes[0], an1 = s1.qcodes[0], bail = 0;
 
@@ -264,6 +296,8 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             rows2 = vadd2(rows2, run & 0x00010001u);
         }
         const h2 nDe = nD & run;
+        c.best = h2_sel(run, c.best, H2C(2047)); // a direction that has stopped can no longer prune in, whatever its masks say
+        c.thr = h2_sel(run, c.thr, H2C(2047 - kXdrop));
         const h2 best0 = c.best;
         c.diag = 0;
         c.hgap = 0;
@@ -302,14 +336,10 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             const uint32_t x = tgw ^ acrep;
             const uint32_t mmw = x | (x >> 1) | phw; // bit 2k of each half: slot k mismatches
             uint32_t acc0 = 0, acc1 = 0;
-            pair_slot<0>(va[0], c, nDg, Jg, mmw, acc0);
-            pair_slot<1>(va[1], c, nDg, Jg, mmw, acc0);
-            pair_slot<2>(va[2], c, nDg, Jg, mmw, acc0);
-            pair_slot<3>(va[3], c, nDg, Jg, mmw, acc0);
-            pair_slot<4>(vb[0], c, nDg, Jg, mmw, acc1);
-            pair_slot<5>(vb[1], c, nDg, Jg, mmw, acc1);
-            pair_slot<6>(vb[2], c, nDg, Jg, mmw, acc1);
-            pair_slot<7>(vb[3], c, nDg, Jg, mmw, acc1);
+            // interior group: no running direction of the warp has a band edge or its leading run in these 8 slots
+            const uint32_t inner = (h2_ge(nDg, H2C(9)) & ~c.Mlead) | ~run;
+            if (__all_sync(kFull, inner == 0xffffffffu)) pair_group<true>(va, vb, c, nDg, Jg, mmw, acc0, acc1);
+            else pair_group<false>(va, vb, c, nDg, Jg, mmw, acc0, acc1);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 sm.v[2 * g][tid][i] = va[i];
@@ -337,7 +367,7 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             tgw = ntg;
             phw = nph;
             if (g < g_std) continue;
-            more = __any_sync(kFull, (c.Ms | c.Mlp) != 0);
+            more = __any_sync(kFull, ((c.Ms | c.Mlp) & run) != 0);
             if (g >= kPairGroups) break;
         }
         if (g & 3) { // the row's last, partial piece
@@ -351,7 +381,7 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             pair_store16(row0 + (size_t)(g >> 2) * kPairQuadStride, t0);
             pair_store16(row1 + (size_t)(g >> 2) * kPairQuadStride, t1);
         }
-        if (more) bail |= c.Ms | c.Mlp; // the window is too narrow for this direction
+        if (more) bail |= (c.Ms | c.Mlp) & run; // the window is too narrow for this direction
         // row end (:142-164): the next band ends one past the last live cell (the sentinel), clipped to column N - 1
         const uint32_t any_live = h2_ge(c.lastj, 0u);
         alive &= any_live | ~run;      // every cell pruned: the reference leaves the loop (:142)
@@ -453,9 +483,9 @@ __device__ int pair_walk(PairSmem &sm, int tid, uint8_t *cta_scratch, int hh, bo
                 } else { // far right of the window: not part of the fetched rows
                     word = *reinterpret_cast<const uint32_t *>(ps.tb + (size_t)a * kPairRowStride + (size_t)(w >> 2) * kPairQuadStride + 4 * (w & 3));
                 }
-                cell = (int)((word >> (4 * (slot & 7))) & 15u);
+                cell = (int)((word >> (16 * ((slot >> 2) & 1) + 4 * (3 - (slot & 3)))) & 15u);
             }
-            int nxt = cell & 3;
+            int nxt = (cell & 1) ? kOpGapA : (cell & 2); // kOpGapB == 2, kOpSub == 0
             if (cur == kOpGapA && (cell & kExtA)) nxt = kOpGapA;
             if (cur == kOpGapB && (cell & kExtB)) nxt = kOpGapB;
             cur = nxt;
