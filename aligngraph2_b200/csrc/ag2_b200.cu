@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kLaneThreads) xdrop_lane_kernel(LaneArgs g)
 
 // Pair path (xdrop_pair.cuh): two directions per thread in packed 16-bit arithmetic, 64 directions in lock step
 // per warp.  The dominant kernel; the lane kernel above restarts the directions it hands over.
-__global__ void __launch_bounds__(kPairThreads, 8) xdrop_pair_kernel(LaneArgs g)
+__global__ void __launch_bounds__(kPairThreads, 7) xdrop_pair_kernel(LaneArgs g)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PairSmem &sm = *reinterpret_cast<PairSmem *>(smem_raw);
@@ -273,7 +273,7 @@ struct ag2_ctx {
     DevBuf out_q, out_t;                // dense output strings
     int64_t out_total = 0;
     DevBuf tb, tb_wide, tb_pair;
-    DevBuf wide_queue, lane_queue;
+    DevBuf wide_queue, lane_queue, lane_resume;
     DevBuf scalars;                     // ChainCounters + work counters + totals
     size_t ws_limit = (size_t)24 << 30; // bytes per workspace string per chunk (resident runs: one chunk, no drain tails)
     size_t ws_limit_streamed = (size_t)3 << 30; // chunk size when results stream to host buffers while the next chunk computes
@@ -423,7 +423,7 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
                      &ctx->km_out, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
-                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->scalars};
+                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->scalars};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->chain_events) {
@@ -549,6 +549,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     RESERVE(ctx->dense_off, (size_t)(n + 1) * 8);
     RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
     RESERVE(ctx->lane_queue, (size_t)n * 2 * 4);
+    RESERVE(ctx->lane_resume, (size_t)n * 2 * sizeof(LaneResume));
 
     // pair kernel: the band window of 128 directions per CTA in shared memory
     int pocc = 0;
@@ -643,6 +644,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         pa.next = &sc->next_pair;
         pa.wide_queue = (int32_t *)ctx->lane_queue.p;
         pa.wide_count = &sc->lane_count;
+        pa.resume = (LaneResume *)ctx->lane_resume.p;
         CK(cudaEventRecord(ctx->chain_events[ci].first, st));
         xdrop_pair_kernel<<<pair_grid, kPairThreads, pair_smem, st>>>(pa);
         CK(cudaEventRecord(ctx->chain_events[ci].second, st));
@@ -653,10 +655,11 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         launches += 2;
         ctx->stats_lane_chains += n_lane;
         if (n_lane > 0) {
-            // directions the pair window could not hold (or with a target block under 32 bases): lane kernel, restarted
+            // directions the pair window could not hold (or with a target block under 32 bases): lane kernel, from that block on
             a.scratch = (uint8_t *)ctx->tb.p;
             a.n_chains = n_lane;
             a.queue = (const int32_t *)ctx->lane_queue.p;
+            a.resume = (LaneResume *)ctx->lane_resume.p;
             a.next = &sc->next_fast;
             a.wide_queue = (int32_t *)ctx->wide_queue.p;
             a.wide_count = &sc->wide_count;

@@ -51,6 +51,14 @@ __device__ __forceinline__ int16_t *band_slot(LaneSmem &sm, int tid, int b)
 __device__ __forceinline__ int16_t band_live(int h) { return (int16_t)(h * 2); }
 constexpr int16_t kBandSentinel = (int16_t)(((kNeg16 + 1) * 2) | 1);
 
+// State of a direction at a block boundary, written by the pair kernel when it hands the direction over: the lane kernel
+// continues from that block instead of restarting the direction.
+struct LaneResume {
+    int32_t qidx, tidx, ncols, qcons, tcons, last_op, nblocks, pad;
+    int64_t seg;
+    unsigned long long cells, rows, blocks;
+};
+
 struct LaneArgs {
     PackedSeqs seqs;
     const Candidate *cand;
@@ -61,6 +69,7 @@ struct LaneArgs {
     uint8_t *scratch;        // kLaneScratch bytes per resident thread
     int64_t n_chains;
     const int32_t *queue;    // nullptr: chains 0..n_chains-1; else chain ids to run
+    LaneResume *resume;      // parallel to `queue` (lane kernel: read) / to `wide_queue` (pair kernel: written); may be null
     unsigned long long *next;
     int32_t *wide_queue;
     unsigned int *wide_count;
@@ -348,6 +357,38 @@ __device__ __forceinline__ void lane_start_chain(const LaneArgs &g, int64_t chai
     s.meta_end = s.meta + (forward ? s.ge.nmetaR : s.ge.nmetaL);
 }
 
+__device__ __forceinline__ void lane_resume(LaneChain &s, const LaneResume &r)
+{
+    s.qidx = r.qidx;
+    s.tidx = r.tidx;
+    s.ncols = r.ncols;
+    s.qcons = r.qcons;
+    s.tcons = r.tcons;
+    s.last_op = r.last_op;
+    s.nblocks = r.nblocks;
+    s.seg = r.seg;
+    s.cells = r.cells;
+    s.rows = r.rows;
+    s.blocks = r.blocks;
+}
+__device__ __forceinline__ LaneResume lane_save(const LaneChain &s)
+{
+    LaneResume r;
+    r.qidx = s.qidx;
+    r.tidx = s.tidx;
+    r.ncols = s.ncols;
+    r.qcons = s.qcons;
+    r.tcons = s.tcons;
+    r.last_op = s.last_op;
+    r.nblocks = s.nblocks;
+    r.pad = 0;
+    r.seg = s.seg;
+    r.cells = s.cells;
+    r.rows = s.rows;
+    r.blocks = s.blocks;
+    return r;
+}
+
 // align_ex's bookkeeping after one block's walk (:334-357): metadata word, consumed counts, next block origin.
 // Returns 0 = chain continues, 1 = chain finished.
 __device__ __forceinline__ int lane_block_tail(const LaneArgs &g, LaneChain &s, int qblk, int tblk, bool last_block, int ae, int be,
@@ -441,6 +482,7 @@ __device__ void lane_kernel_body(const LaneArgs &g, LaneSmem &sm, int tid, uint8
             const unsigned long long t = atomicAdd(g.next, 1ull);
             if ((int64_t)t < g.n_chains) {
                 lane_start_chain(g, g.queue ? (int64_t)g.queue[t] : (int64_t)t, s);
+                if (g.queue && g.resume && s.ge.valid) lane_resume(s, g.resume[t]);
                 if (!s.ge.valid) {
                     const ChainResult out = {0, 0, 0, -1, 0, 0, 0, 0};
                     g.res[s.chain] = out;

@@ -25,7 +25,7 @@
 //     the rows at which the base moved are logged for the walk.
 //
 // A direction this path cannot hold (window overflow, a target block shorter than 32, reservation exceeded) is handed
-// to the lane kernel (xdrop_lane.cuh), which restarts it; behind that stands the wide kernel.
+// to the lane kernel (xdrop_lane.cuh), which continues it from that block; behind that stands the wide kernel.
 #pragma once
 
 #include "h2ops.cuh"
@@ -34,7 +34,7 @@
 namespace ag2 {
 
 constexpr int kPairThreads = 64;                   // threads per CTA (128 directions)
-constexpr int kPairSlots = 88;                     // window width in columns (band + lead fits in 99.98 % of the blocks of CLR reads)
+constexpr int kPairSlots = 96;                     // window width in columns (band + lead of CLR reads: 89 at most in 6500 sampled blocks)
 constexpr int kPairGroups = kPairSlots / 8;
 constexpr int kPairQuads = (kPairGroups + 3) / 4;  // a traceback row = kPairQuads pieces of 16 bytes (4 groups = 32 columns each)
 constexpr int kPairMainGroups = 8;                 // the walk fetches the first 8 groups of a row (64 columns); the rest on demand
@@ -45,6 +45,10 @@ constexpr int kPairLogBytes = 256;                 // rows at which the window b
 constexpr int kPairSeqBytes = 192;                 // kSeqWords (46) words, padded
 constexpr int kPairAux = kPairLogBytes + 2 * kPairSeqBytes; // per direction
 constexpr size_t kPairCtaScratch = kPairTbCta + (size_t)2 * kPairThreads * kPairAux;
+#ifndef AG2_PAIR_SHIFT_MASK
+#define AG2_PAIR_SHIFT_MASK 3
+#endif
+constexpr int kPairShiftMask = AG2_PAIR_SHIFT_MASK;   // the window base is checked every (mask + 1) rows
 constexpr int kPairOff = 1024;                     // score offset
 constexpr int kPairMinN = 32;                      // shortest target block this path takes
 
@@ -236,7 +240,7 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
     uint32_t aw0 = 0, aw1 = 0, an0 = s0.qcodes[0], an1 = s1.qcodes[0], bail = 0;
 
     for (int a = 1; a <= rows_max; ++a) {
-        if ((a & 3) == 0) {
+        if ((a & kPairShiftMask) == 0) {
             // move the window of a direction whose band start has advanced by 8 columns or more
             const uint32_t Msh = h2_ge(frelh, H2C(8));
             if (__any_sync(kFull, Msh != 0)) {
@@ -596,7 +600,9 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
                 pair_prepare(g, s[h], ps[h], blk[h]);
                 if (blk[h].qblk > 0 && blk[h].tblk > 0) {
                     if (blk[h].tblk < kPairMinN) { // the reference's row 0 may reach column N here: lane kernel
-                        g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)s[h].chain;
+                        const unsigned slot = atomicAdd(g.wide_count, 1u);
+                        g.wide_queue[slot] = (int32_t)s[h].chain;
+                        if (g.resume) g.resume[slot] = lane_save(s[h]);
                         ++handed;
                         s[h].chain = -1;
                     } else {
@@ -645,8 +651,10 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
                 rows += c.rows;
                 blocks += c.blocks;
                 c.chain = -1;
-            } else if (rc == 2) {
-                g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)c.chain;
+            } else if (rc == 2) { // c is still the state at the start of this block
+                const unsigned slot = atomicAdd(g.wide_count, 1u);
+                g.wide_queue[slot] = (int32_t)c.chain;
+                if (g.resume) g.resume[slot] = lane_save(c);
                 ++handed;
                 c.chain = -1;
             }

@@ -209,10 +209,12 @@ static int batch_impl(bool pair, const char *ref, long ref_len, const char *read
         static PairSmem psm;
         std::vector<uint8_t> pscratch(kPairCtaScratch + 64);
         std::vector<int32_t> lane_queue(2 * n + 1);
+        std::vector<LaneResume> lane_resume(2 * n + 1);
         LaneArgs pa = a;
         pa.scratch = (uint8_t *)(((uintptr_t)pscratch.data() + 15) & ~(uintptr_t)15);
         pa.wide_queue = lane_queue.data();
         pa.wide_count = &handed;
+        pa.resume = lane_resume.data();
         warp_emu::run_warp([&]() {
             const int lane = warp_emu::st().cur;
             pair_kernel_body(pa, psm, lane, pa.scratch);
@@ -220,6 +222,7 @@ static int batch_impl(bool pair, const char *ref, long ref_len, const char *read
         if (handed) {
             next = 0;
             a.queue = lane_queue.data();
+            a.resume = lane_resume.data();
             a.n_chains = handed;
             warp_emu::run_warp([&]() {
                 const int lane = warp_emu::st().cur;
