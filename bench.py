@@ -30,11 +30,11 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-# dram__bytes_read.sum + dram__bytes_write.sum of xdrop_lane_kernel from the ncu --set full capture
-# profiles/kernel_r01d_lane.md (100k reads: 206.75 GB for 1 052 318 181 aligned bases); DRAM bytes per
+# dram__bytes_read.sum + dram__bytes_write.sum of xdrop_pair_kernel from the ncu --set full capture
+# profiles/kernel_r01f_pair.md (150k reads: 121.51 + 123.78 GB for 1 578 478 191 aligned bases); DRAM bytes per
 # aligned base do not depend on the batch size, so the per-launch figure is that ratio x this launch's bases
-TRAFFIC_BYTES_PER_ALIGNED_BASE = 206.750790e9 / 1052318181
-TRAFFIC_NOTE = "ncu dram bytes per aligned base (profiles/kernel_r01d_lane.md, 100k-read launch) x aligned bases of this launch"
+TRAFFIC_BYTES_PER_ALIGNED_BASE = (121.513232e9 + 123.775029e9) / 1578478191
+TRAFFIC_NOTE = "ncu dram bytes per aligned base (profiles/kernel_r01f_pair.md, 150k-read launch) x aligned bases of this launch"
 METRIC = "aligned_gbp_per_s"
 UNIT = "Gbp/s"
 
