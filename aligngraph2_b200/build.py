@@ -7,7 +7,8 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "libag2_b200.so")
-SOURCES = [os.path.join(PKG, "csrc", "ag2_b200.cu"), os.path.join(PKG, "csrc", "pagraph.cu"), os.path.join(PKG, "host", "pg_job.cpp")]
+SOURCES = [os.path.join(PKG, "csrc", "ag2_b200.cu"), os.path.join(PKG, "csrc", "pagraph.cu"), os.path.join(PKG, "host", "pg_job.cpp"),
+           os.path.join(PKG, "host", "pg_travel.cpp")]
 HEADERS = [os.path.join(PKG, "csrc", n) for n in ("xdrop_device.cuh", "xdrop_lane.cuh", "seed_device.cuh", "index_kernels.cuh",
                                                    "rescue_device.cuh", "map_kernels.cuh", "kmer_kernels.cuh", "pagraph_kernels.cuh", "xdrop_pair.cuh", "h2ops.cuh")] + [
     os.path.join(ROOT, "include", "ag2_b200.h"), os.path.join(ROOT, "include", "ag2_pagraph.h")]
@@ -17,11 +18,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 HOST_SRC = os.path.join(PKG, "host", "mecat2ref_main.cpp")
 HOST_BIN = os.path.join(PKG, "bin", "mecat2ref")
-HOST_PROGRAMS = {"mecat2ref": "mecat2ref_main.cpp", "kmer_counter": "kmer_counter_main.cpp"}
+HOST_PROGRAMS = {"mecat2ref": "mecat2ref_main.cpp", "kmer_counter": "kmer_counter_main.cpp", "pagraph": "pagraph_main.cpp"}
 
 
 def build_host(force: bool = False, name: str = "mecat2ref") -> str:
-    """The drop-in executables (C++ hosts over the C ABI): `mecat2ref`, `kmer_counter`.
+    """The drop-in executables (C++ hosts over the C ABI): `mecat2ref`, `kmer_counter`, `pagraph`.
     Builds all of them, returns the path of `name`."""
     os.makedirs(os.path.dirname(HOST_BIN), exist_ok=True)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

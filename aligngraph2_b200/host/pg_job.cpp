@@ -14,6 +14,7 @@
 #include <sstream>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 namespace {
@@ -233,6 +234,8 @@ struct ag2_pg_job {
     std::vector<Block> blocks;
     std::vector<uint64_t> codes;
     int64_t first_read = 0, n_local = 0;
+    int32_t k = 0;                               // FileKmerIterator::kSize: the first word of the k-mer file
+    std::unordered_set<std::string> ok_ctg;      // okCtg of PGM/pagraph.cpp:164,259-261 (same container: contig.txt is written in its order)
 };
 
 namespace {
@@ -261,6 +264,7 @@ int ag2_pg_job_open(int device, const char* kmer_path, const char* ctg_path, con
     if (!read_file(kmer_path, kbuf) || kbuf.size() < 8) return jfail(j, AG2_EINVAL, std::string("cannot read ") + kmer_path);
     std::vector<uint64_t> words(kbuf.size() / 8);
     memcpy(words.data(), kbuf.data(), words.size() * 8);
+    j->k = (int32_t)words[0];
     int64_t nv = 0;
     if ((rc = ag2_pg_set_kmers(j->pg, words.data(), (int64_t)words.size(), &nv)) != AG2_OK) return jfail(j, rc, "ag2_pg_set_kmers");
     j->codes.resize((size_t)nv);
@@ -366,6 +370,53 @@ int ag2_pg_job_dump(ag2_pg_job* j, int block, const char* path, int append)
         fputc('\n', out);
     }
     fclose(out);
+    return AG2_OK;
+}
+
+// B9 on the graph of the handle: PAssembly::testTravel5 as run2 calls it (PGM/pagraph.cpp:244-261)
+int ag2_pg_job_travel(ag2_pg_job* j, int block, const ag2_pg_travel_params* prm, const char* out_dir)
+{
+    if (!j || !j->pg || !prm || !out_dir || block < 0 || block >= (int)j->blocks.size()) return AG2_EINVAL;
+    ag2_pg_stats st;
+    ag2_pg_get_stats(j->pg, &st);
+    const int64_t nv = st.n_vertices;
+    std::vector<int64_t> po((size_t)nv + 1), eo((size_t)nv + 1);
+    std::vector<uint32_t> ctg((size_t)st.positions + 1), ref((size_t)st.positions + 1), to((size_t)st.edges + 1);
+    std::vector<uint16_t> cnt((size_t)st.positions + 1);
+    std::vector<int32_t> step((size_t)st.edges + 1);
+    int rc = ag2_pg_graph_fetch(j->pg, po.data(), ctg.data(), ref.data(), cnt.data(), st.positions, eo.data(), to.data(), step.data(), st.edges);
+    if (rc != AG2_OK) return jfail(j, rc, "ag2_pg_graph_fetch");
+    ag2_pg_graph_view g{j->k, nv, j->codes.data(), po.data(), ctg.data(), ref.data(), cnt.data(), eo.data(), to.data(), step.data()};
+    std::vector<const char*> cn, rn;
+    for (auto& n : j->ctgs.name) cn.push_back(n.c_str());
+    for (auto& n : j->refs.name) rn.push_back(n.c_str());
+    ag2_pg_seqs cs{j->ctgs.size(), cn.data(), j->ctgs.bases.data(), j->ctgs.off.data()};
+    ag2_pg_seqs rs{j->refs.size(), rn.data(), j->refs.bases.data(), j->refs.off.data()};
+    const Block& B = j->blocks[block];
+    std::vector<int32_t> use;
+    std::vector<uint8_t> fwd;
+    for (auto& c : B.contigs) {
+        const int32_t id = j->ctgs.find(c.first);
+        if (id < 0) return jfail(j, AG2_EINVAL, "config.txt names a contig that is not in the contig file: " + c.first);
+        use.push_back(id);
+        fwd.push_back(c.second ? 1 : 0);
+    }
+    std::vector<int32_t> ok(use.size() * 2 + 1);
+    int64_t n_ok = 0;
+    const std::string prefix = std::to_string(block) + "_";
+    rc = ag2_pg_travel(&g, &cs, &rs, use.data(), fwd.data(), (int64_t)use.size(), prm, out_dir, prefix.c_str(), ok.data(), &n_ok);
+    if (rc != AG2_OK) return jfail(j, rc, std::string("ag2_pg_travel: cannot write under ") + out_dir);
+    for (int64_t i = 0; i < n_ok; ++i) j->ok_ctg.emplace(j->ctgs.name[ok[i]]);
+    return AG2_OK;
+}
+
+int ag2_pg_job_write_contig_list(ag2_pg_job* j, const char* out_dir)
+{
+    if (!j || !out_dir) return AG2_EINVAL;
+    FILE* f = fopen((std::string(out_dir) + "/contig.txt").c_str(), "w");
+    if (!f) return jfail(j, AG2_EINVAL, std::string("cannot write ") + out_dir + "/contig.txt");
+    for (auto& n : j->ok_ctg) fprintf(f, "%s\n", n.c_str());
+    fclose(f);
     return AG2_OK;
 }
 

@@ -1,4 +1,5 @@
-"""ctypes mirror of include/ag2_pagraph.h: PAGraph's A-Bruijn graph build on the GPU.
+"""ctypes mirror of include/ag2_pagraph.h: PAGraph's A-Bruijn graph build on the GPU and the
+traversal of the built graph (row B9) on the host.
 
 ``Job`` follows run2() of PAGraph/src/main/pagraph.cpp:69-243 over the file-level entry points: open the input set, then
 per config block load_block() + build() (+ dump()).  There is no CPU path: without the CUDA library or a GPU the calls
@@ -29,6 +30,20 @@ class Stats(C.Structure):
         return {n: (list(getattr(self, n)) if hasattr(getattr(self, n), "__len__") else getattr(self, n)) for n, _ in self._fields_}
 
 
+class GraphView(C.Structure):
+    _fields_ = [("k", C.c_int32), ("n_vertices", C.c_int64), ("codes", C.c_void_p), ("pos_off", C.c_void_p), ("ctg", C.c_void_p),
+                ("ref", C.c_void_p), ("count", C.c_void_p), ("edge_off", C.c_void_p), ("edge_to", C.c_void_p), ("edge_step", C.c_void_p)]
+
+
+class SeqsView(C.Structure):
+    _fields_ = [("n", C.c_int64), ("names", C.POINTER(C.c_char_p)), ("bases", C.c_char_p), ("offs", C.c_void_p)]
+
+
+class TravelParams(C.Structure):
+    _fields_ = [("deviation", C.c_int64), ("error_rate", C.c_double), ("start_split", C.c_double), ("min_len", C.c_int64),
+                ("threads", C.c_int32)]
+
+
 ALN_DTYPE = np.dtype([("query", "<i4"), ("target", "<i4"), ("score", "<u8"), ("qb", "<i8"), ("qe", "<i8"), ("tb", "<i8"),
                       ("te", "<i8"), ("forward", "<i4"), ("ncols", "<i4"), ("q_off", "<i8"), ("t_off", "<i8")])
 assert ALN_DTYPE.itemsize == 72
@@ -39,6 +54,7 @@ EXPORTS = [
     "ag2_pg_partition", "ag2_pg_stream_dev", "ag2_pg_import_dev", "ag2_pg_join", "ag2_pg_get_stats", "ag2_pg_graph_fetch",
     "ag2_pg_stream", "ag2_pg_job_open", "ag2_pg_job_close", "ag2_pg_job_error", "ag2_pg_job_blocks", "ag2_pg_job_block_ref",
     "ag2_pg_job_handle", "ag2_pg_job_load_block", "ag2_pg_job_dump",
+    "ag2_pg_travel_params_default", "ag2_pg_travel", "ag2_pg_job_travel", "ag2_pg_job_write_contig_list",
 ]
 
 _bound = False
@@ -84,6 +100,12 @@ def _L():
     L.ag2_pg_job_handle.restype = vp
     L.ag2_pg_job_load_block.argtypes = [vp, i32, i32, i32]
     L.ag2_pg_job_dump.argtypes = [vp, i32, C.c_char_p, i32]
+    L.ag2_pg_travel_params_default.argtypes = [C.POINTER(TravelParams)]
+    L.ag2_pg_travel_params_default.restype = None
+    L.ag2_pg_travel.argtypes = [C.POINTER(GraphView), C.POINTER(SeqsView), C.POINTER(SeqsView), vp, vp, i64, C.POINTER(TravelParams),
+                                C.c_char_p, C.c_char_p, vp, C.POINTER(i64)]
+    L.ag2_pg_job_travel.argtypes = [vp, i32, C.POINTER(TravelParams), C.c_char_p]
+    L.ag2_pg_job_write_contig_list.argtypes = [vp, C.c_char_p]
     _bound = True
     return L
 
@@ -93,6 +115,44 @@ def default_params(epsilon: int = 10, cov: int = 1) -> Params:
     _L().ag2_pg_params_default(C.byref(p))
     p.epsilon, p.cov_filter = epsilon, cov
     return p
+
+
+def travel_params(epsilon: int = 10, min_len: int = 50, threads: int = 1) -> TravelParams:
+    """PGM/pagraph.cpp:123-126,247-256: deviation = 2 * epsilon, errorRate 0.15, startSplit 0.90."""
+    p = TravelParams()
+    _L().ag2_pg_travel_params_default(C.byref(p))
+    p.deviation, p.min_len, p.threads = 2 * epsilon, min_len, threads
+    return p
+
+
+def _seqs_view(names, seqs):
+    arr = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+    bases = b"".join(seqs)
+    offs = np.concatenate(([0], np.cumsum([len(x) for x in seqs]))).astype(np.int64)
+    v = SeqsView(len(names), arr, bases, offs.ctypes.data)
+    return v, (arr, bases, offs)
+
+
+def travel(graph: "Graph", codes: np.ndarray, k: int, ctgs, refs, use, params: TravelParams, out_dir: str, prefix: str):
+    """B9 on a host graph (ag2_pg_travel): ``ctgs`` / ``refs`` = (names, sequences as bytes), ``use`` = [(contig index,
+    forward flag)] of the config block.  Writes the reference's files under out_dir; returns the success contig indices."""
+    L = _L()
+    keep = [np.ascontiguousarray(a) for a in (codes.astype(np.uint64), graph.pos_off.astype(np.int64), graph.ctg.astype(np.uint32),
+                                               graph.ref.astype(np.uint32), graph.count.astype(np.uint16), graph.edge_off.astype(np.int64),
+                                               graph.edge_to.astype(np.uint32), graph.edge_step.astype(np.int32))]
+    gv = GraphView(k, len(codes), *[a.ctypes.data for a in keep])
+    cv, ck = _seqs_view(*ctgs)
+    rv, rk = _seqs_view(*refs)
+    uc = np.array([u[0] for u in use], np.int32)
+    uf = np.array([1 if u[1] else 0 for u in use], np.uint8)
+    ok = np.zeros(2 * len(use) + 1, np.int32)
+    n_ok = C.c_int64()
+    rc = L.ag2_pg_travel(C.byref(gv), C.byref(cv), C.byref(rv), uc.ctypes.data, uf.ctypes.data, len(use), C.byref(params),
+                         out_dir.encode(), prefix.encode(), ok.ctypes.data, C.byref(n_ok))
+    if rc != 0:
+        raise _lib.Ag2Error(f"ag2_pg_travel -> {_lib.ERRORS.get(rc, rc)}")
+    del ck, rk
+    return ok[:n_ok.value].tolist()
 
 
 class Graph:
@@ -154,6 +214,13 @@ class Job:
         out = np.zeros(max(self.stats().n_vertices, 1), np.uint64)
         self._check(self.L.ag2_pg_fetch_codes(self.pg, out.ctypes.data, len(out)), "ag2_pg_fetch_codes")
         return out[:self.stats().n_vertices]
+
+    def travel(self, block: int, params: TravelParams, out_dir: str) -> None:
+        """B9 on the graph the handle holds (PAssembly::testTravel5): writes <out_dir>/<block>_<ctg>_<0|1>.txt etc."""
+        self._check(self.L.ag2_pg_job_travel(self.h, block, C.byref(params), out_dir.encode()), "ag2_pg_job_travel")
+
+    def write_contig_list(self, out_dir: str) -> None:
+        self._check(self.L.ag2_pg_job_write_contig_list(self.h, out_dir.encode()), "ag2_pg_job_write_contig_list")
 
     def block_ref(self, block: int) -> str:
         return self.L.ag2_pg_job_block_ref(self.h, block).decode()

@@ -149,6 +149,53 @@ ag2_pg *ag2_pg_job_handle(ag2_pg_job *job);
 int ag2_pg_job_load_block(ag2_pg_job *job, int block, int rank, int world);
 int ag2_pg_job_dump(ag2_pg_job *job, int block, const char *path, int append);
 
+/* ---- B9: traversal and assembly of the walks -----------------------------------------------------------------------
+ * PAssembly::testTravel5 (PAGraph/src/tools/graph/PAssembly.cpp:11-336) over PAlgorithm::travelSequence
+ * (graph/PAlgorithm.cpp:145-426), graphTravel / walkStraight / classifySuccessors (graph/PAlgorithm.tcc:37-298) and
+ * PAlgorithm::seqToString (:428-489).  A host stage by design (SURVEY 8e "replicas only": 2 x contigs independent walks,
+ * each a sequential pointer chase) over the graph the device built; it needs no device and has no device variant. */
+typedef struct ag2_pg_graph_view {       /* what ag2_pg_graph_fetch + ag2_pg_fetch_codes return */
+    int32_t k;                           /* k-mer size (first word of solid_kmer_set.bin) */
+    int64_t n_vertices;
+    const uint64_t *codes;               /* ascending; dense vertex index = rank */
+    const int64_t *pos_off;              /* n_vertices + 1 */
+    const uint32_t *ctg, *ref;           /* packed positions (PositionMapper::dualToSingle), sorted by (ctg, ref) per vertex */
+    const uint16_t *count;               /* abundance of each position */
+    const int64_t *edge_off;             /* n_vertices + 1 */
+    const uint32_t *edge_to;             /* sorted by (to, step) per vertex */
+    const int32_t *edge_step;
+} ag2_pg_graph_view;
+
+typedef struct ag2_pg_seqs {             /* a sequence database (AutoSeqDatabase): names = first token after '>' */
+    int64_t n;
+    const char *const *names;
+    const char *bases;                   /* ASCII as in the file, concatenated; anything but CcGgTt reads as A (CompressedSeq.cpp:16-26) */
+    const int64_t *offs;                 /* n + 1 */
+} ag2_pg_seqs;
+
+typedef struct ag2_pg_travel_params {    /* PGM/pagraph.cpp:123-126,247-256 */
+    int64_t deviation;                   /* 2 * --epsilon */
+    double error_rate;                   /* 0.15 */
+    double start_split;                  /* 0.90 */
+    int64_t min_len;                     /* -l, 50 */
+    int32_t threads;                     /* -t: start vertices per round = min(t, 8) (PAlgorithm.cpp:146), and the host threads used */
+} ag2_pg_travel_params;
+
+void ag2_pg_travel_params_default(ag2_pg_travel_params *p);
+
+/* One config block: walks the contigs (use_ctg[i], use_forward[i]) -- usedCtg of PGM/pagraph.cpp:209-214 -- and writes
+ * <out_dir>/<prefix><ctg>_<0|1>.txt for each, then <..>.fasta / .help / .con for every chain that connects contigs or
+ * extends one (PAssembly.cpp:229-333).  ok_ctg[0..*n_ok) = contig indices of the returned success set in its std::set order
+ * (a contig walked in both orientations appears twice); room for 2 * n_use entries. */
+int ag2_pg_travel(const ag2_pg_graph_view *g, const ag2_pg_seqs *ctgs, const ag2_pg_seqs *refs, const int32_t *use_ctg,
+                  const uint8_t *use_forward, int64_t n_use, const ag2_pg_travel_params *params, const char *out_dir,
+                  const char *prefix, int32_t *ok_ctg, int64_t *n_ok);
+
+/* The same on the job's current block: fetches the graph of the handle, prefix "<block>_", and remembers the success set.
+ * ag2_pg_job_write_contig_list writes <out_dir>/contig.txt (PGM/pagraph.cpp:265-269) from all blocks travelled so far. */
+int ag2_pg_job_travel(ag2_pg_job *job, int block, const ag2_pg_travel_params *params, const char *out_dir);
+int ag2_pg_job_write_contig_list(ag2_pg_job *job, const char *out_dir);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,12 @@
  * B2-B8 because it only ever prints the vertices that end up on a path.
  *
  *   pagraph_dump <thread> <kmer.bin> <ctg.fasta> <ref.fasta> <pre dir> <ctg-to-ref aln> <epsilon> <cov> <out.txt>
+ *                [<travel threads> <travel out dir> [<minLen>]]
+ *
+ * With the optional arguments the program goes on exactly as run2 does (pagraph.cpp:225-269): PAssembly::testTravel5
+ * on every block and contig.txt -- but with its own thread count, so that the traversal's `min(threadNum, 8)` start
+ * vertices (PAlgorithm.cpp:146) can be pinned on the deterministic `-t 1` graph (row B9; the unmodified `pagraph -t 8`
+ * would also build the graph with 8 threads, which is not reproducible).
  *
  * Dump format (one line per vertex that holds anything; vertices in dense-index order):
  *   #config <n> <ref name>
@@ -50,6 +56,8 @@
 #include "align/Aligner.hpp"
 #include "position/PositionProcessor.hpp"
 #include "kmer/FileKmerIterator.hpp"
+#include "graph/PAssembly.hpp"
+#include "position/PositionMapper.hpp"
 #undef private
 
 struct Cfg {
@@ -81,7 +89,7 @@ static std::vector<Cfg> load_cfg(const std::string& path)
 
 int main(int argc, char** argv)
 {
-    if (argc != 10) {
+    if (argc != 10 && argc != 12 && argc != 13) {
         fprintf(stderr, "usage: pagraph_dump t kmer ctg ref pre aln eps cov out\n");
         return 2;
     }
@@ -91,6 +99,11 @@ int main(int argc, char** argv)
     std::size_t posError = (std::size_t)atoll(argv[7]), covFilter = (std::size_t)atoll(argv[8]);
     FILE* out = fopen(argv[9], "w");
     if (!out) return 2;
+    const bool travel = argc >= 12;
+    unsigned travelThreads = travel ? (unsigned)atoi(argv[10]) : 0;
+    std::string outDir = travel ? argv[11] : "";
+    std::size_t minLen = argc == 13 ? (std::size_t)atoll(argv[12]) : 50;
+    std::unordered_set<std::string> okCtg;
 
     auto configs = load_cfg(inputDir + "/config.txt");
     auto pKmerIt = std::make_shared<FileKmerIterator>(kmerPath);
@@ -142,6 +155,19 @@ int main(int argc, char** argv)
             for (auto& e : ch) fprintf(out, " %llu,%d", (unsigned long long)e.first, e.second);
             fputc('\n', out);
         }
+        if (travel) {                             /* pagraph.cpp:209-261 */
+            std::set<std::pair<std::string, bool>> usedCtg;
+            for (auto& ctg : config.contigs) usedCtg.emplace(ctg);
+            auto successCtg = PAssembly::testTravel5(outDir, std::to_string(n - 1) + "_", pPaGraph, pReadDB, pContigDB, pRefDB,
+                                                     std::make_shared<PositionMapper>(*pContigDB),
+                                                     std::make_shared<PositionMapper>(*pRefDB), usedCtg, posError * 2, 0.15, 0.90,
+                                                     minLen, travelThreads);
+            for (auto& success : successCtg) okCtg.emplace(success.first);
+        }
+    }
+    if (travel) {
+        std::ofstream ctgList(outDir + "/contig.txt");
+        for (auto& processCtg : okCtg) ctgList << processCtg << std::endl;
     }
     fclose(out);
     return 0;

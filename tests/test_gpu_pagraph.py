@@ -161,3 +161,74 @@ def test_synthetic_set_with_gpu_kmer_counter_equals_oracle(tmp_path):
     got = open(j("gpu.txt"), "rb").read()
     assert got == want, _explain(got, want)
     assert st.positions > 10000 and st.edges > 10000
+
+
+# ---- row B9 end to end: the drop-in `pagraph` executable (GPU build + host traversal) ---------------------------------
+@pytest.fixture(scope="module")
+def chain(tmp_path_factory):
+    import gen_pagraph_travel_golden as gen_travel
+    d = str(tmp_path_factory.mktemp("pagraph_travel"))
+    gen_travel.unpack(d)
+    return d
+
+
+def _compare_dirs(got, want):
+    bad = []
+    for n in sorted(set(os.listdir(got)) | set(os.listdir(want))):
+        a, b = os.path.join(got, n), os.path.join(want, n)
+        if not os.path.exists(a) or not os.path.exists(b) or open(a, "rb").read() != open(b, "rb").read():
+            bad.append(n)
+    return bad
+
+
+def test_chain_fixture_graph_equals_reference_dump(chain):
+    want = open(os.path.join(chain, "graph.txt"), "rb").read()
+    got, _ = _gpu_dump(chain, "gpu.txt", 10, 2)
+    assert got == want, _explain(got, want)
+
+
+@pytest.mark.parametrize("threads", [1, 8])
+def test_drop_in_pagraph_executable(chain, threads):
+    """bin/pagraph with the argv of AlignGraph2.py:414-427 (incl. the second `-r`): every file it writes -- walks, FASTA,
+    .con, .help, contig.txt -- equals what the reference classes write (t1/ is also what `pagraph -t 1` itself writes)."""
+    import subprocess
+    from aligngraph2_b200 import build
+    build.build()
+    exe = build.build_host(name="pagraph")
+    out = os.path.join(chain, f"exe{threads}")
+    os.makedirs(out, exist_ok=True)
+    r = subprocess.run([exe, "-t", str(threads), "-r", "dummy", "-k", "solid.bin", "-c", "ctg.fasta", "-R", "ref.fasta", "-p", ".", "-a", "c2r.ref",
+                        "-o", out, "-r", "50", "--epsilon", "10", "-v", "2"], cwd=chain, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    assert _compare_dirs(out, os.path.join(chain, f"t{threads}")) == []
+    assert os.path.getsize(os.path.join(out, "0_0_0.fasta")) > 20000
+
+
+def test_drop_in_pagraph_against_reference_binary(small):
+    """Two config blocks, two references, a contig used in reverse: against the unmodified `pagraph -t 1` run on this box."""
+    import subprocess
+    from aligngraph2_b200 import build
+    ref_exe = os.path.join(gen.REFDIR, "pagraph")
+    if not os.path.exists(ref_exe):
+        pytest.skip("oracle/_ref/pagraph not built on this box")
+    build.build()
+    exe = build.build_host(name="pagraph")
+    for name, prog in (("ref_out", ref_exe), ("gpu_out", exe)):
+        os.makedirs(os.path.join(small, name), exist_ok=True)
+        r = subprocess.run([prog, "-t", "1", "-r", "dummy", "-k", "solid.bin", "-c", "ctg.fasta", "-R", "ref.fasta", "-p", ".", "-a", "c2r.ref",
+                            "-o", name, "-r", "50", "--epsilon", "10", "-v", "2"], cwd=small, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+    assert _compare_dirs(os.path.join(small, "gpu_out"), os.path.join(small, "ref_out")) == []
+    assert len(os.listdir(os.path.join(small, "ref_out"))) == 4
+
+
+def test_pagraph_executable_usage_errors(chain):
+    import subprocess
+    from aligngraph2_b200 import build
+    build.build()
+    exe = build.build_host(name="pagraph")
+    assert subprocess.run([exe], capture_output=True).returncode == 0                      # no arguments: help, 0 (pagraph.cpp:88-91)
+    assert subprocess.run([exe, "--bogus", "1"], capture_output=True).returncode == 1       # parse error: 1 (:98-102)
+    r = subprocess.run([exe, "-k", "missing.bin", "-c", "ctg.fasta", "-R", "ref.fasta", "-p", ".", "-a", "c2r.ref", "-o", "."], cwd=chain,
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "missing.bin" in r.stderr
