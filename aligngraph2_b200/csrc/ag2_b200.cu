@@ -10,6 +10,8 @@
 #include "map_kernels.cuh"
 #include "kmer_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -132,6 +134,18 @@ __global__ void set_slots_kernel(ExtGeom *geom, const int64_t *prefix, const int
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         geom[first + i].slot = prefix[first + i] - prefix[first];
         geom[first + i].meta = meta_prefix[first + i] - meta_prefix[first];
+    }
+}
+
+// Longest-first order of a chunk's directions: key = columns reserved for the direction (proportional to the bases it
+// can extend over), so the directions started last, when the queue runs dry, are the shortest ones.
+__global__ void chain_keys_kernel(const ExtGeom *geom, int64_t n_chains, uint32_t *keys, int32_t *ids)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_chains; t += (int64_t)gridDim.x * blockDim.x) {
+        const ExtGeom g = geom[t >> 1];
+        const int32_t cap = g.valid ? ((t & 1) ? g.capR : g.capL) : 0;
+        keys[t] = (uint32_t)max(cap, 0);
+        ids[t] = (int32_t)t;
     }
 }
 
@@ -274,6 +288,7 @@ struct ag2_ctx {
     int64_t out_total = 0;
     DevBuf tb, tb_wide, tb_pair;
     DevBuf wide_queue, lane_queue, lane_resume;
+    DevBuf order_keys, order_keys2, order_ids, order_queue, order_tmp;   // longest-first queue of the pair kernel
     DevBuf scalars;                     // ChainCounters + work counters + totals
     size_t ws_limit = (size_t)24 << 30; // bytes per workspace string per chunk (resident runs: one chunk, no drain tails)
     size_t ws_limit_streamed = (size_t)3 << 30; // chunk size when results stream to host buffers while the next chunk computes
@@ -281,6 +296,7 @@ struct ag2_ctx {
     cudaEvent_t chunk_done = nullptr;
     bool ran = false;
     int64_t stats_lane_chains = 0;      // directions the pair kernel handed to the lane kernel (last run)
+    int64_t stats_direct_wide = 0;      // of those, how many went straight to the wide kernel
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> chain_events;
@@ -423,7 +439,8 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
                      &ctx->km_out, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
-                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->scalars};
+                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->scalars,
+                     &ctx->order_keys, &ctx->order_keys2, &ctx->order_ids, &ctx->order_queue, &ctx->order_tmp};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->chain_events) {
@@ -567,7 +584,15 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     if (occ < 1) occ = 1;
     const int lane_grid = ctx->sm_count * occ;
     RESERVE(ctx->tb, (size_t)kLaneScratch * lane_grid * kLaneThreads);
-    const int wide_grid = ctx->sm_count;
+    int wocc = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, xdrop_chains_kernel<kWideK, kWideWarps>, kWideWarps * 32, 0));
+    if (wocc < 1) wocc = 1;
+    if (wocc > 8) wocc = 8;
+    const int wide_grid = ctx->sm_count * wocc;
+    // what the pair kernel hands over goes straight to the wide kernel (one WARP per direction, restarted from its first
+    // block: a few ms of latency) unless there is more of it than the wide grid absorbs in a few rounds; then the lane
+    // kernel (one THREAD per direction, resumed at the failing block) has the higher throughput
+    const unsigned lane_threshold = (unsigned)wide_grid * kWideWarps * 4;
     const size_t tbw_stride = (size_t)(kMaxBlk + 2) * TbLayout<kWideK>::kRowBytes;
     RESERVE(ctx->tb_wide, tbw_stride * wide_grid * kWideWarps);
 
@@ -576,6 +601,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     if (fresh_stats) {
         CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
         ctx->stats_lane_chains = 0;
+        ctx->stats_direct_wide = 0;
     }
     extend_setup_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(d_cand, n, sq, ctx->n_reads,
                                                                          (ExtGeom *)ctx->geom.p, (int64_t *)ctx->caps.p,
@@ -605,6 +631,16 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     RESERVE(ctx->ws_q, max_chunk + 64);
     RESERVE(ctx->ws_t, max_chunk + 64);
     RESERVE(ctx->meta, (max_meta + 16) * 4);
+    int64_t max_cn = 0;
+    for (auto &c : chunks) max_cn = std::max(max_cn, c.second - c.first);
+    size_t order_tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, order_tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                 (const int32_t *)nullptr, (int32_t *)nullptr, (int)(2 * max_cn), 0, 24, st));
+    RESERVE(ctx->order_keys, (size_t)max_cn * 2 * 4 + 16);
+    RESERVE(ctx->order_keys2, (size_t)max_cn * 2 * 4 + 16);
+    RESERVE(ctx->order_ids, (size_t)max_cn * 2 * 4 + 16);
+    RESERVE(ctx->order_queue, (size_t)max_cn * 2 * 4 + 16);
+    RESERVE(ctx->order_tmp, order_tmp_bytes + 16);
     // upper bound of the dense strings: every column consumes a base of the read or of its window
     {
         int rk = reserve_keep(ctx, ctx->out_q, (size_t)(dense_base_in + pf[n]) + 64, (size_t)dense_base_in);
@@ -640,7 +676,16 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         LaneArgs pa = a;
         pa.scratch = (uint8_t *)ctx->tb_pair.p;
         pa.n_chains = 2 * cn;
-        pa.queue = nullptr;
+        // longest directions first (chain_keys_kernel): no long direction is left running alone when the queue runs dry
+        chain_keys_kernel<<<grid_for(2 * cn, 256, ctx->sm_count), 256, 0, st>>>((const ExtGeom *)ctx->geom.p + lo, 2 * cn,
+                                                                                (uint32_t *)ctx->order_keys.p, (int32_t *)ctx->order_ids.p);
+        {
+            size_t tmp = ctx->order_tmp.cap;
+            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->order_tmp.p, tmp, (const uint32_t *)ctx->order_keys.p, (uint32_t *)ctx->order_keys2.p,
+                                                         (const int32_t *)ctx->order_ids.p, (int32_t *)ctx->order_queue.p, (int)(2 * cn), 0, 24, st));
+        }
+        launches += 2;
+        pa.queue = (const int32_t *)ctx->order_queue.p;
         pa.next = &sc->next_pair;
         pa.wide_queue = (int32_t *)ctx->lane_queue.p;
         pa.wide_count = &sc->lane_count;
@@ -654,7 +699,13 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         CK(cudaStreamSynchronize(st));
         launches += 2;
         ctx->stats_lane_chains += n_lane;
-        if (n_lane > 0) {
+        const bool lane_path = n_lane > lane_threshold;
+        if (n_lane > 0 && !lane_path) { // few: the wide kernel takes them directly
+            n_wide = n_lane;
+            ctx->stats_direct_wide += n_lane;
+            CK(cudaMemcpyAsync(ctx->wide_queue.p, ctx->lane_queue.p, (size_t)n_lane * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        if (n_lane > 0 && lane_path) {
             // directions the pair window could not hold (or with a target block under 32 bases): lane kernel, from that block on
             a.scratch = (uint8_t *)ctx->tb.p;
             a.n_chains = n_lane;
@@ -729,7 +780,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     s.rows = (int64_t)hs.ctr.rows;
     s.blocks = (int64_t)hs.ctr.blocks;
     s.interior = (int64_t)hs.ctr.interior;
-    s.wide_chains = (int64_t)hs.ctr.wide;
+    s.wide_chains = (int64_t)hs.ctr.wide + ctx->stats_direct_wide;
     s.aligned = (int64_t)hs.aligned;
     s.columns = (int64_t)hs.columns;
     s.launches = (fresh_stats ? 0 : s.launches) + launches;

@@ -37,6 +37,7 @@ TRAFFIC_BYTES_PER_ALIGNED_BASE = (121.513232e9 + 123.775029e9) / 1578478191
 TRAFFIC_NOTE = "ncu dram bytes per aligned base (profiles/kernel_r01f_pair.md, 150k-read launch) x aligned bases of this launch"
 METRIC = "aligned_gbp_per_s"
 UNIT = "Gbp/s"
+DTYPE = "f16"          # the DP scores are exact integers held as binary16, two extension directions per 32-bit register (xdrop_pair.cuh)
 
 
 def parse():
@@ -358,11 +359,19 @@ def main():
         h_s = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
         rec_np = rec.numpy().view(RECORD_DTYPE)
 
+        parts = [0.0, 0.0]
+
         def step():
-            dev.load_reads(bases=bases_np, offsets=h_off)
-            return dev.extend_batch_into(h_cand, rec_np, h_q.numpy(), h_s.numpy())
+            t0 = time.perf_counter()
+            dev.load_reads(bases=bases_np, offsets=h_off)                       # returns after the pack kernel (synchronous)
+            t1 = time.perf_counter()
+            u = dev.extend_batch_into(h_cand, rec_np, h_q.numpy(), h_s.numpy())  # returns when the last bytes are home
+            parts[0] += t1 - t0
+            parts[1] += time.perf_counter() - t1
+            return u
 
         step()
+        parts[0] = parts[1] = 0.0
         barrier()
         e0.record(stream)
         used = 0
@@ -379,7 +388,8 @@ def main():
             dist.all_reduce(a2, op=dist.ReduceOp.SUM)
         e2e = {"value": float(a2.item()) * args.steps / (float(t2.item()) * 1e-3) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(total_bases + h_off.nbytes + h_cand.nbytes) * world,
-               "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used) * world, "ms_per_step": float(t2.item()) / args.steps}
+               "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used) * world, "ms_per_step": float(t2.item()) / args.steps,
+               "reads_load_ms": parts[0] * 1e3 / args.steps, "extend_batch_ms": parts[1] * 1e3 / args.steps}
 
     # ---- the stages in front of the extension on the same batch (not part of the headline metric) ----
     stages = None
@@ -434,7 +444,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int32", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+                "dtype": DTYPE, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(st["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
                 "stats": {k: st[k] for k in ("cells", "rows", "blocks", "aligned", "columns", "lane_chains", "wide_chains", "interior")}}
         print(json.dumps(line))

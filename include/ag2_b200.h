@@ -69,7 +69,7 @@ typedef struct ag2_extend_stats {
     int64_t interior;     /* wide kernel: rows that needed the interior-pruned-cell fix-up */
     int64_t launches;     /* kernel launches made by the call */
     double kernel_ms;     /* CUDA-event time of the dominant kernel (xdrop_pair_kernel) */
-    int64_t lane_chains;  /* extension directions the pair kernel handed to the lane kernel (which restarts them) */
+    int64_t lane_chains;  /* extension directions the pair kernel handed on (to the wide kernel when few, else to the lane kernel) */
 } ag2_extend_stats;
 
 int ag2_ctx_create(int device, ag2_ctx **ctx);
