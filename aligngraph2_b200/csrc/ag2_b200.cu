@@ -169,6 +169,13 @@ __global__ void __launch_bounds__(kPairThreads, 7) xdrop_pair_kernel(LaneArgs g)
     const int tid = threadIdx.x;
     uint8_t *scratch = g.scratch + (size_t)blockIdx.x * kPairCtaScratch; // the CTA's: traceback of its 128 directions interleaved
     pair_kernel_body(g, sm, tid, scratch);
+    if (g.done_ctas) { // tells the concurrent consumer that this CTA will publish nothing more
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(g.done_ctas, 1u);
+        }
+    }
 }
 
 // One warp per record: the two directions' workspace areas -> dense strings; fills aln_off.
@@ -213,6 +220,50 @@ __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
             ctr.wide += 1;
             if (lane == 0 && g.wide_count) g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)chain;
         }
+    }
+    if (lane == 0) {
+        atomicAdd(&g.counters->cells, ctr.cells);
+        atomicAdd(&g.counters->rows, ctr.rows);
+        atomicAdd(&g.counters->blocks, ctr.blocks);
+        atomicAdd(&g.counters->interior, ctr.interior);
+        atomicAdd(&g.counters->wide, ctr.wide);
+    }
+}
+
+// The wide path as a CONSUMER that runs beside the pair kernel: a few CTAs, launched first, poll the hand-over queue and
+// rerun each published direction at once (one warp per direction), so that no hand-over is left for after the pair kernel
+// when the GPU would sit idle behind a handful of sequential directions.  Tickets are taken only while producers are
+// active; [min(*next, *count), *count) is what the host still has to run afterwards.
+template <int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) xdrop_stream_kernel(ChainArgs g, const unsigned int *done_ctas, unsigned int n_producers)
+{
+    __shared__ WarpSmem smem[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem &sm = smem[warp];
+    uint8_t *tb = g.tb + ((size_t)blockIdx.x * WARPS + warp) * g.tb_stride;
+    ChainCounters ctr = {0, 0, 0, 0, 0};
+    const volatile int32_t *queue = g.queue;
+    const volatile unsigned int *done = done_ctas;
+    for (;;) {
+        int chain = -1;
+        if (lane == 0 && *done < n_producers) {
+            const unsigned long long t = atomicAdd(g.next, 1ull);
+            for (;;) {
+                chain = queue[t];
+                if (chain >= 0) break;
+                if (*done >= n_producers) { // everything that will ever be published is visible now
+                    __threadfence();
+                    chain = queue[t];
+                    break;
+                }
+                __nanosleep(4000);
+            }
+        }
+        chain = __shfl_sync(kFull, chain, 0);
+        if (chain < 0) break;
+        __threadfence();
+        const bool ok = run_chain<K>(g, chain, sm, tb, lane, ctr);
+        if (!ok) ctr.wide += 1;
     }
     if (lane == 0) {
         atomicAdd(&g.counters->cells, ctr.cells);
@@ -288,11 +339,14 @@ struct ag2_ctx {
     int64_t out_total = 0;
     DevBuf tb, tb_wide, tb_pair;
     DevBuf wide_queue, lane_queue, lane_resume;
+    DevBuf tb_stream;                   // traceback scratch of the consumer kernel's warps
+    cudaEvent_t side_done = nullptr;
     DevBuf order_keys, order_keys2, order_ids, order_queue, order_tmp;   // longest-first queue of the pair kernel
     DevBuf scalars;                     // ChainCounters + work counters + totals
     size_t ws_limit = (size_t)24 << 30; // bytes per workspace string per chunk (resident runs: one chunk, no drain tails)
     size_t ws_limit_streamed = (size_t)3 << 30; // chunk size when results stream to host buffers while the next chunk computes
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // high priority: the consumer of the pair kernel's hand-overs
     cudaEvent_t chunk_done = nullptr;
     bool ran = false;
     int64_t stats_lane_chains = 0;      // directions the pair kernel handed to the lane kernel (last run)
@@ -307,8 +361,8 @@ namespace {
 
 struct Scalars {
     ChainCounters ctr;
-    unsigned long long next_fast, next_wide, next_pair;
-    unsigned int wide_count, lane_count;
+    unsigned long long next_fast, next_wide, next_pair, next_post;
+    unsigned int wide_count, lane_count, pair_done, pad;
     unsigned long long aligned, columns;
 };
 
@@ -415,6 +469,8 @@ int ag2_ctx_create(int device, ag2_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMalloc(&ctx->scalars.p, sizeof(Scalars)) != cudaSuccess) {
@@ -440,7 +496,7 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
                      &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->scalars,
-                     &ctx->order_keys, &ctx->order_keys2, &ctx->order_ids, &ctx->order_queue, &ctx->order_tmp};
+                     &ctx->order_keys, &ctx->order_keys2, &ctx->order_ids, &ctx->order_queue, &ctx->order_tmp, &ctx->tb_stream};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->chain_events) {
@@ -451,6 +507,8 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->chunk_done) cudaEventDestroy(ctx->chunk_done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
+    if (ctx->side_done) cudaEventDestroy(ctx->side_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -595,6 +653,8 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     const unsigned lane_threshold = (unsigned)wide_grid * kWideWarps * 4;
     const size_t tbw_stride = (size_t)(kMaxBlk + 2) * TbLayout<kWideK>::kRowBytes;
     RESERVE(ctx->tb_wide, tbw_stride * wide_grid * kWideWarps);
+    const int stream_grid = std::max(1, std::min(48, ctx->sm_count / 3));   // consumer CTAs beside the pair kernel: each takes one pair CTA's place
+    RESERVE(ctx->tb_stream, tbw_stride * stream_grid * kWideWarps);
 
     const PackedSeqs sq = seqs_of(ctx);
     Scalars *sc = (Scalars *)ctx->scalars.p;
@@ -662,7 +722,8 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         const int64_t lo = chunks[ci].first, cn = chunks[ci].second - chunks[ci].first;
         set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p,
                                                                            (const int64_t *)ctx->meta_prefix.p, lo, cn);
-        CK(cudaMemsetAsync(&sc->next_fast, 0, 3 * sizeof(unsigned long long) + 2 * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(&sc->next_fast, 0, 4 * sizeof(unsigned long long) + 4 * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(ctx->lane_queue.p, 0xff, (size_t)cn * 2 * 4, st));   // -1 = not published
         LaneArgs a = {};
         a.seqs = sq;
         a.cand = d_cand + lo;
@@ -690,27 +751,53 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         pa.wide_queue = (int32_t *)ctx->lane_queue.p;
         pa.wide_count = &sc->lane_count;
         pa.resume = (LaneResume *)ctx->lane_resume.p;
+        pa.done_ctas = &sc->pair_done;
+        // the consumer of the hand-overs (xdrop_stream_kernel) goes first, on its own high-priority stream, once the chunk's
+        // inputs are in place: it must be resident before the pair kernel fills the SMs
+        ChainArgs cw = {};
+        cw.seqs = sq;
+        cw.cand = a.cand;
+        cw.geom = a.geom;
+        cw.res = a.res;
+        cw.ws_q = a.ws_q;
+        cw.ws_t = a.ws_t;
+        cw.tb = (uint8_t *)ctx->tb_stream.p;
+        cw.tb_stride = tbw_stride;
+        cw.queue = (const int32_t *)ctx->lane_queue.p;
+        cw.next = &sc->next_wide;
+        cw.counters = &sc->ctr;
+        CK(cudaStreamSynchronize(st));
+        xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->side_done, ctx->side_stream));
         CK(cudaEventRecord(ctx->chain_events[ci].first, st));
         xdrop_pair_kernel<<<pair_grid, kPairThreads, pair_smem, st>>>(pa);
         CK(cudaEventRecord(ctx->chain_events[ci].second, st));
         CK(cudaGetLastError());
-        unsigned int n_lane = 0, n_wide = 0;
-        CK(cudaMemcpyAsync(&n_lane, &sc->lane_count, sizeof n_lane, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamWaitEvent(st, ctx->side_done, 0));
+        unsigned int n_handed = 0, n_wide = 0;
+        unsigned long long taken = 0;
+        CK(cudaMemcpyAsync(&n_handed, &sc->lane_count, sizeof n_handed, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&taken, &sc->next_wide, sizeof taken, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        launches += 2;
-        ctx->stats_lane_chains += n_lane;
+        launches += 3;
+        ctx->stats_lane_chains += n_handed;
+        // [first, n_handed) was published after the consumer's last ticket: few -> wide kernel, many -> lane kernel
+        const unsigned int first = (unsigned int)std::min<unsigned long long>(taken, n_handed);
+        const unsigned int n_lane = n_handed - first;
+        ctx->stats_direct_wide += first;
         const bool lane_path = n_lane > lane_threshold;
-        if (n_lane > 0 && !lane_path) { // few: the wide kernel takes them directly
+        const int32_t *post_queue = (const int32_t *)ctx->lane_queue.p + first;
+        if (n_lane > 0 && !lane_path) {
             n_wide = n_lane;
             ctx->stats_direct_wide += n_lane;
-            CK(cudaMemcpyAsync(ctx->wide_queue.p, ctx->lane_queue.p, (size_t)n_lane * 4, cudaMemcpyDeviceToDevice, st));
         }
         if (n_lane > 0 && lane_path) {
-            // directions the pair window could not hold (or with a target block under 32 bases): lane kernel, from that block on
+            // one THREAD per direction, resumed at the block the pair window could not hold
             a.scratch = (uint8_t *)ctx->tb.p;
             a.n_chains = n_lane;
-            a.queue = (const int32_t *)ctx->lane_queue.p;
-            a.resume = (LaneResume *)ctx->lane_resume.p;
+            a.queue = post_queue;
+            a.resume = (LaneResume *)ctx->lane_resume.p + first;
             a.next = &sc->next_fast;
             a.wide_queue = (int32_t *)ctx->wide_queue.p;
             a.wide_count = &sc->wide_count;
@@ -719,6 +806,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             // directions that left the lane path too (band > 120 columns, or reservation exceeded): wide kernel
             CK(cudaMemcpyAsync(&n_wide, &sc->wide_count, sizeof n_wide, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            post_queue = (const int32_t *)ctx->wide_queue.p;
             ++launches;
         }
         if (n_wide > 0) {
@@ -732,8 +820,8 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             w.tb = (uint8_t *)ctx->tb_wide.p;
             w.tb_stride = tbw_stride;
             w.n_chains = n_wide;
-            w.queue = (const int32_t *)ctx->wide_queue.p;
-            w.next = &sc->next_wide;
+            w.queue = post_queue;
+            w.next = &sc->next_post;
             w.wide_queue = nullptr;
             w.wide_count = nullptr;
             w.counters = &sc->ctr;

@@ -74,7 +74,16 @@ struct LaneArgs {
     int32_t *wide_queue;
     unsigned int *wide_count;
     ChainCounters *counters;
+    unsigned int *done_ctas; // pair kernel: every CTA adds 1 when it has published all its hand-overs (may be null)
 };
+
+// Hand a direction over: the payload first, then -- fenced -- the queue entry, which a concurrently running consumer
+// (xdrop_stream_kernel) polls; the queue is pre-set to -1.
+__device__ __forceinline__ void publish_chain(int32_t *queue, unsigned slot, int64_t chain)
+{
+    __threadfence();
+    *reinterpret_cast<volatile int32_t *>(queue + slot) = (int32_t)chain;
+}
 
 // 16 two-bit codes starting at base position p (forward) of a packed sequence
 __device__ __forceinline__ uint32_t load16(const uint32_t *seq, int64_t p)

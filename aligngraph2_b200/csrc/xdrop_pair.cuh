@@ -601,8 +601,8 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
                 if (blk[h].qblk > 0 && blk[h].tblk > 0) {
                     if (blk[h].tblk < kPairMinN) { // the reference's row 0 may reach column N here: lane kernel
                         const unsigned slot = atomicAdd(g.wide_count, 1u);
-                        g.wide_queue[slot] = (int32_t)s[h].chain;
                         if (g.resume) g.resume[slot] = lane_save(s[h]);
+                        publish_chain(g.wide_queue, slot, s[h].chain);
                         ++handed;
                         s[h].chain = -1;
                     } else {
@@ -653,8 +653,8 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
                 c.chain = -1;
             } else if (rc == 2) { // c is still the state at the start of this block
                 const unsigned slot = atomicAdd(g.wide_count, 1u);
-                g.wide_queue[slot] = (int32_t)c.chain;
                 if (g.resume) g.resume[slot] = lane_save(c);
+                publish_chain(g.wide_queue, slot, c.chain);
                 ++handed;
                 c.chain = -1;
             }

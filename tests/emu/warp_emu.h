@@ -196,4 +196,5 @@ inline unsigned atomicAdd(unsigned *p, unsigned v)
     return o;
 }
 using std::max;
+inline void __threadfence() {}                 // one emulated warp: program order is memory order
 using std::min;
