@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -53,10 +54,10 @@ __device__ __forceinline__ unsigned encode_ascii(unsigned c, unsigned &irregular
 // one thread = 32 bases of one read = two 2-bit words + one "irregular" word.
 // poff[r] = packed base offset of read r (multiple of 32); offs[r] = ASCII offset.
 __global__ void pack_reads_kernel(const char *__restrict__ ascii, const int64_t *__restrict__ offs,
-                                  const int64_t *__restrict__ poff, int64_t n_reads, int64_t n_groups,
+                                  const int64_t *__restrict__ poff, int64_t n_reads, int64_t g_first, int64_t n_groups,
                                   uint32_t *__restrict__ out2, uint32_t *__restrict__ irr_out)
 {
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t g = g_first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < g_first + n_groups; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pb = g << 5;
         int64_t lo = 0, hi = n_reads - 1; // last read with poff[r] <= pb
         while (lo < hi) {
@@ -345,8 +346,19 @@ struct ag2_ctx {
     DevBuf scalars;                     // ChainCounters + work counters + totals
     size_t ws_limit = (size_t)24 << 30; // bytes per workspace string per chunk (resident runs: one chunk, no drain tails)
     size_t ws_limit_streamed = (size_t)3 << 30; // chunk size when results stream to host buffers while the next chunk computes
+    int64_t piece_bytes = (int64_t)256 << 20;   // ASCII bytes per upload piece of ag2_reads_load
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // high priority: the consumer of the pair kernel's hand-overs
+    cudaStream_t in_stream = nullptr;     // read uploads + packing
+    struct ReadPiece {
+        int64_t end_read;                 // reads [previous end, end_read) are packed once `ready` has happened
+        cudaEvent_t ready;
+    };
+    std::vector<ReadPiece> pieces;
+    std::vector<cudaEvent_t> piece_events;
+    bool reads_pending = false;           // an asynchronous load may still be in flight
+    std::vector<int64_t> h_poff;
+    std::vector<int32_t> h_lens;
     cudaEvent_t chunk_done = nullptr;
     bool ran = false;
     int64_t stats_lane_chains = 0;      // directions the pair kernel handed to the lane kernel (last run)
@@ -471,6 +483,7 @@ int ag2_ctx_create(int device, ag2_ctx **out)
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMalloc(&ctx->scalars.p, sizeof(Scalars)) != cudaSuccess) {
@@ -478,6 +491,9 @@ int ag2_ctx_create(int device, ag2_ctx **out)
         return AG2_ECUDA;
     }
     ctx->scalars.cap = sizeof(Scalars);
+    // test knobs: many small chunks / upload pieces on small inputs
+    if (const char *e = getenv("AG2_WS_STREAMED")) ctx->ws_limit_streamed = (size_t)std::max(1ll, atoll(e));
+    if (const char *e = getenv("AG2_PIECE_BYTES")) ctx->piece_bytes = std::max(1ll, atoll(e));
     *out = ctx;
     return AG2_OK;
 }
@@ -509,6 +525,11 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->side_done) cudaEventDestroy(ctx->side_done);
+    if (ctx->in_stream) {
+        cudaStreamSynchronize(ctx->in_stream);
+        cudaStreamDestroy(ctx->in_stream);
+    }
+    for (cudaEvent_t e : ctx->piece_events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -531,7 +552,7 @@ int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len)
     CK(cudaMemsetAsync(ctx->ref2.p, 0, (size_t)(groups * 2 + 8) * 4, st));
     CK(cudaMemsetAsync(ctx->ref_irr.p, 0, (size_t)(groups + 8) * 4, st));
     pack_reads_kernel<<<grid_for(groups, 256, ctx->sm_count), 256, 0, st>>>(
-        (const char *)ctx->ref_ascii.p, (const int64_t *)ctx->ref_offs.p, (const int64_t *)ctx->ref_offs.p + 2, 1, groups,
+        (const char *)ctx->ref_ascii.p, (const int64_t *)ctx->ref_offs.p, (const int64_t *)ctx->ref_offs.p + 2, 1, 0, groups,
         (uint32_t *)ctx->ref2.p, (uint32_t *)ctx->ref_irr.p);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st)); // h_offs is on the stack
@@ -541,12 +562,28 @@ int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len)
     return AG2_OK;
 }
 
-int ag2_reads_load(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t n)
+// ag2_reads_load / ag2_reads_load_async.  The ASCII bases go up in pieces of ~256 MB on the `in_stream`, each followed by
+// its pack kernel and an event, so that (a) copies and packing overlap and (b) the asynchronous form lets
+// ag2_xdrop_extend_batch start on the first reads while the later ones are still in flight.
+static int reads_barrier(ag2_ctx *ctx)
+{
+    if (ctx->reads_pending) {
+        CK(cudaStreamSynchronize(ctx->in_stream));
+        ctx->reads_pending = false;
+    }
+    return AG2_OK;
+}
+
+static int reads_load_impl(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t n, bool async)
 {
     if (!ctx || !bases || !offs || n <= 0 || offs[0] != 0) return fail(ctx, AG2_EINVAL, "ag2_reads_load: bad argument");
     CK(cudaSetDevice(ctx->device));
-    std::vector<int64_t> poff((size_t)n + 1);
-    std::vector<int32_t> lens((size_t)n);
+    int rb = reads_barrier(ctx);
+    if (rb != AG2_OK) return rb;
+    std::vector<int64_t> &poff = ctx->h_poff;
+    std::vector<int32_t> &lens = ctx->h_lens;
+    poff.resize((size_t)n + 1);
+    lens.resize((size_t)n);
     int64_t p = 0;
     for (int64_t r = 0; r < n; ++r) {
         const int64_t len = offs[r + 1] - offs[r];
@@ -563,28 +600,57 @@ int ag2_reads_load(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t
     RESERVE(ctx->read_len, (size_t)n * 4);
     RESERVE(ctx->reads2, (size_t)(groups * 2 + 4) * 4);
     RESERVE(ctx->reads_irr, (size_t)(groups + 4) * 4);
-    CK(cudaMemcpyAsync(ctx->ascii.p, bases, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->ascii_offs.p, offs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->read_off.p, poff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->read_len.p, lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (groups > 0) {
-        pack_reads_kernel<<<grid_for(groups, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
-            (const char *)ctx->ascii.p, (const int64_t *)ctx->ascii_offs.p, (const int64_t *)ctx->read_off.p, n, groups,
-            (uint32_t *)ctx->reads2.p, (uint32_t *)ctx->reads_irr.p);
-        CK(cudaGetLastError());
+    cudaStream_t in = ctx->in_stream;
+    CK(cudaMemcpyAsync(ctx->ascii_offs.p, offs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, in));
+    CK(cudaMemcpyAsync(ctx->read_off.p, poff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, in));
+    CK(cudaMemcpyAsync(ctx->read_len.p, lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, in));
+    CK(cudaStreamSynchronize(in));   // small; `offs` is the caller's and may go away after an asynchronous return
+    ctx->pieces.clear();
+    const int64_t piece_bytes = ctx->piece_bytes;
+    size_t k = 0;
+    for (int64_t r0 = 0; r0 < n;) {
+        int64_t r1 = r0 + 1;   // reads [r0, r1): up to piece_bytes of ASCII, at least one read
+        if (offs[n] - offs[r0] <= piece_bytes) r1 = n;
+        else r1 = std::max<int64_t>(r0 + 1, std::upper_bound(offs + r0, offs + n + 1, offs[r0] + piece_bytes) - offs - 1);
+        const int64_t b0 = offs[r0], b1 = offs[r1], g0 = poff[r0] >> 5, g1 = poff[r1] >> 5;
+        if (b1 > b0) CK(cudaMemcpyAsync((char *)ctx->ascii.p + b0, bases + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, in));
+        if (g1 > g0) {
+            pack_reads_kernel<<<grid_for(g1 - g0, 256, ctx->sm_count), 256, 0, in>>>(
+                (const char *)ctx->ascii.p, (const int64_t *)ctx->ascii_offs.p, (const int64_t *)ctx->read_off.p, n, g0, g1 - g0,
+                (uint32_t *)ctx->reads2.p, (uint32_t *)ctx->reads_irr.p);
+            CK(cudaGetLastError());
+        }
+        if (k >= ctx->piece_events.size()) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->piece_events.push_back(e);
+        }
+        CK(cudaEventRecord(ctx->piece_events[k], in));
+        ctx->pieces.push_back({r1, ctx->piece_events[k]});
+        ++k;
+        r0 = r1;
     }
-    CK(cudaStreamSynchronize(ctx->stream)); // poff/lens are stack-owned
+    ctx->reads_pending = true;
     ctx->n_reads = n;
     ctx->read_bases = total;
     {   // which reads enter the read index: the first <= 100 000 while the running length (+1 each) < 1e9 (:277)
-        int64_t lenl = 0, k = 0;
-        while (k < n && k < 100000 && lenl < 1000000000ll) {
-            lenl += (offs[k + 1] - offs[k]) + 1;
-            ++k;
+        int64_t lenl = 0, kk = 0;
+        while (kk < n && kk < 100000 && lenl < 1000000000ll) {
+            lenl += (offs[kk + 1] - offs[kk]) + 1;
+            ++kk;
         }
-        ctx->read_prefix_len = offs[k];
+        ctx->read_prefix_len = offs[kk];
     }
-    return AG2_OK;
+    return async ? AG2_OK : reads_barrier(ctx);
+}
+
+int ag2_reads_load(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t n) { return reads_load_impl(ctx, bases, offs, n, false); }
+int ag2_reads_load_async(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t n) { return reads_load_impl(ctx, bases, offs, n, true); }
+int ag2_reads_wait(ag2_ctx *ctx)
+{
+    if (!ctx) return AG2_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    return reads_barrier(ctx);
 }
 
 int ag2_extend_upload(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n)
@@ -609,10 +675,14 @@ struct HostSink { // caller-owned host buffers that receive each chunk's results
 };
 
 static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record *d_rec, int64_t dense_base_in, int64_t *dense_base_out,
-                        bool fresh_stats, HostSink *sink = nullptr)
+                        bool fresh_stats, HostSink *sink = nullptr, const ag2_candidate *h_cand = nullptr)
 {
     cudaStream_t st = ctx->stream;
     int launches = 0;
+    if (!h_cand) { // without the host's copy of the candidates nothing says which reads a chunk needs: wait for all of them
+        int rb = reads_barrier(ctx);
+        if (rb != AG2_OK) return rb;
+    }
     RESERVE(ctx->geom, (size_t)n * sizeof(ExtGeom));
     RESERVE(ctx->caps, (size_t)n * 8);
     RESERVE(ctx->prefix, (size_t)(n + 1) * 8);
@@ -623,7 +693,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     RESERVE(ctx->ok_len, (size_t)n * 8);
     RESERVE(ctx->dense_off, (size_t)(n + 1) * 8);
     RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
-    RESERVE(ctx->lane_queue, (size_t)n * 2 * 4);
+    RESERVE(ctx->lane_queue, ((size_t)n * 2 + 1024) * 4);   // + one unpublished ticket per consumer warp
     RESERVE(ctx->lane_resume, (size_t)n * 2 * sizeof(LaneResume));
 
     // pair kernel: the band window of 128 directions per CTA in shared memory
@@ -653,7 +723,13 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     const unsigned lane_threshold = (unsigned)wide_grid * kWideWarps * 4;
     const size_t tbw_stride = (size_t)(kMaxBlk + 2) * TbLayout<kWideK>::kRowBytes;
     RESERVE(ctx->tb_wide, tbw_stride * wide_grid * kWideWarps);
-    const int stream_grid = std::max(1, std::min(48, ctx->sm_count / 3));   // consumer CTAs beside the pair kernel: each takes one pair CTA's place
+    // same shared-memory carve-out as the pair kernel, or an SM that holds a consumer CTA could not take pair CTAs at all
+    CK(cudaFuncSetAttribute(xdrop_stream_kernel<kWideK, kWideWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int stream_want = 16;
+    if (const char *e = getenv("AG2_STREAM_GRID")) stream_want = atoi(e);   // tuning knob
+    const int stream_grid = std::max(1, std::min(std::min(48, stream_want), ctx->sm_count / 3));
+    static_assert(48 * kWideWarps <= 1024, "the hand-over queue keeps one spare entry per consumer warp");   // consumer CTAs beside the pair kernel: each takes one pair CTA's place
     RESERVE(ctx->tb_stream, tbw_stride * stream_grid * kWideWarps);
 
     const PackedSeqs sq = seqs_of(ctx);
@@ -720,10 +796,19 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     int64_t dense_base = dense_base_in;
     for (size_t ci = 0; ci < chunks.size(); ++ci) {
         const int64_t lo = chunks[ci].first, cn = chunks[ci].second - chunks[ci].first;
+        if (ctx->reads_pending && h_cand) { // an asynchronous read load is in flight: this chunk waits for the piece that holds its last read
+            int64_t last = -1;
+            for (int64_t i = lo; i < lo + cn; ++i) last = std::max<int64_t>(last, h_cand[i].read);
+            for (const auto &pc : ctx->pieces)
+                if (pc.end_read > last || &pc == &ctx->pieces.back()) {
+                    CK(cudaStreamWaitEvent(st, pc.ready, 0));
+                    break;
+                }
+        }
         set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p,
                                                                            (const int64_t *)ctx->meta_prefix.p, lo, cn);
         CK(cudaMemsetAsync(&sc->next_fast, 0, 4 * sizeof(unsigned long long) + 4 * sizeof(unsigned int), st));
-        CK(cudaMemsetAsync(ctx->lane_queue.p, 0xff, (size_t)cn * 2 * 4, st));   // -1 = not published
+        CK(cudaMemsetAsync(ctx->lane_queue.p, 0xff, ((size_t)cn * 2 + 1024) * 4, st));   // -1 = not published
         LaneArgs a = {};
         a.seqs = sq;
         a.cand = d_cand + lo;
@@ -937,8 +1022,9 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
     sink.t = saln_out;
     sink.cap = aln_cap;
     int64_t total = 0;
-    r = extend_batch(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, 0, &total, true, &sink);
+    r = extend_batch(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, 0, &total, true, &sink, cand);
     if (r != AG2_OK) return r;
+    if ((r = reads_barrier(ctx)) != AG2_OK) return r;   // reads no candidate refers to may still be on their way
     ctx->out_total = total;
     ctx->ran = true;
     if (aln_used) *aln_used = total;
@@ -1002,6 +1088,10 @@ int ag2_index_build(ag2_ctx *ctx, int cbl, double alpha, double beta)
     if (!ctx || cbl <= 0) return fail(ctx, AG2_EINVAL, "ag2_index_build: bad argument");
     if (!ctx->ref_len || !ctx->n_reads) return fail(ctx, AG2_ESTATE, "ag2_index_build: load reference and reads first");
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rb_ = reads_barrier(ctx);   // an asynchronous read load must have landed
+        if (rb_ != AG2_OK) return rb_;
+    }
     cudaStream_t st = ctx->stream;
     if (!ctx->ref_indexed) {
         int rc = build_ref_csr(ctx);
@@ -1062,6 +1152,10 @@ int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *ou
     if (!ctx || pass < 0 || pass > 1 || maxc < 1 || maxc > kMaxCand) return fail(ctx, AG2_EINVAL, "ag2_seed_candidates: bad argument");
     if (!ctx->votes_ready) return fail(ctx, AG2_ESTATE, "ag2_seed_candidates: call ag2_index_build first");
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rb_ = reads_barrier(ctx);   // an asynchronous read load must have landed
+        if (rb_ != AG2_OK) return rb_;
+    }
     cudaStream_t st = ctx->stream;
     const int64_t n = ctx->n_reads;
     RefIndex ix = {ctx->ref_len, (const int32_t *)ctx->ix_cnt.p, (const uint32_t *)ctx->ix_off.p, (const uint32_t *)ctx->ix_pos.p,
@@ -1108,6 +1202,10 @@ int ag2_extend_upload_from_seeds(ag2_ctx *ctx, int maxc, int64_t *n_out)
     if (!ctx || maxc < 1 || maxc > kMaxCand) return fail(ctx, AG2_EINVAL, "ag2_extend_upload_from_seeds: bad argument");
     if (!ctx->seed_ncand.p || !ctx->votes_ready) return fail(ctx, AG2_ESTATE, "ag2_extend_upload_from_seeds: call ag2_seed_candidates first");
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rb_ = reads_barrier(ctx);   // an asynchronous read load must have landed
+        if (rb_ != AG2_OK) return rb_;
+    }
     cudaStream_t st = ctx->stream;
     const int64_t n = ctx->n_reads;
     RESERVE(ctx->seed_need, (size_t)n * 8);
@@ -1236,6 +1334,10 @@ int ag2_map_reads(ag2_ctx *ctx, int maxc, int num_output, int64_t *n_records)
     if (!ctx || maxc < 1 || maxc > kMaxCand || num_output < 1) return fail(ctx, AG2_EINVAL, "ag2_map_reads: bad argument");
     if (!ctx->votes_ready) return fail(ctx, AG2_ESTATE, "ag2_map_reads: call ag2_index_build first");
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rb_ = reads_barrier(ctx);   // an asynchronous read load must have landed
+        if (rb_ != AG2_OK) return rb_;
+    }
     cudaStream_t st = ctx->stream;
     const int64_t n = ctx->n_reads;
     if (num_output > maxc) num_output = maxc; // mecat2ref.cpp:196-201
@@ -1315,6 +1417,10 @@ int ag2_kmer_add_reads(ag2_ctx *ctx)
     if (!ctx || !ctx->km_k) return fail(ctx, AG2_ESTATE, "ag2_kmer_add_reads: call ag2_kmer_begin first");
     if (!ctx->n_reads) return fail(ctx, AG2_ESTATE, "ag2_kmer_add_reads: no reads loaded");
     CK(cudaSetDevice(ctx->device));
+    {
+        const int rb_ = reads_barrier(ctx);   // an asynchronous read load must have landed
+        if (rb_ != AG2_OK) return rb_;
+    }
     std::vector<int64_t> last(1);
     CK(cudaMemcpy(last.data(), (const int64_t *)ctx->read_off.p + ctx->n_reads, 8, cudaMemcpyDeviceToHost));
     const int64_t groups = last[0] >> 5;

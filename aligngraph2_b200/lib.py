@@ -32,7 +32,7 @@ class ExtendStats(C.Structure):
 
 
 EXPORTS = [
-    "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load",
+    "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load", "ag2_reads_load_async", "ag2_reads_wait",
     "ag2_xdrop_extend_batch", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
     "ag2_ctx_stream", "ag2_index_build", "ag2_index_fetch", "ag2_seed_candidates",
     "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch",
@@ -65,6 +65,8 @@ def load() -> C.CDLL:
     L.ag2_version.restype = C.c_char_p
     L.ag2_ref_load.argtypes = [vp, vp, i64]
     L.ag2_reads_load.argtypes = [vp, vp, vp, i64]
+    L.ag2_reads_load_async.argtypes = [vp, vp, vp, i64]
+    L.ag2_reads_wait.argtypes = [vp]
     L.ag2_xdrop_extend_batch.argtypes = [vp, vp, i64, vp, vp, vp, i64, C.POINTER(i64)]
     L.ag2_extend_upload.argtypes = [vp, vp, i64]
     L.ag2_extend_run.argtypes = [vp]

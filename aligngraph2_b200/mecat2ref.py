@@ -77,6 +77,21 @@ class Mecat2RefDevice:
         self._check(self._L.ag2_reads_load(self._ctx, bases.ctypes.data, offsets.ctypes.data, n), "ag2_reads_load")
         self.n_reads = n
 
+    def load_reads_async(self, bases, offsets) -> None:
+        """ag2_reads_load_async: returns once the copies are queued; ``bases`` (ideally pinned) must stay alive and unchanged
+        until a later call on this device has returned.  extend_batch_into() then starts on the first reads while the
+        rest is still being copied."""
+        bases = _as_bytes_array(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = offsets.size - 1
+        self._pending_bases = bases
+        self._check(self._L.ag2_reads_load_async(self._ctx, bases.ctypes.data, offsets.ctypes.data, n), "ag2_reads_load_async")
+        self.n_reads = n
+
+    def wait_reads(self) -> None:
+        self._check(self._L.ag2_reads_wait(self._ctx), "ag2_reads_wait")
+        self._pending_bases = None
+
     # -- index + seeding -------------------------------------------------------------------------
     def build_index(self, cbl: int = 200, alpha: float = 0.5, beta: float = 2.0) -> None:
         """build_read_index + creat_ref_index + get_vote (impl_large.cpp:258-608) for the loaded reference and

@@ -363,7 +363,7 @@ def main():
 
         def step():
             t0 = time.perf_counter()
-            dev.load_reads(bases=bases_np, offsets=h_off)                       # returns after the pack kernel (synchronous)
+            dev.load_reads_async(bases_np, h_off)                               # queues the copies; the first chunk starts when its reads are up
             t1 = time.perf_counter()
             u = dev.extend_batch_into(h_cand, rec_np, h_q.numpy(), h_s.numpy())  # returns when the last bytes are home
             parts[0] += t1 - t0

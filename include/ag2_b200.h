@@ -86,6 +86,14 @@ int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len);
  * (anything but upper-case ACGT). */
 int ag2_reads_load(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t n_reads);
 
+/* The same batch, but the call returns as soon as the copies are queued: the bases go up in pieces on a copy stream.
+ * `bases` must stay valid and unchanged until ag2_reads_wait() or any later call on this context has returned (`offs` is
+ * consumed before the call returns).  ag2_xdrop_extend_batch, given candidates in read order, starts extending the first
+ * reads while the later ones are still in flight (the reference has no counterpart: its load_fastq batch,
+ * mecat2ref_impl_large.cpp:1965-1991, is in host memory already).  Every other entry point waits for the whole batch. */
+int ag2_reads_load_async(ag2_ctx *ctx, const char *bases, const int64_t *offs, int64_t n_reads);
+int ag2_reads_wait(ag2_ctx *ctx);
+
 /* extend_candidate x n.  rec_out[n]; qaln_out/saln_out receive ASCII ACGT- columns of the ok
  * records back to back (record i at [aln_off, aln_off + aln_len)); aln_cap is the capacity of
  * each string buffer, *aln_used the bytes written.  AG2_ECAP if too small (rec_out is still

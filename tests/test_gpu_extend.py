@@ -162,3 +162,44 @@ def test_properties_at_scale(dev):
     # idempotence: a second run over the same resident inputs gives identical bytes
     rec2, qa2, sa2 = dev.extend(cand)
     assert np.array_equal(rec, rec2) and np.array_equal(qa, qa2) and np.array_equal(sa, sa2)
+
+
+@pytest.mark.parametrize("order", ["read", "shuffled"])
+def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order):
+    """ag2_reads_load_async + ag2_xdrop_extend_batch with host buffers: the reads go up in many pieces while the candidates
+    are extended in many chunks (test knobs make both small), each chunk waiting only for the piece that holds its last
+    read.  Records and strings must equal the synchronous, resident run -- whatever the candidate order."""
+    from aligngraph2_b200.lib import RECORD_DTYPE
+    from aligngraph2_b200.mecat2ref import Mecat2RefDevice
+    d = synth.make_batch_torch(99, 400_000, 600, 4000)
+    ref, bases, off = d["ref"].numpy(), d["bases"].numpy(), d["offsets"].numpy()
+    idx = np.arange(600)
+    if order == "shuffled":
+        np.random.default_rng(1).shuffle(idx)
+    cand = dev.make_candidates(idx, d["strand"].numpy()[idx], d["loc1"].numpy()[idx], d["loc2"].numpy()[idx], score=7)
+    dev.load_reference(ref)
+    dev.load_reads(bases=bases, offsets=off)
+    rec, qa, sa = dev.extend(cand)
+    assert rec["ok"].mean() > 0.98
+
+    monkeypatch.setenv("AG2_WS_STREAMED", str(400_000))    # ~ 30 reads per chunk
+    monkeypatch.setenv("AG2_PIECE_BYTES", str(100_000))    # ~ 25 reads per piece
+    dev2 = Mecat2RefDevice(0)
+    try:
+        dev2.load_reference(ref)
+        for _ in range(2):                                  # a second batch on the same context reuses pieces and events
+            rec2 = np.zeros(600, RECORD_DTYPE)
+            q2, s2 = np.zeros(qa.size + 64, np.uint8), np.zeros(sa.size + 64, np.uint8)
+            dev2.load_reads_async(bases, off)
+            used = dev2.extend_batch_into(cand, rec2, q2, s2)
+            assert used == qa.size
+            assert np.array_equal(rec2, rec) and np.array_equal(q2[:used], qa) and np.array_equal(s2[:used], sa)
+        st = dev2.stats()
+        assert st["cells"] == dev.stats()["cells"] and st["launches"] > 20 * 5   # really went through many chunks
+        # every other entry point waits for an asynchronous load by itself
+        dev2.load_reads_async(bases, off)
+        dev2.build_index(200, 0.5, 2.0)
+        dev2.load_reads_async(bases, off)
+        dev2.wait_reads()
+    finally:
+        dev2.close()
