@@ -19,6 +19,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <thread>
+#include <chrono>
 
 using namespace ag2;
 
@@ -29,6 +31,7 @@ namespace {
 
 constexpr int kWideK = 23;        // 736 columns: covers every possible block (N <= 718)
 constexpr int kWideWarps = 2;
+constexpr int kMaxStreamChunks = 256;
 
 // ---------------------------------------------------------------------------------------------
 // packing kernels (A8: get_dna_encode_table + ">3 -> 0", MC/defs.cpp:3-36, mecat2ref_aux.cpp:195-197)
@@ -53,9 +56,12 @@ __device__ __forceinline__ unsigned encode_ascii(unsigned c, unsigned &irregular
 
 // one thread = 32 bases of one read = two 2-bit words + one "irregular" word.
 // poff[r] = packed base offset of read r (multiple of 32); offs[r] = ASCII offset.
+// piece_done / piece_flag (may be null): the CTA that finishes last raises the flag a running streamed extension waits for
+// (wait_for_read, xdrop_device.cuh) -- by the kernel itself, not by a memset behind it, which the driver may run as a kernel
+// of its own with another shared-memory carve-out.
 __global__ void pack_reads_kernel(const char *__restrict__ ascii, const int64_t *__restrict__ offs,
                                   const int64_t *__restrict__ poff, int64_t n_reads, int64_t g_first, int64_t n_groups,
-                                  uint32_t *__restrict__ out2, uint32_t *__restrict__ irr_out)
+                                  uint32_t *__restrict__ out2, uint32_t *__restrict__ irr_out, unsigned int *piece_done, int *piece_flag)
 {
     for (int64_t g = g_first + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < g_first + n_groups; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t pb = g << 5;
@@ -82,6 +88,14 @@ __global__ void pack_reads_kernel(const char *__restrict__ ascii, const int64_t 
         out2[2 * g] = w0;
         out2[2 * g + 1] = w1;
         irr_out[g] = ir;
+    }
+    if (piece_flag) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(piece_done, 1u) + 1 == gridDim.x) {
+            __threadfence();
+            *reinterpret_cast<volatile int *>(piece_flag) = 1;
+        }
     }
 }
 
@@ -130,6 +144,36 @@ __global__ void exclusive_scan_i64(const int64_t *in, int64_t n, int64_t *out)
     }
 }
 
+// The same for one output chunk of a streamed run: 128 threads, no static shared array -- it has to fit beside the resident
+// pair kernel.  out[i] = sum in[0..i); *total = sum in[0..n).
+__global__ void __launch_bounds__(128) scan_chunk_kernel(const int64_t *in, int64_t n, int64_t *out, int64_t *total)
+{
+    __shared__ int64_t part[128];
+    const int t = threadIdx.x;
+    const int64_t per = (n + 127) / 128;
+    const int64_t lo = min(n, t * per), hi = min(n, lo + per);
+    int64_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += in[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int64_t acc = 0;
+        for (int i = 0; i < 128; ++i) {
+            const int64_t v = part[i];
+            part[i] = acc;
+            acc += v;
+        }
+        *total = acc;
+    }
+    __syncthreads();
+    s = part[t];
+    for (int64_t i = lo; i < hi; ++i) {
+        const int64_t v = in[i];
+        out[i] = s;
+        s += v;
+    }
+}
+
 __global__ void set_slots_kernel(ExtGeom *geom, const int64_t *prefix, const int64_t *meta_prefix, int64_t first, int64_t n)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -146,6 +190,21 @@ __global__ void chain_keys_kernel(const ExtGeom *geom, int64_t n_chains, uint32_
         const ExtGeom g = geom[t >> 1];
         const int32_t cap = g.valid ? ((t & 1) ? g.capR : g.capL) : 0;
         keys[t] = (uint32_t)max(cap, 0);
+        ids[t] = (int32_t)t;
+    }
+}
+
+// Streamed run: the directions of ALL output chunks share one queue.  A direction of chunk c that needs `cap` units of a
+// slot's time has to start by (c + 1) * delta - cap for its chunk to be complete on schedule (delta = a chunk's share of a
+// slot's time): ascending order of that latest start.  With one chunk this is longest-first.
+__global__ void stream_keys_kernel(const ExtGeom *geom, int64_t n_chains, int32_t chunk_cn, int64_t delta, uint32_t *keys, int32_t *ids)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n_chains; t += (int64_t)gridDim.x * blockDim.x) {
+        const ExtGeom g = geom[t >> 1];
+        const int64_t cap = g.valid ? max((t & 1) ? g.capR : g.capL, 0) : 0;
+        const int64_t c = (t >> 1) / chunk_cn;
+        const int64_t key = (c + 1) * delta - cap + ((int64_t)1 << 30);
+        keys[t] = (uint32_t)(key < 0 ? 0 : key > (int64_t)0xffffffffu ? (int64_t)0xffffffffu : key);
         ids[t] = (int32_t)t;
     }
 }
@@ -345,7 +404,7 @@ struct ag2_ctx {
     DevBuf order_keys, order_keys2, order_ids, order_queue, order_tmp;   // longest-first queue of the pair kernel
     DevBuf scalars;                     // ChainCounters + work counters + totals
     size_t ws_limit = (size_t)24 << 30; // bytes per workspace string per chunk (resident runs: one chunk, no drain tails)
-    size_t ws_limit_streamed = (size_t)3 << 30; // chunk size when results stream to host buffers while the next chunk computes
+    size_t ws_limit_streamed = (size_t)1 << 30; // streamed runs: workspace bytes per OUTPUT chunk (finalised, assembled and copied home while the kernel goes on)
     int64_t piece_bytes = (int64_t)256 << 20;   // ASCII bytes per upload piece of ag2_reads_load
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // high priority: the consumer of the pair kernel's hand-overs
@@ -355,6 +414,13 @@ struct ag2_ctx {
         cudaEvent_t ready;
     };
     std::vector<ReadPiece> pieces;
+    DevBuf piece_flag, piece_end;         // device copies for the streamed run: flag k != 0 once piece k is packed
+    std::vector<int64_t> h_piece_end;
+    DevBuf chunk_count;                   // streamed run: finished directions per output chunk
+    int *chunk_flag = nullptr;            // host-mapped, kMaxStreamChunks ints
+    cudaStream_t post_stream = nullptr;   // streamed run: finalize / assemble of finished chunks beside the extension kernel
+    cudaEvent_t post_done = nullptr;
+    cudaEvent_t chunk_done_ev = nullptr;  // streamed run: pair kernel + consumer finished
     std::vector<cudaEvent_t> piece_events;
     bool reads_pending = false;           // an asynchronous load may still be in flight
     std::vector<int64_t> h_poff;
@@ -374,7 +440,7 @@ namespace {
 struct Scalars {
     ChainCounters ctr;
     unsigned long long next_fast, next_wide, next_pair, next_post;
-    unsigned int wide_count, lane_count, pair_done, pad;
+    unsigned int wide_count, lane_count, pair_done, stream_error;
     unsigned long long aligned, columns;
 };
 
@@ -483,7 +549,11 @@ int ag2_ctx_create(int device, ag2_ctx **out)
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->side_done, cudaEventDisableTiming) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->in_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||   // pack kernels go ahead of pending work
+        cudaStreamCreateWithPriority(&ctx->post_stream, cudaStreamNonBlocking, -1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->post_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->chunk_done_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->chunk_flag, kMaxStreamChunks * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->chunk_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMalloc(&ctx->scalars.p, sizeof(Scalars)) != cudaSuccess) {
@@ -491,6 +561,20 @@ int ag2_ctx_create(int device, ag2_ctx **out)
         return AG2_ECUDA;
     }
     ctx->scalars.cap = sizeof(Scalars);
+    bool carve_ok = true;
+    // The small kernels that must run BESIDE the resident pair kernel (packing of the pieces still arriving, finalize / scan /
+    // assemble of the finished chunks) need the pair kernel's shared-memory carve-out: an SM changes its carve-out only when
+    // idle, so a kernel that asked for another one would wait for the pair kernel to end -- for the pack kernel, whose flags
+    // the pair kernel waits for, that would be a deadlock.
+    carve_ok = carve_ok && cudaSuccess == (cudaFuncSetAttribute(pack_reads_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carve_ok = carve_ok && cudaSuccess == (cudaFuncSetAttribute(extend_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carve_ok = carve_ok && cudaSuccess == (cudaFuncSetAttribute(scan_chunk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carve_ok = carve_ok && cudaSuccess == (cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+
+    if (!carve_ok) {
+        ag2_ctx_destroy(ctx);
+        return AG2_ECUDA;
+    }
     // test knobs: many small chunks / upload pieces on small inputs
     if (const char *e = getenv("AG2_WS_STREAMED")) ctx->ws_limit_streamed = (size_t)std::max(1ll, atoll(e));
     if (const char *e = getenv("AG2_PIECE_BYTES")) ctx->piece_bytes = std::max(1ll, atoll(e));
@@ -512,7 +596,8 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
                      &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->scalars,
-                     &ctx->order_keys, &ctx->order_keys2, &ctx->order_ids, &ctx->order_queue, &ctx->order_tmp, &ctx->tb_stream};
+                     &ctx->order_keys, &ctx->order_keys2, &ctx->order_ids, &ctx->order_queue, &ctx->order_tmp, &ctx->tb_stream,
+                     &ctx->piece_flag, &ctx->piece_end, &ctx->chunk_count};
     for (DevBuf *b : all)
         if (b->p) cudaFree(b->p);
     for (auto &e : ctx->chain_events) {
@@ -523,6 +608,10 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->chunk_done) cudaEventDestroy(ctx->chunk_done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
+    if (ctx->post_done) cudaEventDestroy(ctx->post_done);
+    if (ctx->chunk_done_ev) cudaEventDestroy(ctx->chunk_done_ev);
+    if (ctx->chunk_flag) cudaFreeHost(ctx->chunk_flag);
     if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
     if (ctx->side_done) cudaEventDestroy(ctx->side_done);
     if (ctx->in_stream) {
@@ -553,7 +642,7 @@ int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len)
     CK(cudaMemsetAsync(ctx->ref_irr.p, 0, (size_t)(groups + 8) * 4, st));
     pack_reads_kernel<<<grid_for(groups, 256, ctx->sm_count), 256, 0, st>>>(
         (const char *)ctx->ref_ascii.p, (const int64_t *)ctx->ref_offs.p, (const int64_t *)ctx->ref_offs.p + 2, 1, 0, groups,
-        (uint32_t *)ctx->ref2.p, (uint32_t *)ctx->ref_irr.p);
+        (uint32_t *)ctx->ref2.p, (uint32_t *)ctx->ref_irr.p, nullptr, nullptr);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st)); // h_offs is on the stack
     ctx->ref_len = ref_len;
@@ -582,12 +671,31 @@ static int reads_load_impl(ag2_ctx *ctx, const char *bases, const int64_t *offs,
     if (rb != AG2_OK) return rb;
     std::vector<int64_t> &poff = ctx->h_poff;
     std::vector<int32_t> &lens = ctx->h_lens;
+    std::vector<int64_t> &pend = ctx->h_piece_end;   // pieces: reads [pend[k-1], pend[k]) = up to piece_bytes of ASCII, at least one read
     poff.resize((size_t)n + 1);
     lens.resize((size_t)n);
+    pend.clear();
+    const int64_t piece_bytes = ctx->piece_bytes;
+    for (int64_t r0 = 0; r0 < n;) {
+        int64_t r1 = r0 + 1;
+        if (offs[r0] > offs[n] || offs[r0 + 1] < offs[r0]) return fail(ctx, AG2_EINVAL, "ag2_reads_load: offsets must not decrease");
+        if (offs[n] - offs[r0] <= piece_bytes) r1 = n;
+        else r1 = std::max<int64_t>(r0 + 1, std::upper_bound(offs + r0, offs + n + 1, offs[r0] + piece_bytes) - offs - 1);
+        pend.push_back(r1);
+        r0 = r1;
+    }
     int64_t p = 0;
+    size_t pk = 0;
     for (int64_t r = 0; r < n; ++r) {
         const int64_t len = offs[r + 1] - offs[r];
         if (len < 0 || len > 0x7fffffff) return fail(ctx, AG2_EINVAL, "ag2_reads_load: read %ld has bad length", (long)r);
+        if (r == pend[pk]) {
+            // a piece starts on its own 128-byte lines of both packed arrays (1024 bases of the 1-bit mask), one spare line
+            // behind the previous piece: a kernel that already runs on the earlier pieces (streamed run) must never pull a
+            // line into L1 that a later pack kernel still has to write
+            ++pk;
+            p = ((p + 1023) & ~(int64_t)1023) + 1024;
+        }
         poff[r] = p;
         lens[r] = (int32_t)len;
         p += (len + 31) & ~(int64_t)31;
@@ -600,25 +708,29 @@ static int reads_load_impl(ag2_ctx *ctx, const char *bases, const int64_t *offs,
     RESERVE(ctx->read_len, (size_t)n * 4);
     RESERVE(ctx->reads2, (size_t)(groups * 2 + 4) * 4);
     RESERVE(ctx->reads_irr, (size_t)(groups + 4) * 4);
+    RESERVE(ctx->piece_flag, pend.size() * 8);   // flags, then the pack kernels' CTA counters
+    RESERVE(ctx->piece_end, pend.size() * 8);
     cudaStream_t in = ctx->in_stream;
     CK(cudaMemcpyAsync(ctx->ascii_offs.p, offs, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, in));
     CK(cudaMemcpyAsync(ctx->read_off.p, poff.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, in));
     CK(cudaMemcpyAsync(ctx->read_len.p, lens.data(), (size_t)n * 4, cudaMemcpyHostToDevice, in));
+    CK(cudaMemcpyAsync(ctx->piece_end.p, pend.data(), pend.size() * 8, cudaMemcpyHostToDevice, in));
+    CK(cudaMemsetAsync(ctx->piece_flag.p, 0, pend.size() * 8, in));
     CK(cudaStreamSynchronize(in));   // small; `offs` is the caller's and may go away after an asynchronous return
     ctx->pieces.clear();
-    const int64_t piece_bytes = ctx->piece_bytes;
-    size_t k = 0;
-    for (int64_t r0 = 0; r0 < n;) {
-        int64_t r1 = r0 + 1;   // reads [r0, r1): up to piece_bytes of ASCII, at least one read
-        if (offs[n] - offs[r0] <= piece_bytes) r1 = n;
-        else r1 = std::max<int64_t>(r0 + 1, std::upper_bound(offs + r0, offs + n + 1, offs[r0] + piece_bytes) - offs - 1);
+    int64_t r0 = 0;
+    for (size_t k = 0; k < pend.size(); ++k) {
+        const int64_t r1 = pend[k];
         const int64_t b0 = offs[r0], b1 = offs[r1], g0 = poff[r0] >> 5, g1 = poff[r1] >> 5;
         if (b1 > b0) CK(cudaMemcpyAsync((char *)ctx->ascii.p + b0, bases + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, in));
         if (g1 > g0) {
-            pack_reads_kernel<<<grid_for(g1 - g0, 256, ctx->sm_count), 256, 0, in>>>(
+            pack_reads_kernel<<<grid_for(g1 - g0, 128, ctx->sm_count), 128, 0, in>>>(
                 (const char *)ctx->ascii.p, (const int64_t *)ctx->ascii_offs.p, (const int64_t *)ctx->read_off.p, n, g0, g1 - g0,
-                (uint32_t *)ctx->reads2.p, (uint32_t *)ctx->reads_irr.p);
+                (uint32_t *)ctx->reads2.p, (uint32_t *)ctx->reads_irr.p, (unsigned int *)ctx->piece_flag.p + pend.size() + k,
+                (int *)ctx->piece_flag.p + k);   // raises flag k: what a running streamed extension waits for
             CK(cudaGetLastError());
+        } else {
+            CK(cudaMemsetAsync((int *)ctx->piece_flag.p + k, 1, 4, in));   // a piece of empty reads: nothing to pack
         }
         if (k >= ctx->piece_events.size()) {
             cudaEvent_t e;
@@ -627,7 +739,6 @@ static int reads_load_impl(ag2_ctx *ctx, const char *bases, const int64_t *offs,
         }
         CK(cudaEventRecord(ctx->piece_events[k], in));
         ctx->pieces.push_back({r1, ctx->piece_events[k]});
-        ++k;
         r0 = r1;
     }
     ctx->reads_pending = true;
@@ -728,9 +839,11 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int stream_want = 16;
     if (const char *e = getenv("AG2_STREAM_GRID")) stream_want = atoi(e);   // tuning knob
-    const int stream_grid = std::max(1, std::min(std::min(48, stream_want), ctx->sm_count / 3));
+    // 0 = no concurrent consumer, everything handed over waits for the post-pass (needed under ncu, which serialises kernels:
+    // a consumer launched first would poll for producers that never start)
+    const int stream_grid = stream_want <= 0 ? 0 : std::max(1, std::min(std::min(48, stream_want), ctx->sm_count / 3));
     static_assert(48 * kWideWarps <= 1024, "the hand-over queue keeps one spare entry per consumer warp");   // consumer CTAs beside the pair kernel: each takes one pair CTA's place
-    RESERVE(ctx->tb_stream, tbw_stride * stream_grid * kWideWarps);
+    RESERVE(ctx->tb_stream, tbw_stride * std::max(1, stream_grid) * kWideWarps);
 
     const PackedSeqs sq = seqs_of(ctx);
     Scalars *sc = (Scalars *)ctx->scalars.p;
@@ -852,7 +965,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         cw.next = &sc->next_wide;
         cw.counters = &sc->ctr;
         CK(cudaStreamSynchronize(st));
-        xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
+        if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->side_done, ctx->side_stream));
         CK(cudaEventRecord(ctx->chain_events[ci].first, st));
@@ -967,6 +1080,313 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     return AG2_OK;
 }
 
+// extend_candidate over n device-resident candidates, results streamed to the caller's host buffers (`sink`).
+// ONE launch of the pair kernel covers every direction (a direction is a chain of sequentially dependent block DPs: cutting
+// the batch into separately launched chunks would make each launch as long as its longest direction).  The candidates are
+// cut into output chunks instead: the queue order (stream_keys_kernel) finishes them one after the other, the kernel raises
+// a host-mapped flag per finished chunk, and this thread finalises, assembles and copies that chunk home on side streams
+// while the kernel goes on.  Reads still on their way up (ag2_reads_load_async) are waited for inside the kernel, per piece.
+static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record *d_rec, int64_t *dense_total, HostSink *sink)
+{
+    cudaStream_t st = ctx->stream, post = ctx->post_stream;
+    int launches = 0;
+    static const bool trace = getenv("AG2_TRACE") != nullptr;   // per-chunk host timeline on stderr
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    std::vector<double> tr;
+    RESERVE(ctx->geom, (size_t)n * sizeof(ExtGeom));
+    RESERVE(ctx->caps, (size_t)n * 8);
+    RESERVE(ctx->prefix, (size_t)(n + 1) * 8);
+    RESERVE(ctx->nmeta, (size_t)n * 8);
+    RESERVE(ctx->meta_prefix, (size_t)(n + 1) * 8);
+    RESERVE(ctx->res, (size_t)n * 2 * sizeof(ChainResult));
+    RESERVE(ctx->str_begin, (size_t)n * 8);
+    RESERVE(ctx->ok_len, (size_t)n * 8);
+    RESERVE(ctx->dense_off, (size_t)(n + 2 * kMaxStreamChunks + 1) * 8);
+    RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
+    RESERVE(ctx->lane_queue, ((size_t)n * 2 + 1024) * 4);
+    RESERVE(ctx->lane_resume, (size_t)n * 2 * sizeof(LaneResume));
+    RESERVE(ctx->chunk_count, (size_t)kMaxStreamChunks * 4);
+
+    int pocc = 0;
+    const size_t pair_smem = sizeof(PairSmem);
+    CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+    CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, xdrop_pair_kernel, kPairThreads, pair_smem));
+    if (pocc < 1) pocc = 1;
+    const int pair_full = ctx->sm_count * pocc;
+    RESERVE(ctx->tb_pair, kPairCtaScratch * (size_t)pair_full);
+    int occ = 0;
+    const size_t lane_smem = sizeof(LaneSmem);
+    CK(cudaFuncSetAttribute(xdrop_lane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lane_smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xdrop_lane_kernel, kLaneThreads, lane_smem));
+    if (occ < 1) occ = 1;
+    const int lane_grid = ctx->sm_count * occ;
+    RESERVE(ctx->tb, (size_t)kLaneScratch * lane_grid * kLaneThreads);
+    int wocc = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, xdrop_chains_kernel<kWideK, kWideWarps>, kWideWarps * 32, 0));
+    wocc = std::max(1, std::min(wocc, 8));
+    const int wide_grid = ctx->sm_count * wocc;
+    const unsigned lane_threshold = (unsigned)wide_grid * kWideWarps * 4;
+    const size_t tbw_stride = (size_t)(kMaxBlk + 2) * TbLayout<kWideK>::kRowBytes;
+    RESERVE(ctx->tb_wide, tbw_stride * wide_grid * kWideWarps);
+    CK(cudaFuncSetAttribute(xdrop_stream_kernel<kWideK, kWideWarps>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int stream_want = 16;
+    if (const char *e = getenv("AG2_STREAM_GRID")) stream_want = atoi(e);
+    const int stream_grid = stream_want <= 0 ? 0 : std::max(1, std::min(std::min(48, stream_want), ctx->sm_count / 3));
+    RESERVE(ctx->tb_stream, tbw_stride * std::max(1, stream_grid) * kWideWarps);
+    // every pair CTA resident from the start (a consumer CTA takes one pair CTA's place): nothing of this launch is left
+    // pending in front of the small kernels that have to run beside it
+    const int pair_grid = std::max(1, pair_full - stream_grid);
+
+    const PackedSeqs sq = seqs_of(ctx);
+    Scalars *sc = (Scalars *)ctx->scalars.p;
+    CK(cudaMemsetAsync(sc, 0, sizeof(Scalars), st));
+    ctx->stats_lane_chains = 0;
+    ctx->stats_direct_wide = 0;
+    extend_setup_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>(d_cand, n, sq, ctx->n_reads, (ExtGeom *)ctx->geom.p,
+                                                                         (int64_t *)ctx->caps.p, (int64_t *)ctx->nmeta.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->caps.p, n, (int64_t *)ctx->prefix.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->nmeta.p, n, (int64_t *)ctx->meta_prefix.p);
+    launches += 3;
+    CK(cudaGetLastError());
+    int64_t ws_total = 0, meta_total = 0;
+    CK(cudaMemcpyAsync(&ws_total, (int64_t *)ctx->prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&meta_total, (int64_t *)ctx->meta_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    RESERVE(ctx->ws_q, (size_t)ws_total + 64);
+    RESERVE(ctx->ws_t, (size_t)ws_total + 64);
+    RESERVE(ctx->meta, ((size_t)meta_total + 16) * 4);
+    RESERVE(ctx->out_q, (size_t)ws_total + 64);   // upper bound of the dense strings: every column consumes a base of the read or of its window
+    RESERVE(ctx->out_t, (size_t)ws_total + 64);
+
+    // output chunks: equal candidate counts, about ws_limit_streamed bytes of workspace string each
+    int64_t want = (int64_t)std::min<size_t>(kMaxStreamChunks, std::max<size_t>(1, ((size_t)ws_total + ctx->ws_limit_streamed - 1) / ctx->ws_limit_streamed));
+    const int64_t chunk_cn = std::max<int64_t>(1, (n + want - 1) / want);
+    const int n_chunks = (int)((n + chunk_cn - 1) / chunk_cn);
+    if (chunk_cn > 0x7fffffff) return fail(ctx, AG2_EINVAL, "ag2_xdrop_extend_batch: too many candidates per chunk");
+    const int64_t slots = (int64_t)pair_grid * 2 * kPairThreads;
+    const int64_t delta = std::max<int64_t>(1, ws_total / std::max<int64_t>(1, slots * n_chunks));
+
+    set_slots_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p,
+                                                                      (const int64_t *)ctx->meta_prefix.p, 0, n);
+    CK(cudaMemsetAsync(ctx->lane_queue.p, 0xff, ((size_t)n * 2 + 1024) * 4, st));   // -1 = not published
+    CK(cudaMemsetAsync(ctx->chunk_count.p, 0, (size_t)kMaxStreamChunks * 4, st));
+    for (int c = 0; c < n_chunks; ++c) reinterpret_cast<volatile int *>(ctx->chunk_flag)[c] = 0;
+    size_t order_tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, order_tmp_bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
+                                       (int32_t *)nullptr, (int)(2 * n), 0, 32, st));
+    RESERVE(ctx->order_keys, (size_t)n * 2 * 4 + 16);
+    RESERVE(ctx->order_keys2, (size_t)n * 2 * 4 + 16);
+    RESERVE(ctx->order_ids, (size_t)n * 2 * 4 + 16);
+    RESERVE(ctx->order_queue, (size_t)n * 2 * 4 + 16);
+    RESERVE(ctx->order_tmp, order_tmp_bytes + 16);
+    stream_keys_kernel<<<grid_for(2 * n, 256, ctx->sm_count), 256, 0, st>>>((const ExtGeom *)ctx->geom.p, 2 * n, (int32_t)chunk_cn, delta,
+                                                                            (uint32_t *)ctx->order_keys.p, (int32_t *)ctx->order_ids.p);
+    {
+        size_t tmp = ctx->order_tmp.cap;
+        CK(cub::DeviceRadixSort::SortPairs(ctx->order_tmp.p, tmp, (const uint32_t *)ctx->order_keys.p, (uint32_t *)ctx->order_keys2.p,
+                                           (const int32_t *)ctx->order_ids.p, (int32_t *)ctx->order_queue.p, (int)(2 * n), 0, 32, st));
+    }
+    launches += 3;
+
+    StreamSignal sig = {};
+    sig.chunk_done = (unsigned int *)ctx->chunk_count.p;
+    CK(cudaHostGetDevicePointer((void **)&sig.chunk_flag, ctx->chunk_flag, 0));
+    sig.n_cand = n;
+    sig.chunk_cn = (int32_t)chunk_cn;
+    sig.error = &sc->stream_error;
+    static const bool wait_on_host = getenv("AG2_STREAM_WAIT_HOST") != nullptr;   // knob: no waiting inside the kernel
+    if (ctx->reads_pending && wait_on_host) {
+        CK(cudaStreamWaitEvent(st, ctx->pieces.back().ready, 0));
+    } else if (ctx->reads_pending) {   // an asynchronous read load is in flight: directions wait for their piece inside the kernel
+        sig.piece_flag = (const int *)ctx->piece_flag.p;
+        sig.piece_end = (const int64_t *)ctx->piece_end.p;
+        sig.n_pieces = (int32_t)ctx->h_piece_end.size();
+    }
+    LaneArgs a = {};
+    a.sig = sig;
+    a.seqs = sq;
+    a.cand = d_cand;
+    a.geom = (const ExtGeom *)ctx->geom.p;
+    a.res = (ChainResult *)ctx->res.p;
+    a.meta = (uint32_t *)ctx->meta.p;
+    a.ws_q = (char *)ctx->ws_q.p;
+    a.ws_t = (char *)ctx->ws_t.p;
+    a.counters = &sc->ctr;
+    LaneArgs pa = a;
+    pa.scratch = (uint8_t *)ctx->tb_pair.p;
+    pa.n_chains = 2 * n;
+    pa.queue = (const int32_t *)ctx->order_queue.p;
+    pa.next = &sc->next_pair;
+    pa.wide_queue = (int32_t *)ctx->lane_queue.p;
+    pa.wide_count = &sc->lane_count;
+    pa.resume = (LaneResume *)ctx->lane_resume.p;
+    pa.done_ctas = &sc->pair_done;
+    ChainArgs cw = {};
+    cw.sig = sig;
+    cw.sig.piece_flag = nullptr;   // a handed-over direction was started by the pair kernel: its read is there
+    cw.seqs = sq;
+    cw.cand = a.cand;
+    cw.geom = a.geom;
+    cw.res = a.res;
+    cw.ws_q = a.ws_q;
+    cw.ws_t = a.ws_t;
+    cw.tb = (uint8_t *)ctx->tb_stream.p;
+    cw.tb_stride = tbw_stride;
+    cw.queue = (const int32_t *)ctx->lane_queue.p;
+    cw.next = &sc->next_wide;
+    cw.counters = &sc->ctr;
+    CK(cudaStreamSynchronize(st));
+    if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->side_done, ctx->side_stream));
+    while (ctx->chain_events.size() < 1) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        ctx->chain_events.push_back({e0, e1});
+    }
+    const double t_launch = now_ms();
+    CK(cudaEventRecord(ctx->chain_events[0].first, st));
+    xdrop_pair_kernel<<<pair_grid, kPairThreads, pair_smem, st>>>(pa);
+    CK(cudaEventRecord(ctx->chain_events[0].second, st));
+    CK(cudaGetLastError());
+    CK(cudaStreamWaitEvent(st, ctx->side_done, 0));
+    CK(cudaEventRecord(ctx->chunk_done_ev, st));   // pair kernel and its consumer are through
+    launches += 2;
+
+    // What the consumer did not take ([first, n_handed), published after its last ticket) runs after the pair kernel.
+    auto post_pass = [&]() -> int {
+        unsigned int n_handed = 0, n_wide = 0;
+        unsigned long long taken = 0;
+        CK(cudaMemcpyAsync(&n_handed, &sc->lane_count, sizeof n_handed, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&taken, &sc->next_wide, sizeof taken, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->stats_lane_chains += n_handed;
+        const unsigned int first = (unsigned int)std::min<unsigned long long>(taken, n_handed);
+        const unsigned int n_lane = n_handed - first;
+        ctx->stats_direct_wide += first;
+        const bool lane_path = n_lane > lane_threshold;
+        const int32_t *post_queue = (const int32_t *)ctx->lane_queue.p + first;
+        if (n_lane > 0 && !lane_path) {
+            n_wide = n_lane;
+            ctx->stats_direct_wide += n_lane;
+        }
+        if (n_lane > 0 && lane_path) {
+            LaneArgs la = a;
+            la.sig.piece_flag = nullptr;
+            la.scratch = (uint8_t *)ctx->tb.p;
+            la.n_chains = n_lane;
+            la.queue = post_queue;
+            la.resume = (LaneResume *)ctx->lane_resume.p + first;
+            la.next = &sc->next_fast;
+            la.wide_queue = (int32_t *)ctx->wide_queue.p;
+            la.wide_count = &sc->wide_count;
+            xdrop_lane_kernel<<<lane_grid, kLaneThreads, lane_smem, st>>>(la);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(&n_wide, &sc->wide_count, sizeof n_wide, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            post_queue = (const int32_t *)ctx->wide_queue.p;
+            ++launches;
+        }
+        if (n_wide > 0) {
+            ChainArgs w = cw;
+            w.tb = (uint8_t *)ctx->tb_wide.p;
+            w.n_chains = n_wide;
+            w.queue = post_queue;
+            w.next = &sc->next_post;
+            xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
+            CK(cudaGetLastError());
+            ++launches;
+        }
+        CK(cudaStreamSynchronize(st));
+        return AG2_OK;
+    };
+
+    // drain: chunk after chunk, as their flags come up
+    const volatile int *flags = ctx->chunk_flag;
+    bool post_ran = false;
+    int64_t dense_base = 0;
+    int64_t *d_totals = (int64_t *)ctx->dense_off.p + n + 1;   // per chunk: its dense length
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t lo = (int64_t)c * chunk_cn, cn = std::min<int64_t>(chunk_cn, n - lo);
+        for (unsigned spins = 0; !flags[c]; ++spins) {
+            if (!post_ran && (spins & 63) == 63) {
+                const cudaError_t q = cudaEventQuery(ctx->chunk_done_ev);
+                if (q == cudaSuccess) {   // the kernels are through and this chunk is not: it has directions left for the post-pass
+                    const int rc = post_pass();
+                    if (rc != AG2_OK) return rc;
+                    post_ran = true;
+                    if (!flags[c]) return fail(ctx, AG2_ECUDA, "ag2_xdrop_extend_batch: chunk %d incomplete after the last kernel", c);
+                } else if (q != cudaErrorNotReady) {
+                    return fail(ctx, AG2_ECUDA, "ag2_xdrop_extend_batch: %s", cudaGetErrorString(q));
+                }
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
+        if (trace) tr.push_back(now_ms());
+        // small CTAs: these kernels must fit beside the resident pair kernel
+        extend_finalize_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, post>>>(d_cand, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p,
+                                                                                 (const int32_t *)ctx->read_len.p, lo, cn, d_rec,
+                                                                                 (int64_t *)ctx->str_begin.p, (int64_t *)ctx->ok_len.p);
+        scan_chunk_kernel<<<1, 128, 0, post>>>((const int64_t *)ctx->ok_len.p + lo, cn, (int64_t *)ctx->dense_off.p + lo, d_totals + c);
+        launches += 2;
+        int64_t chunk_total = 0;
+        CK(cudaMemcpyAsync(&chunk_total, d_totals + c, 8, cudaMemcpyDeviceToHost, post));
+        CK(cudaStreamSynchronize(post));
+        if (trace) tr.push_back(now_ms());
+        assemble_kernel<<<grid_for(cn * 32, 128, ctx->sm_count), 128, 0, post>>>(
+            d_rec, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p, (const uint32_t *)ctx->meta.p, (const int64_t *)ctx->dense_off.p,
+            dense_base, lo, cn, (const char *)ctx->ws_q.p, (const char *)ctx->ws_t.p, (char *)ctx->out_q.p, (char *)ctx->out_t.p, &sc->aligned,
+            &sc->columns);
+        ++launches;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->post_done, post));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->post_done, 0));
+        CK(cudaMemcpyAsync(sink->rec + lo, d_rec + lo, (size_t)cn * sizeof(Record), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (sink->q && sink->t && dense_base + chunk_total <= sink->cap) {
+            CK(cudaMemcpyAsync(sink->q + dense_base, (char *)ctx->out_q.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaMemcpyAsync(sink->t + dense_base, (char *)ctx->out_t.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        } else if (sink->q || sink->t) {
+            sink->overflow = true;
+        }
+        dense_base += chunk_total;
+    }
+    if (!post_ran) {   // nothing was missing for any chunk; the bookkeeping of the hand-overs is still due
+        const int rc = post_pass();
+        if (rc != AG2_OK) return rc;
+    }
+    CK(cudaStreamSynchronize(st));
+    const double t_kernels = now_ms();
+    CK(cudaStreamSynchronize(post));
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    *dense_total = dense_base;
+    if (trace) {
+        fprintf(stderr, "[ag2 trace] launch at %.1f ms, kernels done %.1f, all home %.1f; %d chunks (flag seen / scanned):", t_launch, t_kernels, now_ms(), n_chunks);
+        for (size_t k = 0; k + 1 < tr.size(); k += 2) fprintf(stderr, " %.1f/%.1f", tr[k], tr[k + 1]);
+        fprintf(stderr, "\n");
+    }
+
+    Scalars hs;
+    CK(cudaMemcpy(&hs, sc, sizeof hs, cudaMemcpyDeviceToHost));
+    if (hs.stream_error) return fail(ctx, AG2_ECUDA, "ag2_xdrop_extend_batch: %u directions gave up waiting for their reads (upload stalled)", hs.stream_error);
+    ag2_extend_stats &s = ctx->stats;
+    s.cells = (int64_t)hs.ctr.cells;
+    s.rows = (int64_t)hs.ctr.rows;
+    s.blocks = (int64_t)hs.ctr.blocks;
+    s.interior = (int64_t)hs.ctr.interior;
+    s.wide_chains = (int64_t)hs.ctr.wide + ctx->stats_direct_wide;
+    s.aligned = (int64_t)hs.aligned;
+    s.columns = (int64_t)hs.columns;
+    s.launches = launches;
+    s.lane_chains = ctx->stats_lane_chains;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->chain_events[0].first, ctx->chain_events[0].second));
+    s.kernel_ms = ms;
+    return AG2_OK;
+}
+
 int ag2_extend_run(ag2_ctx *ctx)
 {
     if (!ctx || ctx->n_cand <= 0) return fail(ctx, AG2_ESTATE, "ag2_extend_run: no candidates uploaded");
@@ -1022,7 +1442,9 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
     sink.t = saln_out;
     sink.cap = aln_cap;
     int64_t total = 0;
-    r = extend_batch(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, 0, &total, true, &sink, cand);
+    static const bool chunked = getenv("AG2_E2E_CHUNKED") != nullptr;   // the former form: one launch per chunk (kept for comparison runs)
+    if (chunked) r = extend_batch(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, 0, &total, true, &sink, cand);
+    else r = extend_batch_streamed(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, &total, &sink);
     if (r != AG2_OK) return r;
     if ((r = reads_barrier(ctx)) != AG2_OK) return r;   // reads no candidate refers to may still be on their way
     ctx->out_total = total;

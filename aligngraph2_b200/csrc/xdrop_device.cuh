@@ -372,7 +372,75 @@ __device__ int walk_block(const uint8_t *tb, int ae, int be, WarpSmem &sm, int &
     return n;
 }
 
+// Streamed runs (ag2_xdrop_extend_batch with host buffers): ONE launch covers every direction of the batch, and the two
+// ends of the pipeline are signalled through memory instead of through kernel boundaries.
+//   * in:  the reads go up in pieces while the kernel already runs; a direction waits for the flag of the piece that
+//     holds its read (set on the upload stream after the piece's pack kernel);
+//   * out: the candidates are cut into chunks; every finished direction is counted on its chunk, and the direction that
+//     completes a chunk raises the chunk's flag in host-mapped memory -- the host then finalises, assembles and copies
+//     that chunk home while the kernel works on the later ones.
+// All pointers null (chunk_cn 0): resident run, nothing is signalled or waited for.
+struct StreamSignal {
+    unsigned int *chunk_done;   // [chunks] finished directions
+    int *chunk_flag;            // [chunks] host-mapped
+    int64_t n_cand;
+    int32_t chunk_cn;           // candidates per chunk
+    int32_t n_pieces;
+    const int *piece_flag;      // [n_pieces]
+    const int64_t *piece_end;   // [n_pieces] reads [piece_end[k-1], piece_end[k]) arrive with piece k
+    unsigned int *error;        // raised when a wait ran into its time limit
+};
+
+// Called by the thread that wrote the direction's result (its strings, metadata and ChainResult).
+__device__ __forceinline__ void signal_direction_done(const StreamSignal &s, int64_t chain)
+{
+#ifndef AG2_EMU
+    if (!s.chunk_cn) return;
+    const int64_t ci = chain >> 1;
+    const int64_t c = ci / s.chunk_cn;
+    const int64_t in_chunk = min((int64_t)s.chunk_cn, s.n_cand - c * s.chunk_cn);
+    __threadfence();
+    const unsigned int prev = atomicAdd(s.chunk_done + c, 1u);
+    if ((int64_t)prev + 1 == 2 * in_chunk) {
+        __threadfence();
+        *reinterpret_cast<volatile int *>(s.chunk_flag + c) = 1;
+        __threadfence_system();
+    }
+#endif
+}
+
+// Blocks until the piece that holds `read` has been packed.  False: gave up after kStreamWaitNs (the upload stream made
+// no progress -- e.g. under a profiler that serialises kernels); the caller drops the direction and the host reports it.
+constexpr unsigned long long kStreamWaitNs = 3ull * 1000 * 1000 * 1000;
+__device__ __forceinline__ bool wait_for_read(const StreamSignal &s, int64_t read)
+{
+#ifndef AG2_EMU
+    if (!s.piece_flag) return true;
+    int k = 0;
+    while (k + 1 < s.n_pieces && s.piece_end[k] <= read) ++k;
+    const volatile int *flag = s.piece_flag + k;
+    if (*flag == 0) {
+        const volatile unsigned int *err = s.error;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            __nanosleep(2000);
+            if (*flag) break;
+            if (*err) return false;   // somebody else already ran into the limit: the whole run is void, do not wait again
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > kStreamWaitNs) {
+                atomicAdd(s.error, 1u);
+                return false;
+            }
+        }
+    }
+    __threadfence();
+#endif
+    return true;
+}
+
 struct ChainArgs {
+    StreamSignal sig;
     PackedSeqs seqs;
     const Candidate *cand;
     const ExtGeom *geom;
@@ -398,7 +466,10 @@ __device__ bool run_chain(const ChainArgs &g, int64_t chain, WarpSmem &sm, uint8
     const ExtGeom ge = g.geom[ci];
     ChainResult out = {0, 0, 0, -1, 0, 1, 0, 0};
     if (!ge.valid) {
-        if (lane == 0) g.res[chain] = out;
+        if (lane == 0) {
+            g.res[chain] = out;
+            signal_direction_done(g.sig, chain);
+        }
         return true;
     }
     const int rlen = g.seqs.read_len[c.read];
@@ -505,7 +576,11 @@ __device__ bool run_chain(const ChainArgs &g, int64_t chain, WarpSmem &sm, uint8
     out.qcons = qcons;
     out.tcons = tcons;
     out.last_op = last_op;
-    if (lane == 0) g.res[chain] = out;
+    __syncwarp(); // the strings were written by all lanes
+    if (lane == 0) {
+        g.res[chain] = out;
+        signal_direction_done(g.sig, chain);
+    }
     ctr.cells += lc.cells;
     ctr.rows += lc.rows;
     ctr.blocks += lc.blocks;

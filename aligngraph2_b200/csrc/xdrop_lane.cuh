@@ -60,6 +60,7 @@ struct LaneResume {
 };
 
 struct LaneArgs {
+    StreamSignal sig;        // streamed runs: piece flags to wait for, chunk counters to raise (xdrop_device.cuh)
     PackedSeqs seqs;
     const Candidate *cand;
     const ExtGeom *geom;
@@ -495,6 +496,7 @@ __device__ void lane_kernel_body(const LaneArgs &g, LaneSmem &sm, int tid, uint8
                 if (!s.ge.valid) {
                     const ChainResult out = {0, 0, 0, -1, 0, 0, 0, 0};
                     g.res[s.chain] = out;
+                    signal_direction_done(g.sig, s.chain);
                     s.chain = -1;
                 }
             } else {
@@ -508,6 +510,7 @@ __device__ void lane_kernel_body(const LaneArgs &g, LaneSmem &sm, int tid, uint8
             if (rc == 1) {
                 const ChainResult out = {s.ncols, s.qcons, s.tcons, s.last_op, s.nblocks, 0, 0, 0};
                 g.res[s.chain] = out;
+                signal_direction_done(g.sig, s.chain);
                 cells += s.cells;
                 rows += s.rows;
                 blocks += s.blocks;

@@ -198,6 +198,14 @@ __device__ __forceinline__ void pair_group(uint32_t (&va)[4], uint32_t (&vb)[4],
     if (IN) c.Ms = 0xffffffffu;
 }
 
+#ifdef AG2_EMU_STATS
+struct PairEmuStats { long warp_rows, groups, groups_in, dir_rows, dir_groups_need, shifts, rounds, dir_rounds, walk_cols, gstd_groups, tail_groups; };
+static PairEmuStats g_pes;
+#define PES(...) __VA_ARGS__
+#else
+#define PES(...)
+#endif
+
 struct PairIO {
     int M[2], N[2];          // block sizes per direction (M = 0: no block)
     // results
@@ -244,6 +252,7 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             // move the window of a direction whose band start has advanced by 8 columns or more
             const uint32_t Msh = h2_ge(frelh, H2C(8));
             if (__any_sync(kFull, Msh != 0)) {
+                PES(if (tid == 0) g_pes.shifts++;)
                 for (int q = 0; q < kPairSlots / 4; ++q) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -300,6 +309,8 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             rows2 = vadd2(rows2, run & 0x00010001u);
         }
         const h2 nDe = nD & run;
+        PES(if (tid == 0) g_pes.warp_rows++;
+            g_pes.dir_rows += ((run & 0xffffu) != 0) + ((run >> 16) != 0);)
         c.best = h2_sel(run, c.best, H2C(2047)); // a direction that has stopped can no longer prune in, whatever its masks say
         c.thr = h2_sel(run, c.thr, H2C(2047 - kXdrop));
         const h2 best0 = c.best;
@@ -342,7 +353,9 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             uint32_t acc0 = 0, acc1 = 0;
             // interior group: no running direction of the warp has a band edge or its leading run in these 8 slots
             const uint32_t inner = (h2_ge(nDg, H2C(9)) & ~c.Mlead) | ~run;
-            if (__all_sync(kFull, inner == 0xffffffffu)) pair_group<true>(va, vb, c, nDg, Jg, mmw, acc0, acc1);
+            const bool all_in = __all_sync(kFull, inner == 0xffffffffu);
+            PES(if (tid == 0) { g_pes.groups++; g_pes.groups_in += all_in; if (g < g_std) g_pes.gstd_groups++; else g_pes.tail_groups++; })
+            if (all_in) pair_group<true>(va, vb, c, nDg, Jg, mmw, acc0, acc1);
             else pair_group<false>(va, vb, c, nDg, Jg, mmw, acc0, acc1);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -386,6 +399,9 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             pair_store16(row1 + (size_t)(g >> 2) * kPairQuadStride, t1);
         }
         if (more) bail |= (c.Ms | c.Mlp) & run; // the window is too narrow for this direction
+        PES({ const int l0 = h2_lo_int(c.lastj), l1 = h2_hi_int(c.lastj);
+              if (run & 0xffffu) g_pes.dir_groups_need += (max(l0, 0) + 2 + 7) >> 3;
+              if (run >> 16) g_pes.dir_groups_need += (max(l1, 0) + 2 + 7) >> 3; })
         // row end (:142-164): the next band ends one past the last live cell (the sentinel), clipped to column N - 1
         const uint32_t any_live = h2_ge(c.lastj, 0u);
         alive &= any_live | ~run;      // every cell pruned: the reference leaves the loop (:142)
@@ -587,9 +603,11 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
                 const unsigned long long t = atomicAdd(g.next, 1ull);
                 if ((int64_t)t < g.n_chains) {
                     lane_start_chain(g, g.queue ? (int64_t)g.queue[t] : (int64_t)t, s[h]);
+                    if (s[h].ge.valid && !wait_for_read(g.sig, s[h].c.read)) s[h].ge.valid = 0; // streamed run: its read is still on the way
                     if (!s[h].ge.valid) {
                         const ChainResult out = {0, 0, 0, -1, 0, 0, 0, 0};
                         g.res[s[h].chain] = out;
+                        signal_direction_done(g.sig, s[h].chain);
                         s[h].chain = -1;
                     }
                 } else {
@@ -613,6 +631,8 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
             }
         }
         if (!__any_sync(kFull, s[0].chain >= 0 || s[1].chain >= 0 || !drained)) break;
+        PES(if (tid == 0) g_pes.rounds++;
+            g_pes.dir_rounds += (io.M[0] > 0) + (io.M[1] > 0);)
         if (__any_sync(kFull, io.M[0] > 0 || io.M[1] > 0)) pair_dp(sm, tid, ps[0], ps[1], io);
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) { // not unrolled: the chain state is indexed, so it lives in local memory, not in registers
@@ -647,6 +667,7 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
             if (rc == 1) {
                 const ChainResult out = {c.ncols, c.qcons, c.tcons, c.last_op, c.nblocks, 0, 0, 0};
                 g.res[c.chain] = out;
+                signal_direction_done(g.sig, c.chain);
                 cells += c.cells;
                 rows += c.rows;
                 blocks += c.blocks;

@@ -31,10 +31,10 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of xdrop_pair_kernel from the ncu --set full capture
-# profiles/kernel_r01f_pair.md (150k reads: 121.51 + 123.78 GB for 1 578 478 191 aligned bases); DRAM bytes per
+# profiles/kernel_r01h_pair.md (150k reads: 78.28 + 87.24 GB for 1 578 478 191 aligned bases); DRAM bytes per
 # aligned base do not depend on the batch size, so the per-launch figure is that ratio x this launch's bases
-TRAFFIC_BYTES_PER_ALIGNED_BASE = (121.513232e9 + 123.775029e9) / 1578478191
-TRAFFIC_NOTE = "ncu dram bytes per aligned base (profiles/kernel_r01f_pair.md, 150k-read launch) x aligned bases of this launch"
+TRAFFIC_BYTES_PER_ALIGNED_BASE = (78.276094e9 + 87.243725e9) / 1578478191
+TRAFFIC_NOTE = "ncu dram bytes per aligned base (profiles/kernel_r01h_pair.md, 150k-read launch) x aligned bases of this launch"
 METRIC = "aligned_gbp_per_s"
 UNIT = "Gbp/s"
 DTYPE = "f16"          # the DP scores are exact integers held as binary16, two extension directions per 32-bit register (xdrop_pair.cuh)

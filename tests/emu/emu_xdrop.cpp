@@ -297,3 +297,10 @@ int emu_pair_batch(const char *ref, long ref_len, const char *reads, const long 
 }
 
 } // extern "C"
+#ifdef AG2_EMU_STATS
+extern "C" void emu_pair_stats(long *out)
+{
+    memcpy(out, &ag2::g_pes, sizeof(ag2::g_pes));
+    memset(&ag2::g_pes, 0, sizeof(ag2::g_pes));
+}
+#endif

@@ -166,9 +166,10 @@ def test_properties_at_scale(dev):
 
 @pytest.mark.parametrize("order", ["read", "shuffled"])
 def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order):
-    """ag2_reads_load_async + ag2_xdrop_extend_batch with host buffers: the reads go up in many pieces while the candidates
-    are extended in many chunks (test knobs make both small), each chunk waiting only for the piece that holds its last
-    read.  Records and strings must equal the synchronous, resident run -- whatever the candidate order."""
+    """ag2_reads_load_async + ag2_xdrop_extend_batch with host buffers: the reads go up in many pieces while ONE launch
+    already extends the candidates (every direction waits for the piece that holds its read inside the kernel), and the
+    results come home in many output chunks as the kernel raises their flags (test knobs make pieces and chunks small).
+    Records and strings must equal the synchronous, resident run -- whatever the candidate order."""
     from aligngraph2_b200.lib import RECORD_DTYPE
     from aligngraph2_b200.mecat2ref import Mecat2RefDevice
     d = synth.make_batch_torch(99, 400_000, 600, 4000)
@@ -195,7 +196,7 @@ def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order):
             assert used == qa.size
             assert np.array_equal(rec2, rec) and np.array_equal(q2[:used], qa) and np.array_equal(s2[:used], sa)
         st = dev2.stats()
-        assert st["cells"] == dev.stats()["cells"] and st["launches"] > 20 * 5   # really went through many chunks
+        assert st["cells"] == dev.stats()["cells"] and st["launches"] >= 8 + 3 * 15   # really went through many output chunks
         # every other entry point waits for an asynchronous load by itself
         dev2.load_reads_async(bases, off)
         dev2.build_index(200, 0.5, 2.0)
