@@ -1080,6 +1080,9 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     return AG2_OK;
 }
 
+// Which form ag2_xdrop_extend_batch takes when AG2_E2E_PATH does not say (see there).
+constexpr bool kStreamedByDefault = false;
+
 // extend_candidate over n device-resident candidates, results streamed to the caller's host buffers (`sink`).
 // ONE launch of the pair kernel covers every direction (a direction is a chain of sequentially dependent block DPs: cutting
 // the batch into separately launched chunks would make each launch as long as its longest direction).  The candidates are
@@ -1442,7 +1445,12 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
     sink.t = saln_out;
     sink.cap = aln_cap;
     int64_t total = 0;
-    static const bool chunked = getenv("AG2_E2E_CHUNKED") != nullptr;   // the former form: one launch per chunk (kept for comparison runs)
+    // Two forms of the host-buffer run: "chunked" = one pair-kernel launch per output chunk, the chunk's results copied home
+    // while the next chunk computes; "streamed" = ONE launch for the whole batch with flags per output chunk
+    // (extend_batch_streamed).  AG2_E2E_PATH picks one per call; without it the form measured at the full configs[1] size
+    // on B200 is used (kStreamedByDefault).
+    bool chunked = !kStreamedByDefault;
+    if (const char *e = getenv("AG2_E2E_PATH")) chunked = strcmp(e, "streamed") != 0;
     if (chunked) r = extend_batch(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, 0, &total, true, &sink, cand);
     else r = extend_batch_streamed(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, &total, &sink);
     if (r != AG2_OK) return r;

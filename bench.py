@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--cpu-sample-per-core", type=int, default=1000, help="reads per host core in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-path", default="default", choices=["default", "chunked", "streamed"],
+                    help="form of the host-buffer run (AG2_E2E_PATH of ag2_xdrop_extend_batch); default = the library's own choice")
     ap.add_argument("--pagraph-reads", type=int, default=4000, help="reads of the A-Bruijn build stage line (0 = skip)")
     ap.add_argument("--pagraph-k", type=int, default=14)
     return ap.parse_args()
@@ -370,7 +372,18 @@ def main():
             parts[1] += time.perf_counter() - t1
             return u
 
-        step()
+        if args.e2e_path != "default":
+            os.environ["AG2_E2E_PATH"] = args.e2e_path
+        e2e_path, e2e_note = args.e2e_path, None
+        try:
+            step()
+        except Exception as e:  # the streamed form gives up when its uploads stall; the chunked form has no such wait
+            if os.environ.get("AG2_E2E_PATH") == "chunked":
+                raise
+            e2e_note = f"{e2e_path} form failed ({e!r}); measured with the chunked form"
+            print("[bench] " + e2e_note, file=sys.stderr)
+            os.environ["AG2_E2E_PATH"] = e2e_path = "chunked"
+            step()
         parts[0] = parts[1] = 0.0
         barrier()
         e0.record(stream)
@@ -389,7 +402,10 @@ def main():
         e2e = {"value": float(a2.item()) * args.steps / (float(t2.item()) * 1e-3) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(total_bases + h_off.nbytes + h_cand.nbytes) * world,
                "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used) * world, "ms_per_step": float(t2.item()) / args.steps,
-               "reads_load_ms": parts[0] * 1e3 / args.steps, "extend_batch_ms": parts[1] * 1e3 / args.steps}
+               "reads_load_ms": parts[0] * 1e3 / args.steps, "extend_batch_ms": parts[1] * 1e3 / args.steps, "path": e2e_path}
+        if e2e_note:
+            e2e["note"] = e2e_note
+        os.environ.pop("AG2_E2E_PATH", None)
 
     # ---- the stages in front of the extension on the same batch (not part of the headline metric) ----
     stages = None

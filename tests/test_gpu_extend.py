@@ -164,8 +164,9 @@ def test_properties_at_scale(dev):
     assert np.array_equal(rec, rec2) and np.array_equal(qa, qa2) and np.array_equal(sa, sa2)
 
 
+@pytest.mark.parametrize("path", ["streamed", "chunked"])
 @pytest.mark.parametrize("order", ["read", "shuffled"])
-def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order):
+def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order, path):
     """ag2_reads_load_async + ag2_xdrop_extend_batch with host buffers: the reads go up in many pieces while ONE launch
     already extends the candidates (every direction waits for the piece that holds its read inside the kernel), and the
     results come home in many output chunks as the kernel raises their flags (test knobs make pieces and chunks small).
@@ -183,6 +184,7 @@ def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order):
     rec, qa, sa = dev.extend(cand)
     assert rec["ok"].mean() > 0.98
 
+    monkeypatch.setenv("AG2_E2E_PATH", path)               # both forms of the host-buffer run (ag2_xdrop_extend_batch)
     monkeypatch.setenv("AG2_WS_STREAMED", str(400_000))    # ~ 30 reads per chunk
     monkeypatch.setenv("AG2_PIECE_BYTES", str(100_000))    # ~ 25 reads per piece
     dev2 = Mecat2RefDevice(0)
