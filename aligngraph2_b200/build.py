@@ -30,7 +30,7 @@ def build_host(force: bool = False, name: str = "mecat2ref") -> str:
         src_path, out = os.path.join(PKG, "host", src), os.path.join(PKG, "bin", prog)
         if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src_path), os.path.getmtime(SO)):
             continue
-        subprocess.run([cxx, "-O2", "-std=c++17", "-Wall", "-o", out, src_path, "-L" + PKG, "-lag2_b200",
+        subprocess.run([cxx, "-O2", "-std=c++17", "-Wall", "-pthread", "-o", out, src_path, "-L" + PKG, "-lag2_b200",
                         "-Wl,-rpath,$ORIGIN/.."], check=True, cwd=ROOT)
     return os.path.join(PKG, "bin", name)
 

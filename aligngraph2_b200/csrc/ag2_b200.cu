@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kPairThreads, 7) xdrop_pair_kernel(LaneArgs g)
     PairSmem &sm = *reinterpret_cast<PairSmem *>(smem_raw);
     const int tid = threadIdx.x;
     uint8_t *scratch = g.scratch + (size_t)blockIdx.x * kPairCtaScratch; // the CTA's: traceback of its 128 directions interleaved
+    if (g.done_ctas && tid == 0) reinterpret_cast<volatile unsigned int *>(g.done_ctas)[1] = 1u; // a producer runs: the consumer may take tickets
     pair_kernel_body(g, sm, tid, scratch);
     if (g.done_ctas) { // tells the concurrent consumer that this CTA will publish nothing more
         __syncthreads();
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
 // rerun each published direction at once (one warp per direction), so that no hand-over is left for after the pair kernel
 // when the GPU would sit idle behind a handful of sequential directions.  Tickets are taken only while producers are
 // active; [min(*next, *count), *count) is what the host still has to run afterwards.
+constexpr unsigned long long kConsumerStartNs = 1500ull * 1000 * 1000;
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) xdrop_stream_kernel(ChainArgs g, const unsigned int *done_ctas, unsigned int n_producers)
 {
@@ -304,7 +306,24 @@ __global__ void __launch_bounds__(WARPS * 32) xdrop_stream_kernel(ChainArgs g, c
     ChainCounters ctr = {0, 0, 0, 0, 0};
     const volatile int32_t *queue = g.queue;
     const volatile unsigned int *done = done_ctas;
-    for (;;) {
+    // No ticket before a producer is seen running beside this kernel (done_ctas[1]).  Where kernels do not overlap -- a
+    // profiler that serialises launches -- the producers start only after this kernel has ended: it leaves after
+    // kConsumerStartNs without a ticket and the host's post-pass runs every hand-over.
+    int go = 1;
+    if (lane == 0 && done[1] == 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (done[1] == 0) {
+            __nanosleep(2000);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > kConsumerStartNs) {
+                go = 0;
+                break;
+            }
+        }
+    }
+    go = __shfl_sync(kFull, go, 0);
+    while (go) {
         int chain = -1;
         if (lane == 0 && *done < n_producers) {
             const unsigned long long t = atomicAdd(g.next, 1ull);
@@ -440,7 +459,8 @@ namespace {
 struct Scalars {
     ChainCounters ctr;
     unsigned long long next_fast, next_wide, next_pair, next_post;
-    unsigned int wide_count, lane_count, pair_done, stream_error;
+    unsigned int wide_count, lane_count, stream_error, pad_;
+    unsigned int pair_done, pair_started;   // adjacent: the pair kernel gets &pair_done and raises pair_done[1] when its first CTA runs
     unsigned long long aligned, columns;
 };
 
@@ -529,6 +549,16 @@ extern "C" {
 const char *ag2_version(void) { return "aligngraph2_b200 0.1 (sm_100a)"; }
 
 const char *ag2_last_error(const ag2_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int ag2_device_count(int *count)
+{
+    if (!count) return AG2_EINVAL;
+    *count = 0;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return AG2_ENODEV;
+    *count = n;
+    return AG2_OK;
+}
 
 int ag2_ctx_create(int device, ag2_ctx **out)
 {
@@ -920,7 +950,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         }
         set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p,
                                                                            (const int64_t *)ctx->meta_prefix.p, lo, cn);
-        CK(cudaMemsetAsync(&sc->next_fast, 0, 4 * sizeof(unsigned long long) + 4 * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(&sc->next_fast, 0, 4 * sizeof(unsigned long long) + 6 * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(ctx->lane_queue.p, 0xff, ((size_t)cn * 2 + 1024) * 4, st));   // -1 = not published
         LaneArgs a = {};
         a.seqs = sq;
@@ -1140,7 +1170,9 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     RESERVE(ctx->tb_stream, tbw_stride * std::max(1, stream_grid) * kWideWarps);
     // every pair CTA resident from the start (a consumer CTA takes one pair CTA's place): nothing of this launch is left
     // pending in front of the small kernels that have to run beside it
-    const int pair_grid = std::max(1, pair_full - stream_grid);
+    int spare = 0;
+    if (const char *e = getenv("AG2_STREAM_SPARE_CTAS")) spare = std::max(0, atoi(e));   // tuning knob: pair CTAs left out to make room for the small kernels
+    const int pair_grid = std::max(1, pair_full - stream_grid - spare);
 
     const PackedSeqs sq = seqs_of(ctx);
     Scalars *sc = (Scalars *)ctx->scalars.p;
@@ -1199,7 +1231,10 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     sig.n_cand = n;
     sig.chunk_cn = (int32_t)chunk_cn;
     sig.error = &sc->stream_error;
-    static const bool wait_on_host = getenv("AG2_STREAM_WAIT_HOST") != nullptr;   // knob: no waiting inside the kernel
+    // An asynchronous read load in flight: the launch waits for its last piece.  AG2_STREAM_WAIT_KERNEL=1 lets the kernel
+    // start at once and wait per direction for the piece that holds its read instead -- that needs the pack kernels to find
+    // room beside the resident pair kernel, which they did not at the full configs[1] size (the waits ran into their limit).
+    const bool wait_on_host = getenv("AG2_STREAM_WAIT_KERNEL") == nullptr;
     if (ctx->reads_pending && wait_on_host) {
         CK(cudaStreamWaitEvent(st, ctx->pieces.back().ready, 0));
     } else if (ctx->reads_pending) {   // an asynchronous read load is in flight: directions wait for their piece inside the kernel
@@ -1451,6 +1486,7 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
     // on B200 is used (kStreamedByDefault).
     bool chunked = !kStreamedByDefault;
     if (const char *e = getenv("AG2_E2E_PATH")) chunked = strcmp(e, "streamed") != 0;
+    if (const char *e = getenv("AG2_WS_STREAMED")) ctx->ws_limit_streamed = (size_t)std::max(1ll, atoll(e));   // tuning / test knob, per call
     if (chunked) r = extend_batch(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, 0, &total, true, &sink, cand);
     else r = extend_batch_streamed(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, &total, &sink);
     if (r != AG2_OK) return r;

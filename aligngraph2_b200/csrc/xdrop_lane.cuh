@@ -75,7 +75,7 @@ struct LaneArgs {
     int32_t *wide_queue;
     unsigned int *wide_count;
     ChainCounters *counters;
-    unsigned int *done_ctas; // pair kernel: every CTA adds 1 when it has published all its hand-overs (may be null)
+    unsigned int *done_ctas; // pair kernel: every CTA adds 1 when it has published all its hand-overs (may be null); done_ctas[1] is raised when the first CTA starts
 };
 
 // Hand a direction over: the payload first, then -- fenced -- the queue entry, which a concurrently running consumer

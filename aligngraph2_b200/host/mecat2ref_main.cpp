@@ -13,6 +13,8 @@
 //     order (2.r..N.r and refN.r are created empty).  The reference's own per-read results do not depend on -t
 //     (SURVEY F6), only their order and, through polish_result's "last group of every thread file is not
 //     filtered" rule (:854), which groups escape the filter -- with one thread file that is deterministic.
+//   * the reads of every load_fastq batch are sharded over all visible GPUs (AG2_DEVICES names another set), one host
+//     thread per GPU, records written in device order = read order: the files do not depend on the number of GPUs.
 //   * -x is parsed and ignored, as in the reference.
 //   * no CPU fallback: without a usable GPU the program exits 1 (AlignGraph2.py:280-296 then falls back to the
 //     vanilla mecat2ref exactly as it does for any mecat2ref+ failure).
@@ -30,7 +32,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -496,17 +500,74 @@ void die_ag2(ag2_ctx *ctx, const char *what, int rc)
     exit(1);
 }
 
+// The GPUs the mapping runs on (reads shard across the GPUs of one box, no data-path collective): all visible
+// devices, or the list AG2_DEVICES names ("0,1,2"; a device may be named twice -- two contexts on one GPU, which is how the
+// sharding is tested on a one-GPU box).  CUDA_VISIBLE_DEVICES restricts what is visible as usual.
+std::vector<int> device_list()
+{
+    std::vector<int> devs;
+    if (const char *e = getenv("AG2_DEVICES")) {
+        for (const char *p = e; *p;) {
+            char *q = nullptr;
+            const long d = strtol(p, &q, 10);
+            if (q == p) break;
+            devs.push_back((int)d);
+            p = (*q == ',') ? q + 1 : q;
+        }
+    } else {
+        int n = 0;
+        if (ag2_device_count(&n) == AG2_OK)
+            for (int d = 0; d < n; ++d) devs.push_back(d);
+    }
+    return devs;
+}
+
+struct DeviceShard {   // one GPU's context and what it produced for the current batch
+    ag2_ctx *ctx = nullptr;
+    int64_t lo = 0, hi = 0;   // its contiguous range of the batch's reads
+    std::vector<int64_t> offs;
+    std::vector<ag2_record> rec;
+    std::vector<char> qaln, saln;
+    int64_t n_rec = 0;
+    int rc = AG2_OK;
+    const char *what = "";
+};
+
+template <class F> void on_every_device(std::vector<DeviceShard> &sh, F f)
+{
+    if (sh.size() == 1) {
+        f(sh[0]);
+    } else {
+        std::vector<std::thread> th;
+        for (DeviceShard &d : sh) th.emplace_back([&d, &f] { f(d); });
+        for (std::thread &t : th) t.join();
+    }
+    for (DeviceShard &d : sh)
+        if (d.rc != AG2_OK) die_ag2(d.ctx, d.what, d.rc);
+}
+
 // the mapping part of meap_ref_impl_large (:1994-2149) on the GPU; returns seconds {read index, ref index, mapping}
 void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
 {
-    ag2_ctx *ctx = nullptr;
-    int rc = ag2_ctx_create(0, &ctx);
-    if (rc != AG2_OK) {
-        fprintf(stderr, "mecat2ref (aligngraph2_b200): no usable CUDA device (%d); there is no CPU path\n", rc);
+    const std::vector<int> devs = device_list();
+    std::vector<DeviceShard> sh(devs.size());
+    for (size_t k = 0; k < devs.size(); ++k) {
+        const int rc = ag2_ctx_create(devs[k], &sh[k].ctx);
+        if (rc != AG2_OK) {
+            sh.clear();
+            break;
+        }
+    }
+    if (sh.empty()) {
+        fprintf(stderr, "mecat2ref (aligngraph2_b200): no usable CUDA device; there is no CPU path\n");
         exit(1);
     }
+    const size_t ndev = sh.size();
     double t0 = now_sec();
-    if ((rc = ag2_ref_load(ctx, ref_seq.data(), (int64_t)ref_seq.size())) != AG2_OK) die_ag2(ctx, "ag2_ref_load", rc);
+    on_every_device(sh, [&](DeviceShard &d) {
+        d.what = "ag2_ref_load";
+        d.rc = ag2_ref_load(d.ctx, ref_seq.data(), (int64_t)ref_seq.size());
+    });
     secs[1] = now_sec() - t0;
     const std::string wrk = o.wrk_dir;
     FILE *fq = fopen((wrk + "/0.fq").c_str(), "r");
@@ -522,8 +583,6 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
     size_t cap = 0;
     bool first_batch = true, more = true;
     secs[0] = secs[2] = 0;
-    std::vector<ag2_record> rec;
-    std::vector<char> qaln, saln;
     while (more) {
         // load_fastq (:1965-1991): up to SVM reads / MAXSTR characters, plus the record that ended the loop
         std::string bases;
@@ -550,38 +609,63 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
             }
         }
         if (ids.empty()) break;
+        const int64_t n_reads = (int64_t)ids.size();
         t0 = now_sec();
-        if ((rc = ag2_reads_load(ctx, bases.data(), offs.data(), (int64_t)ids.size())) != AG2_OK) die_ag2(ctx, "ag2_reads_load", rc);
         if (first_batch) {
-            // build_read_index uses the first <= 100 000 reads of the file; the index is built once (:2017-2033)
-            const double ti = now_sec();
-            if ((rc = ag2_index_build(ctx, o.block, o.alpha, o.beta)) != AG2_OK) die_ag2(ctx, "ag2_index_build", rc);
-            secs[0] = now_sec() - ti;
-            first_batch = false;
+            // build_read_index uses the first <= 100 000 reads of the file; the index is built once (:2017-2033), on every
+            // GPU from the same reads (the whole first batch), so every GPU votes and seeds with the same tables
+            on_every_device(sh, [&](DeviceShard &d) {
+                d.what = "ag2_reads_load";
+                if ((d.rc = ag2_reads_load(d.ctx, bases.data(), offs.data(), n_reads)) != AG2_OK) return;
+                d.what = "ag2_index_build";
+                d.rc = ag2_index_build(d.ctx, o.block, o.alpha, o.beta);
+            });
+            secs[0] = now_sec() - t0;
             t0 = now_sec();
         }
-        int64_t n_rec = 0, used = 0;
-        if ((rc = ag2_map_reads(ctx, o.num_candidates, o.num_output, &n_rec)) != AG2_OK) die_ag2(ctx, "ag2_map_reads", rc);
-        rec.resize((size_t)n_rec + 1);
-        if ((rc = ag2_map_fetch(ctx, rec.data(), nullptr, nullptr, 0, &used)) != AG2_OK) die_ag2(ctx, "ag2_map_fetch", rc);
-        qaln.resize((size_t)used + 1);
-        saln.resize((size_t)used + 1);
-        if ((rc = ag2_map_fetch(ctx, rec.data(), qaln.data(), saln.data(), used, &used)) != AG2_OK) die_ag2(ctx, "ag2_map_fetch", rc);
-        secs[2] += now_sec() - t0;
-        for (int64_t k = 0; k < n_rec; ++k) { // output_temp_result (output.cpp:237-251)
-            const ag2_record &r = rec[(size_t)k];
-            fprintf(out, "%d\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld\n", ids[(size_t)r.read], r.strand ? 'R' : 'F', r.vscore, r.qb, r.qe, r.qs, (long)r.sb,
-                    (long)r.se);
-            fwrite(qaln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
-            fputc('\n', out);
-            fwrite(saln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
-            fputc('\n', out);
+        // contiguous read ranges, balanced by bases: concatenating the GPUs' records in device order keeps the file order
+        for (size_t k = 0; k < ndev; ++k) {
+            const int64_t want = (int64_t)((double)offs[(size_t)n_reads] * (double)(k + 1) / (double)ndev);
+            sh[k].lo = k ? sh[k - 1].hi : 0;
+            sh[k].hi = k + 1 == ndev ? n_reads : std::max<int64_t>(sh[k].lo, std::upper_bound(offs.begin(), offs.end(), want) - offs.begin() - 1);
+            sh[k].hi = std::min(sh[k].hi, n_reads);
         }
+        on_every_device(sh, [&](DeviceShard &d) {
+            d.n_rec = 0;
+            if (d.hi <= d.lo) return;
+            if (!(first_batch && ndev == 1)) {   // (one GPU, first batch: its reads are the batch that is loaded already)
+                d.offs.resize((size_t)(d.hi - d.lo) + 1);
+                for (int64_t r = d.lo; r <= d.hi; ++r) d.offs[(size_t)(r - d.lo)] = offs[(size_t)r] - offs[(size_t)d.lo];
+                d.what = "ag2_reads_load";
+                if ((d.rc = ag2_reads_load(d.ctx, bases.data() + offs[(size_t)d.lo], d.offs.data(), d.hi - d.lo)) != AG2_OK) return;
+            }
+            int64_t used = 0;
+            d.what = "ag2_map_reads";
+            if ((d.rc = ag2_map_reads(d.ctx, o.num_candidates, o.num_output, &d.n_rec)) != AG2_OK) return;
+            d.rec.resize((size_t)d.n_rec + 1);
+            d.what = "ag2_map_fetch";
+            if ((d.rc = ag2_map_fetch(d.ctx, d.rec.data(), nullptr, nullptr, 0, &used)) != AG2_OK) return;
+            d.qaln.resize((size_t)used + 1);
+            d.saln.resize((size_t)used + 1);
+            d.rc = ag2_map_fetch(d.ctx, d.rec.data(), d.qaln.data(), d.saln.data(), used, &used);
+        });
+        first_batch = false;
+        secs[2] += now_sec() - t0;
+        for (const DeviceShard &d : sh)
+            for (int64_t k = 0; k < d.n_rec; ++k) { // output_temp_result (output.cpp:237-251)
+                const ag2_record &r = d.rec[(size_t)k];
+                fprintf(out, "%d\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld\n", ids[(size_t)(d.lo + r.read)], r.strand ? 'R' : 'F', r.vscore, r.qb, r.qe, r.qs,
+                        (long)r.sb, (long)r.se);
+                fwrite(d.qaln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
+                fputc('\n', out);
+                fwrite(d.saln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
+                fputc('\n', out);
+            }
     }
     free(line);
     fclose(fq);
     fclose(out);
-    ag2_ctx_destroy(ctx);
+    for (DeviceShard &d : sh) ag2_ctx_destroy(d.ctx);
 }
 
 } // namespace

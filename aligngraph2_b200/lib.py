@@ -32,7 +32,7 @@ class ExtendStats(C.Structure):
 
 
 EXPORTS = [
-    "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load", "ag2_reads_load_async", "ag2_reads_wait",
+    "ag2_device_count", "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load", "ag2_reads_load_async", "ag2_reads_wait",
     "ag2_xdrop_extend_batch", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
     "ag2_ctx_stream", "ag2_index_build", "ag2_index_fetch", "ag2_seed_candidates",
     "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch",
@@ -57,6 +57,7 @@ def load() -> C.CDLL:
                        "(nvcc, sm_100a).  aligngraph2_b200 has no CPU fallback.")
     L = C.CDLL(SO)
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.ag2_device_count.argtypes = [C.POINTER(i32)]
     L.ag2_ctx_create.argtypes = [i32, C.POINTER(vp)]
     L.ag2_ctx_destroy.argtypes = [vp]
     L.ag2_ctx_destroy.restype = None

@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-path", default="default", choices=["default", "chunked", "streamed"],
                     help="form of the host-buffer run (AG2_E2E_PATH of ag2_xdrop_extend_batch); default = the library's own choice")
+    ap.add_argument("--e2e-sweep", default="", help="tuning: ';'-separated sets of NAME=VALUE,... library knobs, each timed like e2e and reported on stderr")
     ap.add_argument("--pagraph-reads", type=int, default=4000, help="reads of the A-Bruijn build stage line (0 = skip)")
     ap.add_argument("--pagraph-k", type=int, default=14)
     return ap.parse_args()
@@ -372,26 +373,45 @@ def main():
             parts[1] += time.perf_counter() - t1
             return u
 
+        def timed_steps(k):
+            step()
+            parts[0] = parts[1] = 0.0
+            barrier()
+            e0.record(stream)
+            u = 0
+            for _ in range(k):
+                u = step()
+            e1.record(stream)
+            barrier()
+            return u
+
+        # tuning runs (--e2e-sweep "NAME=VALUE,NAME=VALUE;..."): each entry is a set of AG2_* knobs, reported on stderr
+        for entry in [x for x in args.e2e_sweep.split(";") if x]:
+            knobs = dict(kv.split("=", 1) for kv in entry.split(","))
+            os.environ.update(knobs)
+            try:
+                timed_steps(args.steps)
+                aligned = float(rec_np["qe"][rec_np["ok"] == 1].astype(np.int64).sum() - rec_np["qb"][rec_np["ok"] == 1].astype(np.int64).sum())
+                out = {"knobs": knobs, "ms_per_step": e0.elapsed_time(e1) / args.steps,
+                       "gbp_per_s": aligned * args.steps / (e0.elapsed_time(e1) * 1e-3) / 1e9}
+            except Exception as e:
+                out = {"knobs": knobs, "error": repr(e)}
+            print("[bench sweep] " + json.dumps(out), file=sys.stderr, flush=True)
+            for k in knobs:
+                os.environ.pop(k, None)
+
         if args.e2e_path != "default":
             os.environ["AG2_E2E_PATH"] = args.e2e_path
         e2e_path, e2e_note = args.e2e_path, None
         try:
-            step()
+            used = timed_steps(args.steps)
         except Exception as e:  # the streamed form gives up when its uploads stall; the chunked form has no such wait
             if os.environ.get("AG2_E2E_PATH") == "chunked":
                 raise
             e2e_note = f"{e2e_path} form failed ({e!r}); measured with the chunked form"
             print("[bench] " + e2e_note, file=sys.stderr)
             os.environ["AG2_E2E_PATH"] = e2e_path = "chunked"
-            step()
-        parts[0] = parts[1] = 0.0
-        barrier()
-        e0.record(stream)
-        used = 0
-        for _ in range(args.steps):
-            used = step()
-        e1.record(stream)
-        barrier()
+            used = timed_steps(args.steps)
         t2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)

@@ -72,6 +72,10 @@ typedef struct ag2_extend_stats {
     int64_t lane_chains;  /* extension directions the pair kernel handed on (to the wide kernel when few, else to the lane kernel) */
 } ag2_extend_stats;
 
+/* Number of CUDA devices this process sees.  The hosts shard reads over them, one ag2_ctx and one host thread per
+ * device (the counterpart of the reference's -t worker threads, mecat2ref_impl_large.cpp:2072-2087, which share one
+ * index; here every device holds its own copy). */
+int ag2_device_count(int *count);
 int ag2_ctx_create(int device, ag2_ctx **ctx);
 void ag2_ctx_destroy(ag2_ctx *ctx);
 const char *ag2_last_error(const ag2_ctx *ctx);
@@ -97,7 +101,10 @@ int ag2_reads_wait(ag2_ctx *ctx);
 /* extend_candidate x n.  rec_out[n]; qaln_out/saln_out receive ASCII ACGT- columns of the ok
  * records back to back (record i at [aln_off, aln_off + aln_len)); aln_cap is the capacity of
  * each string buffer, *aln_used the bytes written.  AG2_ECAP if too small (rec_out is still
- * filled, so the caller can size the buffers and call ag2_extend_fetch). */
+ * filled, so the caller can size the buffers and call ag2_extend_fetch).
+ * Results travel home while later candidates are still being extended.  Environment AG2_E2E_PATH (read per call)
+ * picks how: "chunked" = one kernel launch per output chunk, "streamed" = one launch for the whole batch with a flag
+ * per finished output chunk; unset = the library's default.  The bytes written are the same. */
 int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out,
                            char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used);
 

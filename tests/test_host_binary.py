@@ -95,6 +95,19 @@ def test_whole_program_matches_reference(binary, tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0,0,0"])
+def test_reads_sharded_over_devices_give_the_same_files(binary, tmp_path, devices):
+    """every load_fastq batch is cut into contiguous read ranges, one per device (its own context, index copy
+    and host thread); the thread file is written in device order.  AG2_DEVICES may name a device more than once, so the
+    sharding runs on a one-GPU box: all files must equal the reference's, whatever the number of shards."""
+    gold = golden_ref_outputs()
+    _inputs(tmp_path)
+    r = subprocess.run([binary] + ARGS, cwd=tmp_path, env=dict(os.environ, AG2_DEVICES=devices), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    _check_outputs(tmp_path, gold, thread_file=True)
+
+
+@pytest.mark.gpu
 def test_whole_program_matches_reference_binary_run(binary, tmp_path):
     from oracle import binding
     if not os.path.exists(binding.REF_BIN):
@@ -139,3 +152,12 @@ def test_more_than_one_load_fastq_batch(binary, tmp_path):
     for name in ("wrk/0.fq", "wrk/chrindex.txt", "wrk/1.r", "o.txt", "p.txt"):
         assert (a / name).read_bytes() == (b / name).read_bytes(), name
     assert (b / "p.txt").read_bytes().count(b"\n") > 3 * 99_000
+    # the same with both batches sharded over three contexts (the index still comes from the whole first batch)
+    c = tmp_path / "gpu3"
+    c.mkdir()
+    for name in ("ref.fa", "reads.fq"):
+        os.link(b / name, c / name)
+    r = subprocess.run([binary] + ARGS, cwd=c, env=dict(os.environ, AG2_DEVICES="0,0,0"), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    for name in ("wrk/1.r", "o.txt", "p.txt"):
+        assert (b / name).read_bytes() == (c / name).read_bytes(), name
