@@ -423,7 +423,13 @@ struct ag2_ctx {
     DevBuf order_keys, order_keys2, order_ids, order_queue, order_tmp;   // longest-first queue of the pair kernel
     DevBuf scalars;                     // ChainCounters + work counters + totals
     size_t ws_limit = (size_t)24 << 30; // bytes per workspace string per chunk (resident runs: one chunk, no drain tails)
-    size_t ws_limit_streamed = (size_t)1 << 30; // streamed runs: workspace bytes per OUTPUT chunk (finalised, assembled and copied home while the kernel goes on)
+    // host-buffer runs (ag2_xdrop_extend_batch), workspace bytes per OUTPUT chunk.  Chunked form: one launch per chunk, and a
+    // launch lasts at least as long as its longest direction, so a chunk must hold several times the 132 k directions the GPU
+    // runs at once (6 GiB = 2 chunks at configs[1]: 606 ms per step; 1 GiB = 13 chunks: 1187 ms).  Streamed form: one launch,
+    // the chunk is only the unit that is finalised, assembled and copied home while the kernel goes on.
+    size_t ws_limit_chunked = (size_t)6 << 30;
+    size_t ws_limit_streamed = (size_t)1 << 30;
+    size_t ws_call = 0;                   // the limit of the call in progress (AG2_WS_STREAMED overrides either default)
     int64_t piece_bytes = (int64_t)256 << 20;   // ASCII bytes per upload piece of ag2_reads_load
     cudaStream_t copy_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // high priority: the consumer of the pair kernel's hand-overs
@@ -606,7 +612,6 @@ int ag2_ctx_create(int device, ag2_ctx **out)
         return AG2_ECUDA;
     }
     // test knobs: many small chunks / upload pieces on small inputs
-    if (const char *e = getenv("AG2_WS_STREAMED")) ctx->ws_limit_streamed = (size_t)std::max(1ll, atoll(e));
     if (const char *e = getenv("AG2_PIECE_BYTES")) ctx->piece_bytes = std::max(1ll, atoll(e));
     *out = ctx;
     return AG2_OK;
@@ -899,13 +904,21 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     // candidates are processed in chunks whose workspace strings fit ws_limit
     size_t max_chunk = 0, max_meta = 0;
     std::vector<std::pair<int64_t, int64_t>> chunks;
-    for (int64_t lo = 0; lo < n;) {
-        int64_t hi = lo + 1;
-        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= (sink ? ctx->ws_limit_streamed : ctx->ws_limit)) ++hi;
-        chunks.push_back({lo, hi});
-        max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
-        max_meta = std::max(max_meta, (size_t)(mf[hi] - mf[lo]));
-        lo = hi;
+    {   // as few chunks as the limit allows, of equal size (a small last chunk would still cost a whole launch)
+        const size_t limit = std::max<size_t>(1, sink ? ctx->ws_call : ctx->ws_limit);
+        const int64_t nch = std::max<int64_t>(1, (int64_t)(((size_t)pf[n] + limit - 1) / limit));
+        for (int64_t k = 0, lo = 0; lo < n; ++k) {
+            int64_t hi = n;
+            if (k + 1 < nch) {
+                const int64_t end = (int64_t)((double)pf[n] * (double)(k + 1) / (double)nch);
+                hi = std::upper_bound(pf.begin() + lo + 1, pf.begin() + n + 1, end) - pf.begin() - 1;
+                hi = std::min<int64_t>(n, std::max<int64_t>(lo + 1, hi));
+            }
+            chunks.push_back({lo, hi});
+            max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
+            max_meta = std::max(max_meta, (size_t)(mf[hi] - mf[lo]));
+            lo = hi;
+        }
     }
     RESERVE(ctx->ws_q, max_chunk + 64);
     RESERVE(ctx->ws_t, max_chunk + 64);
@@ -1112,6 +1125,8 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
 
 // Which form ag2_xdrop_extend_batch takes when AG2_E2E_PATH does not say (see there).
 constexpr bool kStreamedByDefault = false;
+constexpr int kStreamPairCtasPerSm = 6;   // streamed form: pair CTAs per SM (7 fit), see extend_batch_streamed
+constexpr int kStreamStalled = 1;         // extend_batch_streamed: in-kernel waits for the reads ran into their limit, results void
 
 // extend_candidate over n device-resident candidates, results streamed to the caller's host buffers (`sink`).
 // ONE launch of the pair kernel covers every direction (a direction is a chain of sequentially dependent block DPs: cutting
@@ -1141,11 +1156,21 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     RESERVE(ctx->lane_resume, (size_t)n * 2 * sizeof(LaneResume));
     RESERVE(ctx->chunk_count, (size_t)kMaxStreamChunks * 4);
 
-    int pocc = 0;
-    const size_t pair_smem = sizeof(PairSmem);
-    CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+    // The small kernels of this form (packing of the pieces still arriving, finalize / scan / assemble of the finished
+    // chunks) must run BESIDE the resident pair kernel.  At its full 7 CTAs per SM they did not get onto the SMs before pair
+    // CTAs retired (configs[1]: the first chunk's finalize waited 250 ms, in-kernel waits for the pack kernels ran into their
+    // limit), so this launch asks for more dynamic shared memory than it uses until only kStreamPairCtasPerSm fit: every SM
+    // keeps a free slot (shared memory, 8 k registers, 64 threads) for them.
+    int pocc = 0, want_occ = kStreamPairCtasPerSm;
+    if (const char *e = getenv("AG2_STREAM_CTAS_PER_SM")) want_occ = std::max(1, atoi(e));   // tuning knob
+    size_t pair_smem = sizeof(PairSmem);
     CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, xdrop_pair_kernel, kPairThreads, pair_smem));
+    for (;;) {
+        CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, xdrop_pair_kernel, kPairThreads, pair_smem));
+        if (pocc <= want_occ || pair_smem + 1024 > (size_t)200 * 1024) break;
+        pair_smem += 1024;
+    }
     if (pocc < 1) pocc = 1;
     const int pair_full = ctx->sm_count * pocc;
     RESERVE(ctx->tb_pair, kPairCtaScratch * (size_t)pair_full);
@@ -1170,9 +1195,7 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     RESERVE(ctx->tb_stream, tbw_stride * std::max(1, stream_grid) * kWideWarps);
     // every pair CTA resident from the start (a consumer CTA takes one pair CTA's place): nothing of this launch is left
     // pending in front of the small kernels that have to run beside it
-    int spare = 0;
-    if (const char *e = getenv("AG2_STREAM_SPARE_CTAS")) spare = std::max(0, atoi(e));   // tuning knob: pair CTAs left out to make room for the small kernels
-    const int pair_grid = std::max(1, pair_full - stream_grid - spare);
+    const int pair_grid = std::max(1, pair_full - stream_grid);
 
     const PackedSeqs sq = seqs_of(ctx);
     Scalars *sc = (Scalars *)ctx->scalars.p;
@@ -1196,7 +1219,7 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     RESERVE(ctx->out_t, (size_t)ws_total + 64);
 
     // output chunks: equal candidate counts, about ws_limit_streamed bytes of workspace string each
-    int64_t want = (int64_t)std::min<size_t>(kMaxStreamChunks, std::max<size_t>(1, ((size_t)ws_total + ctx->ws_limit_streamed - 1) / ctx->ws_limit_streamed));
+    int64_t want = (int64_t)std::min<size_t>(kMaxStreamChunks, std::max<size_t>(1, ((size_t)ws_total + ctx->ws_call - 1) / ctx->ws_call));
     const int64_t chunk_cn = std::max<int64_t>(1, (n + want - 1) / want);
     const int n_chunks = (int)((n + chunk_cn - 1) / chunk_cn);
     if (chunk_cn > 0x7fffffff) return fail(ctx, AG2_EINVAL, "ag2_xdrop_extend_batch: too many candidates per chunk");
@@ -1408,7 +1431,10 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
 
     Scalars hs;
     CK(cudaMemcpy(&hs, sc, sizeof hs, cudaMemcpyDeviceToHost));
-    if (hs.stream_error) return fail(ctx, AG2_ECUDA, "ag2_xdrop_extend_batch: %u directions gave up waiting for their reads (upload stalled)", hs.stream_error);
+    if (hs.stream_error) {   // the caller reruns the batch in the chunked form
+        fail(ctx, AG2_ECUDA, "ag2_xdrop_extend_batch: %u directions gave up waiting for their reads (upload stalled)", hs.stream_error);
+        return kStreamStalled;
+    }
     ag2_extend_stats &s = ctx->stats;
     s.cells = (int64_t)hs.ctr.cells;
     s.rows = (int64_t)hs.ctr.rows;
@@ -1486,9 +1512,20 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
     // on B200 is used (kStreamedByDefault).
     bool chunked = !kStreamedByDefault;
     if (const char *e = getenv("AG2_E2E_PATH")) chunked = strcmp(e, "streamed") != 0;
-    if (const char *e = getenv("AG2_WS_STREAMED")) ctx->ws_limit_streamed = (size_t)std::max(1ll, atoll(e));   // tuning / test knob, per call
+    ctx->ws_call = chunked ? ctx->ws_limit_chunked : ctx->ws_limit_streamed;
+    if (const char *e = getenv("AG2_WS_STREAMED")) ctx->ws_call = (size_t)std::max(1ll, atoll(e));   // tuning / test knob, per call
+    if (!chunked) {
+        r = extend_batch_streamed(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, &total, &sink);
+        if (r == kStreamStalled) {   // only with AG2_STREAM_WAIT_KERNEL: nothing of this run is valid, the reads are up by now
+            fprintf(stderr, "[ag2] %s; running the batch again in the chunked form\n", ctx->err.c_str());
+            if ((r = reads_barrier(ctx)) != AG2_OK) return r;
+            sink.overflow = false;
+            total = 0;
+            chunked = true;
+            ctx->ws_call = ctx->ws_limit_chunked;
+        }
+    }
     if (chunked) r = extend_batch(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, 0, &total, true, &sink, cand);
-    else r = extend_batch_streamed(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, &total, &sink);
     if (r != AG2_OK) return r;
     if ((r = reads_barrier(ctx)) != AG2_OK) return r;   // reads no candidate refers to may still be on their way
     ctx->out_total = total;
