@@ -1124,9 +1124,11 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
 }
 
 // Which form ag2_xdrop_extend_batch takes when AG2_E2E_PATH does not say (see there).
-constexpr bool kStreamedByDefault = false;
+constexpr bool kStreamedByDefault = true;
 constexpr int kStreamPairCtasPerSm = 6;   // streamed form: pair CTAs per SM (7 fit), see extend_batch_streamed
-constexpr int kStreamStalled = 1;         // extend_batch_streamed: in-kernel waits for the reads ran into their limit, results void
+// extend_batch_streamed asks for the chunked form instead (positive: not an error of the call)
+constexpr int kStreamStalled = 1;         // in-kernel waits for the reads ran into their limit, results void
+constexpr int kStreamTooBig = 2;          // the whole batch's workspace does not fit beside what is resident; nothing ran
 
 // extend_candidate over n device-resident candidates, results streamed to the caller's host buffers (`sink`).
 // ONE launch of the pair kernel covers every direction (a direction is a chain of sequentially dependent block DPs: cutting
@@ -1212,6 +1214,13 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     CK(cudaMemcpyAsync(&ws_total, (int64_t *)ctx->prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&meta_total, (int64_t *)ctx->meta_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    {   // one launch needs the workspace strings of the WHOLE batch (the chunked form only those of a chunk)
+        size_t free_b = 0, total_b = 0, grow = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        for (const DevBuf *b : {&ctx->ws_q, &ctx->ws_t})
+            if (b->cap < (size_t)ws_total + 64) grow += (size_t)ws_total + 64;
+        if (grow + ((size_t)meta_total + 16) * 4 > free_b - std::min(free_b, (size_t)1 << 30)) return kStreamTooBig;
+    }
     RESERVE(ctx->ws_q, (size_t)ws_total + 64);
     RESERVE(ctx->ws_t, (size_t)ws_total + 64);
     RESERVE(ctx->meta, ((size_t)meta_total + 16) * 4);
@@ -1254,10 +1263,11 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     sig.n_cand = n;
     sig.chunk_cn = (int32_t)chunk_cn;
     sig.error = &sc->stream_error;
-    // An asynchronous read load in flight: the launch waits for its last piece.  AG2_STREAM_WAIT_KERNEL=1 lets the kernel
-    // start at once and wait per direction for the piece that holds its read instead -- that needs the pack kernels to find
-    // room beside the resident pair kernel, which they did not at the full configs[1] size (the waits ran into their limit).
-    const bool wait_on_host = getenv("AG2_STREAM_WAIT_KERNEL") == nullptr;
+    // An asynchronous read load in flight: the kernel starts at once and every direction waits for the piece that holds its
+    // read (wait_for_read) -- the pack kernels of the later pieces run in the slot every SM keeps free (see above; with all 7
+    // pair CTAs per SM they did not, and the waits ran into their limit: kStreamStalled).  AG2_STREAM_WAIT_HOST=1 makes the
+    // launch wait for the last piece instead (configs[1]: 571 ms per step instead of 519).
+    const bool wait_on_host = getenv("AG2_STREAM_WAIT_HOST") != nullptr;
     if (ctx->reads_pending && wait_on_host) {
         CK(cudaStreamWaitEvent(st, ctx->pieces.back().ready, 0));
     } else if (ctx->reads_pending) {   // an asynchronous read load is in flight: directions wait for their piece inside the kernel
@@ -1508,16 +1518,16 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
     int64_t total = 0;
     // Two forms of the host-buffer run: "chunked" = one pair-kernel launch per output chunk, the chunk's results copied home
     // while the next chunk computes; "streamed" = ONE launch for the whole batch with flags per output chunk
-    // (extend_batch_streamed).  AG2_E2E_PATH picks one per call; without it the form measured at the full configs[1] size
-    // on B200 is used (kStreamedByDefault).
+    // (extend_batch_streamed).  AG2_E2E_PATH picks one per call; without it the faster one at the full configs[1] size on
+    // B200 is used (kStreamedByDefault; 519 vs 602 ms per step, profiles/e2e_sweep_r01l.md).
     bool chunked = !kStreamedByDefault;
     if (const char *e = getenv("AG2_E2E_PATH")) chunked = strcmp(e, "streamed") != 0;
     ctx->ws_call = chunked ? ctx->ws_limit_chunked : ctx->ws_limit_streamed;
     if (const char *e = getenv("AG2_WS_STREAMED")) ctx->ws_call = (size_t)std::max(1ll, atoll(e));   // tuning / test knob, per call
     if (!chunked) {
         r = extend_batch_streamed(ctx, (const Candidate *)ctx->cand.p, n, (Record *)ctx->rec.p, &total, &sink);
-        if (r == kStreamStalled) {   // only with AG2_STREAM_WAIT_KERNEL: nothing of this run is valid, the reads are up by now
-            fprintf(stderr, "[ag2] %s; running the batch again in the chunked form\n", ctx->err.c_str());
+        if (r == kStreamStalled || r == kStreamTooBig) {   // stalled: nothing of that run is valid, and the reads are up by now
+            if (r == kStreamStalled) fprintf(stderr, "[ag2] %s; running the batch again in the chunked form\n", ctx->err.c_str());
             if ((r = reads_barrier(ctx)) != AG2_OK) return r;
             sink.overflow = false;
             total = 0;

@@ -102,9 +102,11 @@ int ag2_reads_wait(ag2_ctx *ctx);
  * records back to back (record i at [aln_off, aln_off + aln_len)); aln_cap is the capacity of
  * each string buffer, *aln_used the bytes written.  AG2_ECAP if too small (rec_out is still
  * filled, so the caller can size the buffers and call ag2_extend_fetch).
- * Results travel home while later candidates are still being extended.  Environment AG2_E2E_PATH (read per call)
- * picks how: "chunked" = one kernel launch per output chunk, "streamed" = one launch for the whole batch with a flag
- * per finished output chunk; unset = the library's default.  The bytes written are the same. */
+ * Results travel home while later candidates are still being extended: one kernel launch covers the whole batch and
+ * raises a flag per finished output chunk ("streamed" form; after ag2_reads_load_async the kernel also starts before
+ * the reads are all up).  Environment AG2_E2E_PATH=chunked (read per call) selects one launch per output chunk instead,
+ * which needs device workspace for a chunk only; the library falls back to it by itself when the batch's workspace
+ * does not fit.  The bytes written are the same. */
 int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out,
                            char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used);
 

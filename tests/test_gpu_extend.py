@@ -164,7 +164,7 @@ def test_properties_at_scale(dev):
     assert np.array_equal(rec, rec2) and np.array_equal(qa, qa2) and np.array_equal(sa, sa2)
 
 
-@pytest.mark.parametrize("path", ["streamed", "streamed-kernelwait", "chunked"])
+@pytest.mark.parametrize("path", ["streamed", "streamed-hostwait", "chunked"])
 @pytest.mark.parametrize("order", ["read", "shuffled"])
 def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order, path):
     """ag2_reads_load_async + ag2_xdrop_extend_batch with host buffers: the reads go up in many pieces while ONE launch
@@ -185,8 +185,8 @@ def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order, path):
     assert rec["ok"].mean() > 0.98
 
     monkeypatch.setenv("AG2_E2E_PATH", path.split("-")[0])  # both forms of the host-buffer run (ag2_xdrop_extend_batch)
-    if path.endswith("kernelwait"):                         # streamed, and the reads are waited for inside the kernel, per piece
-        monkeypatch.setenv("AG2_STREAM_WAIT_KERNEL", "1")
+    if path.endswith("hostwait"):                           # streamed, but the launch waits for the last piece of the reads
+        monkeypatch.setenv("AG2_STREAM_WAIT_HOST", "1")
     monkeypatch.setenv("AG2_WS_STREAMED", str(400_000))    # ~ 30 reads per chunk
     monkeypatch.setenv("AG2_PIECE_BYTES", str(100_000))    # ~ 25 reads per piece
     dev2 = Mecat2RefDevice(0)
