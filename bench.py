@@ -402,7 +402,7 @@ def main():
 
         if args.e2e_path != "default":
             os.environ["AG2_E2E_PATH"] = args.e2e_path
-        e2e_path, e2e_note = args.e2e_path, None
+        e2e_path, e2e_note = ("streamed (library default)" if args.e2e_path == "default" else args.e2e_path), None
         try:
             used = timed_steps(args.steps)
         except Exception as e:  # the streamed form gives up when its uploads stall; the chunked form has no such wait
