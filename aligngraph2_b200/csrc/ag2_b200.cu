@@ -1219,7 +1219,7 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
         CK(cudaMemGetInfo(&free_b, &total_b));
         for (const DevBuf *b : {&ctx->ws_q, &ctx->ws_t})
             if (b->cap < (size_t)ws_total + 64) grow += (size_t)ws_total + 64;
-        if (grow + ((size_t)meta_total + 16) * 4 > free_b - std::min(free_b, (size_t)1 << 30)) return kStreamTooBig;
+        if (grow > 0 && grow + ((size_t)meta_total + 16) * 4 > free_b - std::min(free_b, (size_t)1 << 30)) return kStreamTooBig;
     }
     RESERVE(ctx->ws_q, (size_t)ws_total + 64);
     RESERVE(ctx->ws_t, (size_t)ws_total + 64);
