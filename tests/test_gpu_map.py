@@ -62,3 +62,38 @@ def test_more_outputs_and_fewer_candidates(dev, tmp_path):
     exp = str(tmp_path / "oracle.r")
     MapperOracle().map_batch(genome, bases, offs, np.arange(1, len(offs)), exp, cbl=10000, maxc=5, num_output=3)
     assert open(out, "rb").read() == open(exp, "rb").read()
+
+
+def test_250mb_reference_properties(dev):
+    """BASELINE configs[2] scale on the reference side: a 250 Mb reference (13-mer buckets of 3.7 positions, 1.25 M vote
+    blocks, positions beyond 2^27), whole per-read path.  No oracle at this size: the reads were cut from the reference, so
+    every read must come back on its own strand at its own template start, and the strings must spell the read and the
+    reference interval they claim."""
+    import torch
+    n, R = 1500, 250_000_000
+    d = synth.make_batch_torch(777, R, n, 10000, device="cuda")
+    ref = d["ref"].cpu().numpy()
+    bases, off = d["bases"].cpu().numpy(), d["offsets"].cpu().numpy()
+    start = d["start"].cpu().numpy()
+    del d
+    torch.cuda.empty_cache()
+    dev.load_reference(ref)
+    dev.load_reads(bases=bases, offsets=off)
+    dev.build_index(200, 0.5, 2.0)
+    rec, qa, sa = dev.map_reads(10, 1)
+    assert len(np.unique(rec["read"])) >= 0.98 * n
+    assert np.all(rec["se"] <= R) and np.all(rec["sb"] >= 0) and np.all(rec["se"] > rec["sb"])
+    # the longest record of every read: right strand, right place, (nearly) the whole read
+    order = np.lexsort((-(rec["qe"] - rec["qb"]), rec["read"]))
+    best = rec[order][np.unique(rec["read"][order], return_index=True)[1]]
+    assert np.mean(best["strand"] == (best["read"] & 1)) > 0.98
+    assert np.mean(np.abs(best["sb"] - start[best["read"]]) < 50) > 0.95
+    assert np.mean((best["qe"] - best["qb"]) > 0.9 * best["qs"]) > 0.95
+    rng = np.random.default_rng(5)
+    for i in rng.choice(len(best), size=60, replace=False):
+        r = best[i]
+        o, m = int(r["aln_off"]), int(r["aln_len"])
+        q, s = qa[o:o + m].tobytes(), sa[o:o + m].tobytes()
+        rd = synth.orient(bases[off[r["read"]]:off[r["read"] + 1]].tobytes(), int(r["strand"]))
+        assert len(q) == len(s) and q.replace(b"-", b"") == rd[r["qb"]:r["qe"]]
+        assert s.replace(b"-", b"") == ref[r["sb"]:r["se"]].tobytes()
