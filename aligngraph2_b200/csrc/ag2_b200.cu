@@ -406,7 +406,7 @@ struct ag2_ctx {
         map_list, map_out_prefix, map_out_rec;
     int64_t map_n_out = 0;
     bool mapped = false;
-    size_t seed_scratch_limit = (size_t)4 << 30;
+    size_t seed_scratch_limit = 0;        // 0 = from the free memory (seed_limit); else a fixed limit in bytes
     DevBuf reads2, reads_irr, read_off, read_len, ascii_offs;
     int64_t n_reads = 0, read_bases = 0;
 
@@ -1659,6 +1659,20 @@ int ag2_index_fetch(ag2_ctx *ctx, int32_t *rcnt, int32_t *cnt, uint32_t *off, ui
 }
 
 // ---- seeding + candidate scoring (A5-A7) --------------------------------------------------------
+// Scratch for the per-read block tables of one seeding launch.  The table of a read grows with its index hits (250 Mb
+// reference: 2 600 hits per strand, 8 192 slots of 96 B = 786 KB per read), and a launch runs as many reads at once as
+// fit: with the former fixed 4 GiB that was 5 000 reads -- 34 threads per SM, 1.7 s per 100 k reads
+// (profiles/bench_r01o_250mb_100k.json).  Now a third of the free HBM, between 4 and 48 GiB.
+static size_t seed_limit(ag2_ctx *ctx)
+{
+    if (const char *e = getenv("AG2_SEED_SCRATCH")) return (size_t)std::max(1ll, atoll(e));   // test knob: many small launches
+    if (ctx->seed_scratch_limit) return ctx->seed_scratch_limit;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (size_t)4 << 30;
+    const size_t third = (free_b + ctx->seed_scratch.cap) / 3;
+    return std::min<size_t>((size_t)48 << 30, std::max<size_t>((size_t)4 << 30, third));
+}
+
 int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *out, int32_t *ncand_out)
 {
     static_assert(sizeof(ag2_seed_candidate) == sizeof(SeedCand), "ag2_seed_candidate layout");
@@ -1687,9 +1701,10 @@ int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *ou
     CK(cudaStreamSynchronize(st));
     size_t max_chunk = 0;
     std::vector<std::pair<int64_t, int64_t>> chunks;
+    const size_t scratch_limit = seed_limit(ctx);
     for (int64_t lo = 0; lo < n;) {
         int64_t hi = lo + 1;
-        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= ctx->seed_scratch_limit) ++hi;
+        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= scratch_limit) ++hi;
         chunks.push_back({lo, hi});
         max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
         lo = hi;
@@ -1766,9 +1781,10 @@ static int map_pass(ag2_ctx *ctx, int pass, int maxc, int num_output, const int3
     CK(cudaStreamSynchronize(st));
     size_t max_chunk = 0;
     std::vector<std::pair<int64_t, int64_t>> chunks;
+    const size_t scratch_limit = seed_limit(ctx);
     for (int64_t lo = 0; lo < n;) {
         int64_t hi = lo + 1;
-        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= ctx->seed_scratch_limit) ++hi;
+        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= scratch_limit) ++hi;
         chunks.push_back({lo, hi});
         max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
         lo = hi;

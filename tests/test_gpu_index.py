@@ -63,3 +63,11 @@ def test_other_parameters(dev):
     z = np.load(os.path.join(GOLDEN, "mapper_stress.npz"))
     _check(dev, z["genome"].tobytes(), z["bases"].tobytes(), z["offsets"].astype(np.int64), cbl=10000, alpha=0.3, beta=1.5,
            maxc=4, passes=(0,))
+
+
+def test_seeding_in_many_launches(dev, monkeypatch):
+    # the per-read block tables of one seeding launch share a scratch arena; a small arena cuts the batch into many launches
+    # (a few reads each), which must not change any candidate
+    monkeypatch.setenv("AG2_SEED_SCRATCH", str(300_000))
+    d = synth.make_batch_torch(123, 1_000_000, 60, 10000)
+    _check(dev, d["ref"].numpy().tobytes(), d["bases"].numpy().tobytes(), d["offsets"].numpy(), cbl=200, passes=(0, 1))
