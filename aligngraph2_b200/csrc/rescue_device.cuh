@@ -303,12 +303,7 @@ __device__ void plan_read(const RefIndex &ix, const uint32_t *reads2, const uint
         const int strand = alnv[i].qdir == 'F' ? 0 : 1;
         if (have_strand != strand) {
             const int64_t hits = count_hits(ix, reads2, irr, roff, rlen, strand, BC);
-            const uint32_t cap = table_capacity(hits);
-            tb.slots = reinterpret_cast<BlockSlot *>(scratch);
-            tb.mask = cap - 1;
-            tb.index_list = nullptr;
-            tb.index_score = nullptr;
-            for (uint32_t q = 0; q < cap; ++q) tb.slots[q].key = -1;
+            table_init(tb, scratch, hits, false);
             seed_only(ix, reads2, irr, roff, rlen, strand, BC, zv, tb);
             have_strand = strand;
         }

@@ -59,9 +59,9 @@ struct BackList {           // Back_List, M2R/mecat2ref_defs.h:84-88
     int32_t index;
 };
 
-struct BlockSlot {
+struct alignas(8) BlockSlot {   // open addressing over 8-byte slots; the 92-byte Back_Lists live in a pool, one per block touched
     int32_t key;            // block id, -1 = empty
-    BackList b;
+    int32_t val;            // index into BlockTable::pool
 };
 
 struct SeedCand {           // candidate_save, M2R/mecat2ref_defs.h:90-95
@@ -72,6 +72,8 @@ struct SeedCand {           // candidate_save, M2R/mecat2ref_defs.h:90-95
 
 struct BlockTable {
     BlockSlot *slots;
+    BackList *pool;         // [hits + 1]: a hit touches at most one new block
+    mutable int32_t n_pool;
     uint32_t mask;          // capacity - 1 (power of two)
     int32_t *index_list;    // first-touch order
     int16_t *index_score;
@@ -84,8 +86,8 @@ __device__ __forceinline__ BackList *table_find(const BlockTable &t, int32_t key
 {
     uint32_t h = (block_hash(key) >> 7) & t.mask;
     for (;;) {
-        BlockSlot &s = t.slots[h];
-        if (s.key == key) return &s.b;
+        const BlockSlot s = t.slots[h];
+        if (s.key == key) return &t.pool[s.val];
         if (s.key == -1) return nullptr;
         h = (h + 1) & t.mask;
     }
@@ -95,15 +97,17 @@ __device__ __forceinline__ BackList *table_get(const BlockTable &t, int32_t key)
 {
     uint32_t h = (block_hash(key) >> 7) & t.mask;
     for (;;) {
-        BlockSlot &s = t.slots[h];
-        if (s.key == key) return &s.b;
+        const BlockSlot s = t.slots[h];
+        if (s.key == key) return &t.pool[s.val];
         if (s.key == -1) {
-            s.key = key;
-            s.b.score = 0;
-            s.b.score2 = 0;
-            s.b.seednum = 0;
-            s.b.index = -1;
-            return &s.b;
+            const BlockSlot fresh = {key, t.n_pool};
+            t.slots[h] = fresh;
+            BackList *b = &t.pool[t.n_pool++];
+            b->score = 0;
+            b->score2 = 0;
+            b->seednum = 0;
+            b->index = -1;
+            return b;
         }
         h = (h + 1) & t.mask;
     }
@@ -429,8 +433,24 @@ __device__ __forceinline__ uint32_t table_capacity(int64_t hits)
 __device__ __forceinline__ int64_t table_bytes(int64_t hits)
 {
     const int64_t cap = table_capacity(hits);
-    int64_t b = cap * (int64_t)sizeof(BlockSlot) + (hits + 1) * (int64_t)sizeof(int32_t) + (hits + 1) * (int64_t)sizeof(int16_t);
+    int64_t b = cap * (int64_t)sizeof(BlockSlot) + (hits + 1) * (int64_t)(sizeof(BackList) + sizeof(int32_t) + sizeof(int16_t));
     return (b + 15) & ~(int64_t)15;
+}
+
+// lays the table of a strand with `hits` index hits out in scratch (table_bytes(hits) bytes, 16-byte aligned) and empties it
+__device__ __forceinline__ void table_init(BlockTable &tb, uint8_t *scratch, int64_t hits, bool with_index)
+{
+    const uint32_t cap = table_capacity(hits);
+    tb.slots = reinterpret_cast<BlockSlot *>(scratch);
+    tb.mask = cap - 1;
+    tb.pool = reinterpret_cast<BackList *>(scratch + (size_t)cap * sizeof(BlockSlot));
+    tb.n_pool = 0;
+    int32_t *il = reinterpret_cast<int32_t *>(tb.pool + hits + 1);
+    tb.index_list = with_index ? il : nullptr;
+    tb.index_score = with_index ? reinterpret_cast<int16_t *>(il + hits + 1) : nullptr;
+    tb.n_index = 0;
+    const BlockSlot empty = {-1, 0};
+    for (uint32_t i = 0; i < cap; ++i) tb.slots[i] = empty;
 }
 
 __device__ __forceinline__ int seed_stride(int rlen, int pass)
@@ -452,13 +472,7 @@ __device__ int map_read_candidates(const RefIndex &ix, const uint32_t *reads2, c
     for (int strand = 0; strand < 2; ++strand) {
         const int64_t hits = count_hits(ix, reads2, irr, roff, rlen, strand, BC);
         BlockTable tb;
-        const uint32_t cap = table_capacity(hits);
-        tb.slots = reinterpret_cast<BlockSlot *>(scratch);
-        tb.mask = cap - 1;
-        tb.index_list = reinterpret_cast<int32_t *>(scratch + (size_t)cap * sizeof(BlockSlot));
-        tb.index_score = reinterpret_cast<int16_t *>(tb.index_list + hits + 1);
-        tb.n_index = 0;
-        for (uint32_t i = 0; i < cap; ++i) tb.slots[i].key = -1;
+        table_init(tb, scratch, hits, true);
         seed_and_scan(ix, reads2, irr, roff, rlen, strand, BC, zv, thresh, maxc, tb, cands, ncand);
     }
     return ncand;
