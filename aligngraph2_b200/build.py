@@ -28,7 +28,8 @@ def build_host(force: bool = False, name: str = "mecat2ref") -> str:
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     for prog, src in HOST_PROGRAMS.items():
         src_path, out = os.path.join(PKG, "host", src), os.path.join(PKG, "bin", prog)
-        if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src_path), os.path.getmtime(SO)):
+        deps = [src_path, SO, os.path.join(PKG, "host", "shard_split.h")]
+        if not force and os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(p) for p in deps):
             continue
         subprocess.run([cxx, "-O2", "-std=c++17", "-Wall", "-pthread", "-o", out, src_path, "-L" + PKG, "-lag2_b200",
                         "-Wl,-rpath,$ORIGIN/.."], check=True, cwd=ROOT)

@@ -21,6 +21,7 @@
 // AG2_SKIP_MAP=1 in the environment skips the GPU stage and reuses the thread files already in <wrk> (used by
 // the CPU-side tests of the file handling, result_combine and polish_result).
 #include "../../include/ag2_b200.h"
+#include "shard_split.h"
 
 #include <dirent.h>
 #include <sys/stat.h>
@@ -507,13 +508,7 @@ std::vector<int> device_list()
 {
     std::vector<int> devs;
     if (const char *e = getenv("AG2_DEVICES")) {
-        for (const char *p = e; *p;) {
-            char *q = nullptr;
-            const long d = strtol(p, &q, 10);
-            if (q == p) break;
-            devs.push_back((int)d);
-            p = (*q == ',') ? q + 1 : q;
-        }
+        devs = ag2host::parse_device_list(e);
     } else {
         int n = 0;
         if (ag2_device_count(&n) == AG2_OK)
@@ -624,11 +619,10 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
             t0 = now_sec();
         }
         // contiguous read ranges, balanced by bases: concatenating the GPUs' records in device order keeps the file order
+        const std::vector<std::pair<int64_t, int64_t>> ranges = ag2host::split_by_bases(offs, ndev);
         for (size_t k = 0; k < ndev; ++k) {
-            const int64_t want = (int64_t)((double)offs[(size_t)n_reads] * (double)(k + 1) / (double)ndev);
-            sh[k].lo = k ? sh[k - 1].hi : 0;
-            sh[k].hi = k + 1 == ndev ? n_reads : std::max<int64_t>(sh[k].lo, std::upper_bound(offs.begin(), offs.end(), want) - offs.begin() - 1);
-            sh[k].hi = std::min(sh[k].hi, n_reads);
+            sh[k].lo = ranges[k].first;
+            sh[k].hi = ranges[k].second;
         }
         on_every_device(sh, [&](DeviceShard &d) {
             d.n_rec = 0;
