@@ -1,0 +1,44 @@
+"""The drop-in `mecat2ref` executable's HOST flow in the GPU-less container: load_fastq batching, the cut of a batch into
+per-device read ranges (one host thread and one context per device), read ids, record order, thread file, result_combine and
+polish_result -- with a TEST DOUBLE of the C ABI behind it (tests/host/fake_ag2_lib.cpp: the oracle answers the host's calls)
+instead of the CUDA library.  Every file must equal what the unmodified reference binary wrote, whatever the device count.
+The real library on a real GPU runs the same comparison in tests/test_host_binary.py (`-m gpu`)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import golden_ref_outputs
+from test_host_binary import ARGS, _check_outputs, _inputs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def staged(tmp_path_factory):
+    """<tmp>/libag2_b200.so = the test double, <tmp>/bin/mecat2ref = a copy of the product's executable (rpath $ORIGIN/..)."""
+    from aligngraph2_b200 import build
+    from oracle import binding
+    build.build()
+    exe = build.build_host()
+    binding.build(ref=False)
+    d = tmp_path_factory.mktemp("fake_lib")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    oracle_dir = os.path.join(ROOT, "oracle")
+    subprocess.run([cxx, "-O1", "-std=c++17", "-Wall", "-fPIC", "-shared", "-pthread", "-o", str(d / "libag2_b200.so"),
+                    os.path.join(HERE, "host", "fake_ag2_lib.cpp"), "-L" + oracle_dir, "-lag2_oracle", "-Wl,-rpath," + oracle_dir], check=True)
+    (d / "bin").mkdir()
+    shutil.copy2(exe, d / "bin" / "mecat2ref")
+    return str(d / "bin" / "mecat2ref")
+
+
+@pytest.mark.parametrize("devices", [1, 3, 7])
+def test_host_flow_with_test_double(staged, tmp_path, devices):
+    gold = golden_ref_outputs()
+    _inputs(tmp_path)
+    env = {k: v for k, v in os.environ.items() if k not in ("AG2_DEVICES", "AG2_SKIP_MAP", "LD_LIBRARY_PATH")}
+    r = subprocess.run([staged] + ARGS, cwd=tmp_path, env=dict(env, FAKE_AG2_DEVICES=str(devices)), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    _check_outputs(tmp_path, gold, thread_file=True)
