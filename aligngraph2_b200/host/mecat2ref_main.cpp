@@ -674,8 +674,15 @@ int main(int argc, char **argv)
         return 1;
     }
     const std::string wrk = o.wrk_dir;
+    const bool trace = getenv("AG2_TRACE") != nullptr;   // host timeline on stderr
+    double t_stage = now_sec();
+    auto stage_done = [&](const char *what) {
+        if (trace) fprintf(stderr, "[mecat2ref host] %-28s %8.3f s\n", what, now_sec() - t_stage);
+        t_stage = now_sec();
+    };
     const int readcount = convert_to_fq(o.reads, wrk + "/0.fq");
     const int refcount = convert_to_fq(o.reference, wrk + "/ref.fq");
+    stage_done("inputs -> 0.fq, ref.fq");
     {
         FILE *cfg = fopen("config.txt", "w");
         if (!cfg) { fprintf(stderr, "failed to open config.txt for writing\n"); return 1; }
@@ -689,8 +696,10 @@ int main(int argc, char **argv)
         const double t0 = now_sec();
         load_reference(o.reference, wrk, ref_seq);
         const double t_load = now_sec() - t0;
+        stage_done("reference, chrindex.txt");
         if (!getenv("AG2_SKIP_MAP")) map_on_gpu(o, ref_seq, secs);
         secs[1] += t_load;
+        stage_done("mapping (read, map, 1.r)");
     }
     {
         FILE *cfg = fopen("config.txt", "a");
@@ -701,7 +710,9 @@ int main(int argc, char **argv)
     }
     const std::vector<ChrInfo> chr = read_chrindex(wrk);
     result_combine(o, chr, argc, argv);
+    stage_done("result_combine (-o)");
     polish_result(o, chr, argc, argv);
+    stage_done("polish_result (-p)");
     {
         FILE *cfg = fopen("config.txt", "a");
         fprintf(cfg, "The total Time : %f sec\n", now_sec() - t_start);
