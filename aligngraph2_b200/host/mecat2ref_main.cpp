@@ -15,6 +15,8 @@
 //     filtered" rule (:854), which groups escape the filter -- with one thread file that is deterministic.
 //   * the reads of every load_fastq batch are sharded over all visible GPUs (AG2_DEVICES names another set), one host
 //     thread per GPU, records written in device order = read order: the files do not depend on the number of GPUs.
+//   * the next load_fastq batch is parsed on a second thread while the current one is mapped and printed, and
+//     result_combine / polish_result run side by side (separate output files): same bytes, less waiting on text.
 //   * -x is parsed and ignored, as in the reference.
 //   * no CPU fallback: without a usable GPU the program exits 1 (AlignGraph2.py:280-296 then falls back to the
 //     vanilla mecat2ref exactly as it does for any mecat2ref+ failure).
@@ -576,15 +578,19 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
 
     char *line = nullptr;
     size_t cap = 0;
-    bool first_batch = true, more = true;
-    secs[0] = secs[2] = 0;
-    while (more) {
-        // load_fastq (:1965-1991): up to SVM reads / MAXSTR characters, plus the record that ended the loop
+    // load_fastq (:1965-1991): up to SVM reads / MAXSTR characters, plus the record that ended the loop
+    struct Batch {
         std::string bases;
-        std::vector<int64_t> offs(1, 0);
+        std::vector<int64_t> offs;
         std::vector<int> ids;
+        bool more = false;
+    };
+    auto load_fastq = [&](Batch &b) {
+        b.bases.clear();
+        b.offs.assign(1, 0);
+        b.ids.clear();
+        b.more = false;
         long sum = 0;
-        more = false;
         for (;;) {
             const ssize_t n = getline(&line, &cap, fq);
             if (n < 0) break;
@@ -593,17 +599,35 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
             if (sscanf(line, "%d\t%d\t%n", &readno, &readlen, &consumed) < 2) continue;
             size_t len = (size_t)n - (size_t)consumed;
             while (len && (line[consumed + len - 1] == '\n' || line[consumed + len - 1] == '\r')) --len;
-            const bool within = (int)ids.size() < kSVM && sum < kMAXSTR;
-            bases.append(line + consumed, len);
-            offs.push_back((int64_t)bases.size());
-            ids.push_back(readno);
+            const bool within = (int)b.ids.size() < kSVM && sum < kMAXSTR;
+            b.bases.append(line + consumed, len);
+            b.offs.push_back((int64_t)b.bases.size());
+            b.ids.push_back(readno);
             sum += (long)len + 1;
             if (!within) {
-                more = true;
+                b.more = true;
                 break;
             }
         }
-        if (ids.empty()) break;
+    };
+    // two batches in flight: while the GPUs map one and its records are printed, a second thread parses the next
+    Batch batches[2];
+    int cur_i = 0;
+    load_fastq(batches[0]);
+    bool first_batch = true;
+    secs[0] = secs[2] = 0;
+    for (;;) {
+        Batch &cur = batches[cur_i];
+        if (cur.ids.empty()) break;
+        std::thread ahead;
+        if (cur.more) ahead = std::thread([&load_fastq, &batches, cur_i] { load_fastq(batches[cur_i ^ 1]); });
+        struct JoinAhead {   // on every way out of this round, the exits of die_ag2 aside
+            std::thread &t;
+            ~JoinAhead() { if (t.joinable()) t.join(); }
+        } join_ahead{ahead};
+        const std::string &bases = cur.bases;
+        const std::vector<int64_t> &offs = cur.offs;
+        const std::vector<int> &ids = cur.ids;
         const int64_t n_reads = (int64_t)ids.size();
         t0 = now_sec();
         if (first_batch) {
@@ -655,6 +679,8 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
                 fwrite(d.saln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
                 fputc('\n', out);
             }
+        if (!cur.more) break;
+        cur_i ^= 1;   // the batch read ahead (join_ahead waits for it before the next round starts)
     }
     free(line);
     fclose(fq);
@@ -709,10 +735,19 @@ int main(int argc, char **argv)
         fclose(cfg);
     }
     const std::vector<ChrInfo> chr = read_chrindex(wrk);
-    result_combine(o, chr, argc, argv);
-    stage_done("result_combine (-o)");
-    polish_result(o, chr, argc, argv);
-    stage_done("polish_result (-p)");
+    // the two passes over the thread files are independent (own output file, no shared state): side by side, unless -o and
+    // -p name the same file, which the reference would write one after the other
+    if (strcmp(o.output, o.refoutput) != 0) {
+        std::thread combine([&] { result_combine(o, chr, argc, argv); });
+        polish_result(o, chr, argc, argv);
+        combine.join();
+        stage_done("result_combine + polish_result");
+    } else {
+        result_combine(o, chr, argc, argv);
+        stage_done("result_combine (-o)");
+        polish_result(o, chr, argc, argv);
+        stage_done("polish_result (-p)");
+    }
     {
         FILE *cfg = fopen("config.txt", "a");
         fprintf(cfg, "The total Time : %f sec\n", now_sec() - t_start);
