@@ -298,6 +298,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: aligngraph2_b200 has no CPU path")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's own log lines (its version banner) off stdout: one JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
