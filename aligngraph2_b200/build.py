@@ -10,7 +10,7 @@ SO = os.path.join(PKG, "libag2_b200.so")
 SOURCES = [os.path.join(PKG, "csrc", "ag2_b200.cu"), os.path.join(PKG, "csrc", "pagraph.cu"), os.path.join(PKG, "host", "pg_job.cpp"),
            os.path.join(PKG, "host", "pg_travel.cpp")]
 HEADERS = [os.path.join(PKG, "csrc", n) for n in ("xdrop_device.cuh", "xdrop_lane.cuh", "seed_device.cuh", "index_kernels.cuh",
-                                                   "rescue_device.cuh", "map_kernels.cuh", "kmer_kernels.cuh", "pagraph_kernels.cuh", "xdrop_pair.cuh", "h2ops.cuh")] + [
+                                                   "rescue_device.cuh", "seed_cta.cuh", "plan_cta.cuh", "map_kernels.cuh", "kmer_kernels.cuh", "pagraph_kernels.cuh", "xdrop_pair.cuh", "h2ops.cuh")] + [
     os.path.join(ROOT, "include", "ag2_b200.h"), os.path.join(ROOT, "include", "ag2_pagraph.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -397,6 +397,9 @@ struct ag2_ctx {
     bool ref_indexed = false, votes_ready = false;
     int64_t read_prefix_len = 0;       // bytes of the concatenated reads that enter the read index (A2)
     DevBuf seed_need, seed_prefix, seed_scratch, seed_cands, seed_ncand;
+    DevBuf seed_ctl, seed_ovf1, seed_ovf2, seed_pool, plan_list;   // CTA-per-read seeding / rescue planning: control words, overflow lists, heavy-block pool
+    ag2_map_stats map_stats = {};
+    unsigned seed_overflow[2] = {0, 0};   // items the last seeding stage passed on to the second CTA launch / to the thread path
     // ag2_kmer_* (PAGraph kmer_counter)
     DevBuf km_table, km_hist, km_flags, km_offs, km_out;
     int km_k = 0;
@@ -624,7 +627,7 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     DevBuf *all[] = {&ctx->ref_irr, &ctx->ref_ascii, &ctx->ref_offs, &ctx->ix_rcnt, &ctx->ix_cnt, &ctx->ix_off, &ctx->ix_pos,
                      &ctx->ix_fill, &ctx->ix_tiles, &ctx->ix_kcount, &ctx->ix_vote, &ctx->seed_need, &ctx->seed_prefix,
-                     &ctx->seed_scratch, &ctx->seed_cands, &ctx->seed_ncand, &ctx->rec_pool, &ctx->map_cand, &ctx->map_cand_prefix,
+                     &ctx->seed_scratch, &ctx->seed_cands, &ctx->seed_ncand, &ctx->seed_ctl, &ctx->seed_ovf1, &ctx->seed_ovf2, &ctx->seed_pool, &ctx->plan_list, &ctx->rec_pool, &ctx->map_cand, &ctx->map_cand_prefix,
                      &ctx->map_plans, &ctx->map_rescue_n, &ctx->map_rescue_prefix, &ctx->map_out_refs, &ctx->map_nout, &ctx->map_flags,
                      &ctx->map_list, &ctx->map_out_prefix, &ctx->map_out_rec, &ctx->km_table, &ctx->km_hist, &ctx->km_flags, &ctx->km_offs,
                      &ctx->km_out, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
@@ -1673,6 +1676,141 @@ static size_t seed_limit(ag2_ctx *ctx)
     return std::min<size_t>((size_t)48 << 30, std::max<size_t>((size_t)4 << 30, third));
 }
 
+// Control words of the seeding / rescue-planning stage (device): work counters and overflow list lengths.
+struct SeedCtl {
+    unsigned next1, ovf1, next2, ovf2;            // seeding: CTA launch 1, its overflow, CTA launch 2, its overflow
+    unsigned plan_n, pnext1, povf1, pnext2, povf2; // planning: listed items, then as above
+    unsigned pad[7];
+};
+
+constexpr int kSeedCapMax = 14208;   // events per strand that fit the 227 KB of shared memory of one CTA
+
+// Events per strand the first CTA launch is sized for: seeds x (index positions per bucket + share of exact seeds of a
+// 15 %-error read), with a margin; what exceeds it goes to the second launch (kSeedCapMax), then to the thread path.
+static int seed_cap(const ag2_ctx *ctx, int pass, int tier)
+{
+    if (tier == 0)
+        if (const char *e = getenv("AG2_SEED_CAP")) return std::max(64, std::min(kSeedCapMax, atoi(e) & ~63));   // test knob
+    if (tier == 1) {
+        if (const char *e = getenv("AG2_SEED_CAP2")) return std::max(64, std::min(kSeedCapMax, atoi(e) & ~63));
+        return kSeedCapMax;
+    }
+    const double mean_len = ctx->n_reads ? (double)ctx->read_bases / (double)ctx->n_reads : 10000.0;
+    const double bc = pass == 0 ? std::min(20.0, 5.0 + mean_len / 1000.0) : 5.0;
+    const double density = (double)ctx->ix_npos / (double)kNCodes;
+    const double ev = (mean_len / bc + 1.0) * (density + 0.2);
+    const int cap = ((int)(ev * 1.3) + 128 + 255) & ~255;
+    return std::max(256, std::min(kSeedCapMax, cap));
+}
+
+static int seed_cta_config(ag2_ctx *ctx, const void *kernel, int cap, size_t *smem_out, int *grid_out)
+{
+    const size_t smem = seed_cta_smem_bytes(cap);
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSeedCtaThreads, smem));
+    if (occ < 1) return fail(ctx, AG2_ECUDA, "seeding kernel does not fit an SM (cap %d)", cap);
+    *smem_out = smem;
+    *grid_out = ctx->sm_count * occ;
+    return AG2_OK;
+}
+
+// Scratch layout of a one-thread-per-read launch over work[0..n_work): per-entry table bytes -> prefix (host) -> chunks
+// that fit the scratch limit.  Rare path: only what overflowed both CTA launches comes here.
+static int thread_path_scratch(ag2_ctx *ctx, const RefIndex &ix, int pass, const int32_t *d_reads, const int32_t *d_work, int64_t n_work,
+                               std::vector<std::pair<int64_t, int64_t>> &chunks)
+{
+    cudaStream_t st = ctx->stream;
+    const PackedSeqs sq = seqs_of(ctx);
+    RESERVE(ctx->seed_need, (size_t)n_work * 8);
+    RESERVE(ctx->seed_prefix, (size_t)(n_work + 1) * 8);
+    seed_need_sub_kernel<<<grid_for(n_work, 128, ctx->sm_count), 128, 0, st>>>(ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads,
+                                                                            d_work, n_work, pass, (int64_t *)ctx->seed_need.p);
+    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->seed_need.p, n_work, (int64_t *)ctx->seed_prefix.p);
+    CK(cudaGetLastError());
+    std::vector<int64_t> pf((size_t)n_work + 1);
+    CK(cudaMemcpyAsync(pf.data(), ctx->seed_prefix.p, (size_t)(n_work + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    size_t max_chunk = 0;
+    const size_t scratch_limit = seed_limit(ctx);
+    chunks.clear();
+    for (int64_t lo = 0; lo < n_work;) {
+        int64_t hi = lo + 1;
+        while (hi < n_work && (size_t)(pf[hi + 1] - pf[lo]) <= scratch_limit) ++hi;
+        chunks.push_back({lo, hi});
+        max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
+        lo = hi;
+    }
+    RESERVE(ctx->seed_scratch, max_chunk + 64);
+    return AG2_OK;
+}
+
+// Seeding + candidate scoring (A5-A7) of n items (item k = read d_reads[k], or read k): candidates into seed_cands /
+// seed_ncand.  Two CTA-per-read launches (the second takes the first one's overflow list straight from device memory),
+// then one small read-back that says whether anything is left for the thread path.
+static int seed_stage(ag2_ctx *ctx, int pass, int maxc, const int32_t *d_reads, int64_t n)
+{
+    cudaStream_t st = ctx->stream;
+    const PackedSeqs sq = seqs_of(ctx);
+    RefIndex ix = {ctx->ref_len, (const int32_t *)ctx->ix_cnt.p, (const uint32_t *)ctx->ix_off.p, (const uint32_t *)ctx->ix_pos.p,
+                   (const float *)ctx->ix_vote.p, ctx->ix_cbl};
+    RESERVE(ctx->seed_cands, (size_t)n * maxc * sizeof(SeedCand));
+    RESERVE(ctx->seed_ncand, (size_t)n * 4);
+    RESERVE(ctx->seed_ctl, sizeof(SeedCtl));
+    RESERVE(ctx->seed_ovf1, (size_t)n * 4);
+    RESERVE(ctx->seed_ovf2, (size_t)n * 4);
+    SeedCtl *ctl = (SeedCtl *)ctx->seed_ctl.p;
+    CK(cudaMemsetAsync(ctl, 0, sizeof(SeedCtl), st));
+    const int caps[2] = {seed_cap(ctx, pass, 0), seed_cap(ctx, pass, 1)};
+    for (int tier = 0; tier < 2; ++tier) {
+        size_t smem = 0;
+        int grid = 0;
+        int rc = seed_cta_config(ctx, (const void *)seed_cta_kernel, caps[tier], &smem, &grid);
+        if (rc != AG2_OK) return rc;
+        if (tier == 0) grid = (int)std::min<int64_t>(grid, n);
+        RESERVE(ctx->seed_pool, (size_t)grid * (caps[tier] / (kSM + 1) + 1) * kHeavyWords * 4);
+        SeedCtaArgs a = {};
+        a.ix = ix;
+        a.reads2 = sq.reads2;
+        a.irr = sq.reads_irr;
+        a.read_off = sq.read_off;
+        a.read_len = sq.read_len;
+        a.reads = d_reads;
+        a.work = tier == 0 ? nullptr : (const int32_t *)ctx->seed_ovf1.p;
+        a.n_work_dev = tier == 0 ? nullptr : &ctl->ovf1;
+        a.n_work = (unsigned)n;
+        a.pass = pass;
+        a.maxc = maxc;
+        a.cap = caps[tier];
+        a.next = tier == 0 ? &ctl->next1 : &ctl->next2;
+        a.cands = (SeedCand *)ctx->seed_cands.p;
+        a.ncand = (int32_t *)ctx->seed_ncand.p;
+        a.ovf = (int32_t *)(tier == 0 ? ctx->seed_ovf1.p : ctx->seed_ovf2.p);
+        a.ovf_count = tier == 0 ? &ctl->ovf1 : &ctl->ovf2;
+        a.heavy_pool = (uint32_t *)ctx->seed_pool.p;
+        seed_cta_kernel<<<grid, kSeedCtaThreads, smem, st>>>(a);
+        CK(cudaGetLastError());
+    }
+    SeedCtl h;
+    CK(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->seed_overflow[0] = h.ovf1;
+    ctx->seed_overflow[1] = h.ovf2;
+    if (h.ovf2 > 0) {   // one thread per read, table in global memory
+        std::vector<std::pair<int64_t, int64_t>> chunks;
+        int rc = thread_path_scratch(ctx, ix, pass, d_reads, (const int32_t *)ctx->seed_ovf2.p, h.ovf2, chunks);
+        if (rc != AG2_OK) return rc;
+        for (auto &c : chunks) {
+            const int64_t cn = c.second - c.first;
+            seed_map_sub_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(
+                ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads, (const int32_t *)ctx->seed_ovf2.p, c.first, cn, pass, maxc,
+                (const int64_t *)ctx->seed_prefix.p, (uint8_t *)ctx->seed_scratch.p, (SeedCand *)ctx->seed_cands.p, (int32_t *)ctx->seed_ncand.p);
+        }
+        CK(cudaGetLastError());
+    }
+    return AG2_OK;
+}
+
 int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *out, int32_t *ncand_out)
 {
     static_assert(sizeof(ag2_seed_candidate) == sizeof(SeedCand), "ag2_seed_candidate layout");
@@ -1685,39 +1823,8 @@ int ag2_seed_candidates(ag2_ctx *ctx, int pass, int maxc, ag2_seed_candidate *ou
     }
     cudaStream_t st = ctx->stream;
     const int64_t n = ctx->n_reads;
-    RefIndex ix = {ctx->ref_len, (const int32_t *)ctx->ix_cnt.p, (const uint32_t *)ctx->ix_off.p, (const uint32_t *)ctx->ix_pos.p,
-                   (const float *)ctx->ix_vote.p, ctx->ix_cbl};
-    RESERVE(ctx->seed_need, (size_t)n * 8);
-    RESERVE(ctx->seed_prefix, (size_t)(n + 1) * 8);
-    RESERVE(ctx->seed_cands, (size_t)n * maxc * sizeof(SeedCand));
-    RESERVE(ctx->seed_ncand, (size_t)n * 4);
-    seed_need_kernel<<<grid_for(n, 128, ctx->sm_count), 128, 0, st>>>(ix, (const uint32_t *)ctx->reads2.p, (const uint32_t *)ctx->reads_irr.p,
-                                                                       (const int64_t *)ctx->read_off.p, (const int32_t *)ctx->read_len.p, n,
-                                                                       pass, (int64_t *)ctx->seed_need.p);
-    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->seed_need.p, n, (int64_t *)ctx->seed_prefix.p);
-    CK(cudaGetLastError());
-    std::vector<int64_t> pf((size_t)n + 1);
-    CK(cudaMemcpyAsync(pf.data(), ctx->seed_prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    size_t max_chunk = 0;
-    std::vector<std::pair<int64_t, int64_t>> chunks;
-    const size_t scratch_limit = seed_limit(ctx);
-    for (int64_t lo = 0; lo < n;) {
-        int64_t hi = lo + 1;
-        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= scratch_limit) ++hi;
-        chunks.push_back({lo, hi});
-        max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
-        lo = hi;
-    }
-    RESERVE(ctx->seed_scratch, max_chunk + 64);
-    for (auto &c : chunks) {
-        const int64_t cn = c.second - c.first;
-        seed_map_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(
-            ix, (const uint32_t *)ctx->reads2.p, (const uint32_t *)ctx->reads_irr.p, (const int64_t *)ctx->read_off.p,
-            (const int32_t *)ctx->read_len.p, c.first, cn, pass, maxc, (const int64_t *)ctx->seed_prefix.p, (uint8_t *)ctx->seed_scratch.p,
-            (SeedCand *)ctx->seed_cands.p, (int32_t *)ctx->seed_ncand.p);
-        CK(cudaGetLastError());
-    }
+    const int rc = seed_stage(ctx, pass, maxc, nullptr, n);
+    if (rc != AG2_OK) return rc;
     if (out) CK(cudaMemcpyAsync(out, ctx->seed_cands.p, (size_t)n * maxc * sizeof(SeedCand), cudaMemcpyDeviceToHost, st));
     if (ncand_out) CK(cudaMemcpyAsync(ncand_out, ctx->seed_ncand.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1768,36 +1875,21 @@ static int map_pass(ag2_ctx *ctx, int pass, int maxc, int num_output, const int3
     RefIndex ix = {ctx->ref_len, (const int32_t *)ctx->ix_cnt.p, (const uint32_t *)ctx->ix_off.p, (const uint32_t *)ctx->ix_pos.p,
                    (const float *)ctx->ix_vote.p, ctx->ix_cbl};
     const int g = grid_for(n, 128, ctx->sm_count);
+    ag2_map_stats &ms = ctx->map_stats;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](double &acc) {   // host wall time since the last lap; every stage below ends at a host synchronisation
+        const auto t = std::chrono::steady_clock::now();
+        acc += std::chrono::duration<double, std::milli>(t - t_prev).count();
+        t_prev = t;
+    };
     // seeding + candidates
-    RESERVE(ctx->seed_need, (size_t)n * 8);
-    RESERVE(ctx->seed_prefix, (size_t)(n + 1) * 8);
-    RESERVE(ctx->seed_cands, (size_t)n * maxc * sizeof(SeedCand));
-    RESERVE(ctx->seed_ncand, (size_t)n * 4);
-    seed_need_sub_kernel<<<g, 128, 0, st>>>(ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads, n, pass, (int64_t *)ctx->seed_need.p);
-    exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->seed_need.p, n, (int64_t *)ctx->seed_prefix.p);
-    CK(cudaGetLastError());
-    std::vector<int64_t> pf((size_t)n + 1);
-    CK(cudaMemcpyAsync(pf.data(), ctx->seed_prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    size_t max_chunk = 0;
-    std::vector<std::pair<int64_t, int64_t>> chunks;
-    const size_t scratch_limit = seed_limit(ctx);
-    for (int64_t lo = 0; lo < n;) {
-        int64_t hi = lo + 1;
-        while (hi < n && (size_t)(pf[hi + 1] - pf[lo]) <= scratch_limit) ++hi;
-        chunks.push_back({lo, hi});
-        max_chunk = std::max(max_chunk, (size_t)(pf[hi] - pf[lo]));
-        lo = hi;
+    {
+        const int rc = seed_stage(ctx, pass, maxc, d_reads, n);
+        if (rc != AG2_OK) return rc;
+        ms.seed_overflow1 += ctx->seed_overflow[0];
+        ms.seed_overflow2 += ctx->seed_overflow[1];
     }
-    RESERVE(ctx->seed_scratch, max_chunk + 64);
-    for (auto &c : chunks) {
-        const int64_t cn = c.second - c.first;
-        seed_map_sub_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads,
-                                                                              c.first, cn, pass, maxc, (const int64_t *)ctx->seed_prefix.p,
-                                                                              (uint8_t *)ctx->seed_scratch.p, (SeedCand *)ctx->seed_cands.p,
-                                                                              (int32_t *)ctx->seed_ncand.p);
-    }
-    CK(cudaGetLastError());
+    lap(pass == 0 ? ms.seed_ms : ms.pass2_ms);
     // candidates of all reads, in order
     RESERVE(ctx->map_cand_prefix, (size_t)(n + 1) * 8);
     RESERVE(ctx->map_rescue_n, (size_t)n * 8);
@@ -1822,22 +1914,70 @@ static int map_pass(ag2_ctx *ctx, int pass, int maxc, int num_output, const int3
         if (rc != AG2_OK) return rc;
     }
     *pool_n = base0 + n_cand;
-    // rescue planning (same scratch layout as the seeding)
+    ms.n_candidates += n_cand;
+    lap(pass == 0 ? ms.extend_ms : ms.pass2_ms);
+    // rescue planning: the alignment lists of all items, then the seeding tables of the few that look clipped
     RESERVE(ctx->map_plans, (size_t)n * sizeof(ReadPlan));
     RESERVE(ctx->map_rescue_prefix, (size_t)(n + 1) * 8);
-    for (auto &c : chunks) {
-        const int64_t cn = c.second - c.first;
-        plan_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads, c.first, cn,
-                                                                      pass, (const int32_t *)ctx->seed_ncand.p,
-                                                                      (const int64_t *)ctx->map_cand_prefix.p, (const Record *)ctx->rec_pool.p,
-                                                                      base0, (const int64_t *)ctx->seed_prefix.p, (uint8_t *)ctx->seed_scratch.p,
-                                                                      (ReadPlan *)ctx->map_plans.p, (int64_t *)ctx->map_rescue_n.p);
+    RESERVE(ctx->plan_list, (size_t)n * 4);
+    SeedCtl *ctl = (SeedCtl *)ctx->seed_ctl.p;
+    plan_alns_kernel<<<g, 128, 0, st>>>(sq.read_len, d_reads, n, (const int32_t *)ctx->seed_ncand.p, (const int64_t *)ctx->map_cand_prefix.p,
+                                        (const Record *)ctx->rec_pool.p, base0, (ReadPlan *)ctx->map_plans.p, (int64_t *)ctx->map_rescue_n.p,
+                                        (int32_t *)ctx->plan_list.p, &ctl->plan_n);
+    CK(cudaGetLastError());
+    {
+        const int caps[2] = {seed_cap(ctx, pass, 0), seed_cap(ctx, pass, 1)};
+        for (int tier = 0; tier < 2; ++tier) {
+            size_t smem = 0;
+            int grid = 0;
+            int rc = seed_cta_config(ctx, (const void *)plan_cta_kernel, caps[tier], &smem, &grid);
+            if (rc != AG2_OK) return rc;
+            if (tier == 0) grid = (int)std::min<int64_t>(grid, n);
+            RESERVE(ctx->seed_pool, (size_t)grid * (caps[tier] / (kSM + 1) + 1) * kHeavyWords * 4);
+            PlanCtaArgs a = {};
+            a.ix = ix;
+            a.reads2 = sq.reads2;
+            a.irr = sq.reads_irr;
+            a.read_off = sq.read_off;
+            a.read_len = sq.read_len;
+            a.reads = d_reads;
+            a.work = (const int32_t *)(tier == 0 ? ctx->plan_list.p : ctx->seed_ovf1.p);
+            a.n_work_dev = tier == 0 ? &ctl->plan_n : &ctl->povf1;
+            a.pass = pass;
+            a.cap = caps[tier];
+            a.next = tier == 0 ? &ctl->pnext1 : &ctl->pnext2;
+            a.plans = (ReadPlan *)ctx->map_plans.p;
+            a.n_rescue = (int64_t *)ctx->map_rescue_n.p;
+            a.ovf = (int32_t *)(tier == 0 ? ctx->seed_ovf1.p : ctx->seed_ovf2.p);
+            a.ovf_count = tier == 0 ? &ctl->povf1 : &ctl->povf2;
+            a.heavy_pool = (uint32_t *)ctx->seed_pool.p;
+            plan_cta_kernel<<<grid, kSeedCtaThreads, smem, st>>>(a);
+            CK(cudaGetLastError());
+        }
+        SeedCtl h;
+        CK(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h.povf2 > 0) {
+            std::vector<std::pair<int64_t, int64_t>> chunks;
+            int rc = thread_path_scratch(ctx, ix, pass, d_reads, (const int32_t *)ctx->seed_ovf2.p, h.povf2, chunks);
+            if (rc != AG2_OK) return rc;
+            for (auto &c : chunks) {
+                const int64_t cn = c.second - c.first;
+                plan_search_sub_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(
+                    ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads, (const int32_t *)ctx->seed_ovf2.p, c.first, cn, pass,
+                    (const int64_t *)ctx->seed_prefix.p, (uint8_t *)ctx->seed_scratch.p, (ReadPlan *)ctx->map_plans.p,
+                    (int64_t *)ctx->map_rescue_n.p);
+            }
+            CK(cudaGetLastError());
+        }
     }
     exclusive_scan_i64<<<1, 1024, 0, st>>>((const int64_t *)ctx->map_rescue_n.p, n, (int64_t *)ctx->map_rescue_prefix.p);
     CK(cudaGetLastError());
     int64_t n_resc = 0;
     CK(cudaMemcpyAsync(&n_resc, (int64_t *)ctx->map_rescue_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    ms.n_rescue += n_resc;
+    lap(pass == 0 ? ms.plan_ms : ms.pass2_ms);
     const int64_t base1 = *pool_n;
     if (n_resc > 0) {
         int rk = reserve_keep(ctx, ctx->rec_pool, (size_t)(base1 + n_resc + 1) * sizeof(Record), (size_t)base1 * sizeof(Record));
@@ -1855,6 +1995,8 @@ static int map_pass(ag2_ctx *ctx, int pass, int maxc, int num_output, const int3
                                      (const Record *)ctx->rec_pool.p, base1, num_output, (int64_t *)ctx->map_out_refs.p,
                                      (int32_t *)ctx->map_nout.p, pass == 0 ? (int32_t *)ctx->map_flags.p : nullptr);
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    lap(pass == 0 ? ms.rescue_ms : ms.pass2_ms);
     return AG2_OK;
 }
 
@@ -1876,6 +2018,8 @@ int ag2_map_reads(ag2_ctx *ctx, int maxc, int num_output, int64_t *n_records)
     RESERVE(ctx->map_list, (size_t)n * 4);
     RESERVE(ctx->map_out_prefix, (size_t)(n + 1) * 8);
     int64_t pool_n = 0, dense = 0;
+    ctx->map_stats = ag2_map_stats{};
+    const auto t_begin = std::chrono::steady_clock::now();
     int rc = map_pass(ctx, 0, maxc, num_output, nullptr, n, &pool_n, &dense, true);
     if (rc != AG2_OK) return rc;
     // second pass for the reads none of whose candidates extended (:1049)
@@ -1886,6 +2030,7 @@ int ag2_map_reads(ag2_ctx *ctx, int maxc, int num_output, int64_t *n_records)
     int64_t n2 = 0;
     CK(cudaMemcpyAsync(&n2, (int64_t *)ctx->map_out_prefix.p + n, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    ctx->map_stats.n_pass2_reads = n2;
     if (n2 > 0) {
         rc = map_pass(ctx, 1, maxc, num_output, (const int32_t *)ctx->map_list.p, n2, &pool_n, &dense, false);
         if (rc != AG2_OK) return rc;
@@ -1906,7 +2051,22 @@ int ag2_map_reads(ag2_ctx *ctx, int maxc, int num_output, int64_t *n_records)
     ctx->out_total = dense;
     ctx->mapped = true;
     ctx->stats.aligned = 0; // per-call totals of the extension batches are in cells / rows / blocks; aligned counts every extension
+    ctx->ran = true;
+    ctx->map_stats.n_reads = n;
+    ctx->map_stats.n_records = n_out;
+    ctx->map_stats.cells = ctx->stats.cells;
+    ctx->map_stats.pair_kernel_ms = ctx->stats.kernel_ms;
+    ctx->map_stats.launches = ctx->stats.launches;
+    ctx->map_stats.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     if (n_records) *n_records = n_out;
+    return AG2_OK;
+}
+
+int ag2_map_get_stats(ag2_ctx *ctx, ag2_map_stats *out)
+{
+    if (!ctx || !out) return AG2_EINVAL;
+    if (!ctx->mapped) return fail(ctx, AG2_ESTATE, "ag2_map_get_stats: call ag2_map_reads first");
+    *out = ctx->map_stats;
     return AG2_OK;
 }
 

@@ -240,33 +240,6 @@ __global__ void vote_kernel(const int32_t *kcount, int64_t nblk, const unsigned 
 }
 
 // ---- seeding stage (A5-A7) ----------------------------------------------------------------------
-__global__ void seed_need_kernel(RefIndex ix, const uint32_t *reads2, const uint32_t *irr, const int64_t *read_off,
-                                 const int32_t *read_len, int64_t n_reads, int pass, int64_t *need)
-{
-    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_reads; r += (int64_t)gridDim.x * blockDim.x) {
-        const int rlen = read_len[r];
-        const int BC = seed_stride(rlen, pass);
-        const int64_t a = table_bytes(count_hits(ix, reads2, irr, read_off[r], rlen, 0, BC));
-        const int64_t b = table_bytes(count_hits(ix, reads2, irr, read_off[r], rlen, 1, BC));
-        need[r] = a > b ? a : b;
-    }
-}
-
-__global__ void seed_map_kernel(RefIndex ix, const uint32_t *reads2, const uint32_t *irr, const int64_t *read_off,
-                                const int32_t *read_len, int64_t first, int64_t n, int pass, int maxc,
-                                const int64_t *need_prefix, uint8_t *scratch, SeedCand *cands, int32_t *ncand)
-{
-    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = first + k;
-        SeedCand local[kMaxCand + 1];
-        const int nc = map_read_candidates(ix, reads2, irr, read_off[r], read_len[r], pass, maxc,
-                                           scratch + (need_prefix[r] - need_prefix[first]), local);
-        ncand[r] = nc;
-        for (int i = 0; i < nc; ++i) cands[r * maxc + i] = local[i];
-    }
-}
-
-// every seed candidate of every read becomes one extension candidate, reads in order, canidate_loc[] order inside
 __global__ void seeds_to_candidates_kernel(const SeedCand *cands, const int32_t *ncand, const int64_t *prefix, int64_t n_reads,
                                            int maxc, Candidate *out)
 {

@@ -4,7 +4,7 @@
 // reads without any alignment) -> records in thread-file order.
 #pragma once
 
-#include "rescue_device.cuh"
+#include "plan_cta.cuh"
 
 namespace ag2 {
 
@@ -13,29 +13,39 @@ constexpr int kOutCap = 3 * kMaxAlns; // output_results writes at most 3 records
 // reads[k] (or k itself when reads == nullptr) is the read index of work item k
 __device__ __forceinline__ int64_t item_read(const int32_t *reads, int64_t k) { return reads ? reads[k] : k; }
 
-__global__ void seed_need_sub_kernel(RefIndex ix, const uint32_t *reads2, const uint32_t *irr, const int64_t *read_off,
-                                     const int32_t *read_len, const int32_t *reads, int64_t n, int pass, int64_t *need)
+// ---- seeding + candidate scoring: one CTA per read (seed_cta.cuh) ----
+__global__ void __launch_bounds__(kSeedCtaThreads) seed_cta_kernel(SeedCtaArgs a)
 {
-    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = item_read(reads, k);
+    extern __shared__ __align__(16) uint8_t seed_smem[];
+    seed_cta_body(a, seed_smem);
+}
+
+// ---- the same on the one-thread-per-read path (seed_device.cuh), for the items the CTA path reported as overflow ----
+// work[w] is the item of work entry w; need / need_prefix are indexed by w, the results by item
+__global__ void seed_need_sub_kernel(RefIndex ix, const uint32_t *reads2, const uint32_t *irr, const int64_t *read_off,
+                                     const int32_t *read_len, const int32_t *reads, const int32_t *work, int64_t n, int pass, int64_t *need)
+{
+    for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < n; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = item_read(reads, item_read(work, w));
         const int rlen = read_len[r];
         const int BC = seed_stride(rlen, pass);
         const int64_t a = table_bytes(count_hits(ix, reads2, irr, read_off[r], rlen, 0, BC));
         const int64_t b = table_bytes(count_hits(ix, reads2, irr, read_off[r], rlen, 1, BC));
-        need[k] = a > b ? a : b;
+        need[w] = a > b ? a : b;
     }
 }
 
 __global__ void seed_map_sub_kernel(RefIndex ix, const uint32_t *reads2, const uint32_t *irr, const int64_t *read_off,
-                                    const int32_t *read_len, const int32_t *reads, int64_t first, int64_t n, int pass, int maxc,
-                                    const int64_t *need_prefix, uint8_t *scratch, SeedCand *cands, int32_t *ncand)
+                                    const int32_t *read_len, const int32_t *reads, const int32_t *work, int64_t first, int64_t n, int pass,
+                                    int maxc, const int64_t *need_prefix, uint8_t *scratch, SeedCand *cands, int32_t *ncand)
 {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = first + q;
+        const int64_t w = first + q;
+        const int64_t k = item_read(work, w);
         const int64_t r = item_read(reads, k);
         SeedCand local[kMaxCand + 1];
         const int nc = map_read_candidates(ix, reads2, irr, read_off[r], read_len[r], pass, maxc,
-                                           scratch + (need_prefix[k] - need_prefix[first]), local);
+                                           scratch + (need_prefix[w] - need_prefix[first]), local);
         ncand[k] = nc;
         for (int i = 0; i < nc; ++i) cands[k * maxc + i] = local[i];
     }
@@ -59,17 +69,35 @@ __global__ void seeds_to_candidates_sub_kernel(const SeedCand *cands, const int3
     }
 }
 
-__global__ void plan_kernel(RefIndex ix, const uint32_t *reads2, const uint32_t *irr, const int64_t *read_off, const int32_t *read_len,
-                            const int32_t *reads, int64_t first, int64_t n, int pass, const int32_t *ncand, const int64_t *cand_prefix,
-                            const Record *pool, int64_t pool_base, const int64_t *need_prefix, uint8_t *scratch, ReadPlan *plans,
-                            int64_t *n_rescue)
+// rescue planning, first half (plan_alns): one thread per item; the items that need the seeding table go to `list`
+__global__ void plan_alns_kernel(const int32_t *read_len, const int32_t *reads, int64_t n, const int32_t *ncand, const int64_t *cand_prefix,
+                                 const Record *pool, int64_t pool_base, ReadPlan *plans, int64_t *n_rescue, int32_t *list, unsigned *list_count)
 {
-    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t k = first + q;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = item_read(reads, k);
         const int64_t rec_base = pool_base + cand_prefix[k];
-        plan_read(ix, reads2, irr, read_off[r], read_len[r], pass, pool + rec_base, ncand[k], rec_base,
-                  scratch + (need_prefix[k] - need_prefix[first]), plans[k]);
+        n_rescue[k] = 0;
+        if (plan_alns(pool + rec_base, ncand[k], rec_base, read_len[r], plans[k])) list[atomicAdd(list_count, 1u)] = (int32_t)k;
+    }
+}
+
+// second half, one CTA per listed item (plan_cta.cuh)
+__global__ void __launch_bounds__(kSeedCtaThreads) plan_cta_kernel(PlanCtaArgs a)
+{
+    extern __shared__ __align__(16) uint8_t seed_smem[];
+    plan_cta_body(a, seed_smem);
+}
+
+// second half on the one-thread-per-read path, for the items the CTA path reported as overflow
+__global__ void plan_search_sub_kernel(RefIndex ix, const uint32_t *reads2, const uint32_t *irr, const int64_t *read_off, const int32_t *read_len,
+                                       const int32_t *reads, const int32_t *work, int64_t first, int64_t n, int pass,
+                                       const int64_t *need_prefix, uint8_t *scratch, ReadPlan *plans, int64_t *n_rescue)
+{
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = first + q;
+        const int64_t k = work[w];
+        const int64_t r = item_read(reads, k);
+        plan_search(ix, reads2, irr, read_off[r], read_len[r], pass, scratch + (need_prefix[w] - need_prefix[first]), plans[k]);
         n_rescue[k] = plans[k].n_rescue;
     }
 }

@@ -86,7 +86,7 @@ __device__ __forceinline__ bool right_clipped(const AlnInfo &a, const AlnInfo &b
 __device__ int find_location2(const int *t_loc, const int *t_seedn, int *t_score, int64_t *loc, int k, int *rep_loc, float len,
                               int read_len1)
 {
-    int i, j, maxval = 0, maxi = 0, rep = 0, lasti = 0;
+    int i, j;
     for (i = 0; i < k; i++) t_score[i] = 0;
     for (i = 0; i < k - 1; i++)
         for (j = i + 1; j < k; j++)
@@ -95,59 +95,7 @@ __device__ int find_location2(const int *t_loc, const int *t_seedn, int *t_score
                 t_score[i]++;
                 t_score[j]++;
             }
-    for (i = 0; i < k; i++) {
-        if (maxval < t_score[i]) {
-            maxval = t_score[i];
-            maxi = i;
-            rep = 0;
-        } else if (maxval == t_score[i]) {
-            rep++;
-            lasti = i;
-        }
-    }
-    for (i = 0; i < 4; i++) loc[i] = 0;
-    if (maxval >= 5 && rep == maxval) {
-        loc[0] = t_loc[maxi], loc[1] = t_seedn[maxi];
-        *rep_loc = maxi;
-        loc[2] = t_loc[lasti], loc[3] = t_seedn[lasti];
-        return 1;
-    } else if (maxval >= 5 && rep != maxval) {
-        for (j = 0; j < maxi; j++)
-            if (t_seedn[maxi] - t_seedn[j] > 0 && t_loc[maxi] - t_loc[j] > 0 && t_loc[maxi] - t_loc[j] < read_len1 &&
-                ddf_ok_f(t_loc[maxi] - t_loc[j], t_seedn[maxi] - t_seedn[j], len)) {
-                if (loc[0] == 0) {
-                    loc[0] = t_loc[j];
-                    loc[1] = t_seedn[j];
-                    *rep_loc = j;
-                } else {
-                    loc[2] = t_loc[j];
-                    loc[3] = t_seedn[j];
-                }
-            }
-        j = maxi;
-        if (loc[0] == 0) {
-            loc[0] = t_loc[j];
-            loc[1] = t_seedn[j];
-            *rep_loc = j;
-        } else {
-            loc[2] = t_loc[j];
-            loc[3] = t_seedn[j];
-        }
-        for (j = maxi + 1; j < k; j++)
-            if (t_seedn[j] - t_seedn[maxi] > 0 && t_loc[j] - t_loc[maxi] > 0 && t_loc[j] - t_loc[maxi] <= read_len1 &&
-                ddf_ok_f(t_loc[j] - t_loc[maxi], t_seedn[j] - t_seedn[maxi], len)) {
-                if (loc[0] == 0) {
-                    loc[0] = t_loc[j];
-                    loc[1] = t_seedn[j];
-                    *rep_loc = j;
-                } else {
-                    loc[2] = t_loc[j];
-                    loc[3] = t_seedn[j];
-                }
-            }
-        return 1;
-    }
-    return 0;
+    return find_location_choose(t_loc, t_seedn, t_score, loc, k, rep_loc, len, read_len1);
 }
 
 // seeding only (impl_large.cpp:842-878): the strand's block table as rescue_clipped_align sees it
@@ -255,10 +203,10 @@ __device__ bool find_right_clipped(const AlnInfo &aln, RescueCand &can, const Bl
     return false;
 }
 
-// First half of rescue_clipped_align (:416-445 and the searches of :446-520).  recs: the records of this read's
-// seed candidates in canidate_loc[] order, rec_base their index in the record pool.
-__device__ void plan_read(const RefIndex &ix, const uint32_t *reads2, const uint32_t *irr, int64_t roff, int rlen, int pass,
-                          const Record *recs, int ncand, int64_t rec_base, uint8_t *scratch, ReadPlan &P)
+// First half of rescue_clipped_align (:416-445): the read's alignments sorted by span, contained ones dropped.  recs: the
+// records of this read's seed candidates in canidate_loc[] order, rec_base their index in the record pool.  Returns true
+// if the searches for clipped candidates (:446-520) are due: they need the strand's seeding table.
+__device__ bool plan_alns(const Record *recs, int ncand, int64_t rec_base, int rlen, ReadPlan &P)
 {
     P.naln = P.naln_ext = P.nres = P.n_rescue = 0;
     for (int s = 0; s < kMaxRescue; ++s) P.rescue[s].on = 0;
@@ -276,7 +224,7 @@ __device__ void plan_read(const RefIndex &ix, const uint32_t *reads2, const uint
         P.res_ref[P.nres++] = rec_base + c;
     }
     P.naln_ext = P.naln;
-    if (P.naln == 0) return;
+    if (P.naln == 0) return false;
     AlnInfo *alnv = P.alns;
     int naln = P.naln;
     sort_alns(alnv, naln);
@@ -292,13 +240,23 @@ __device__ void plan_read(const RefIndex &ix, const uint32_t *reads2, const uint
         if (alnv[i].valid) alnv[k++] = alnv[i];
     naln = k;
     P.naln = naln;
-    if (aln_full(alnv[0], rlen)) return;
+    return !aln_full(alnv[0], rlen);
     // (:430-444) links clipped pairs only when prev_id / next_id != -1, which is never the case here: no effect
-    const int n = naln < 3 ? naln : 3;
+}
+
+// The searches of rescue_clipped_align (:446-520) on the one-thread-per-read path: the strand's table is rebuilt in
+// `scratch` (global memory).  P as plan_alns left it.
+__device__ void plan_search(const RefIndex &ix, const uint32_t *reads2, const uint32_t *irr, int64_t roff, int rlen, int pass,
+                            uint8_t *scratch, ReadPlan &P)
+{
+    AlnInfo *alnv = P.alns;
+    const int n = P.naln < 3 ? P.naln : 3;
     const int BC = seed_stride(rlen, pass);
     const int64_t zv = pass == 0 ? 1000 : 2000;
     int have_strand = -1;
     BlockTable tb;
+    P.n_rescue = 0;
+    for (int s = 0; s < kMaxRescue; ++s) P.rescue[s].on = 0;
     for (int i = 0; i < n; ++i) {
         const int strand = alnv[i].qdir == 'F' ? 0 : 1;
         if (have_strand != strand) {
@@ -310,6 +268,12 @@ __device__ void plan_read(const RefIndex &ix, const uint32_t *reads2, const uint
         if (find_left_clipped(alnv[i], P.rescue[2 * i], tb, (int)zv, rlen, BC)) ++P.n_rescue;
         if (find_right_clipped(alnv[i], P.rescue[2 * i + 1], tb, (int)zv, rlen, ix.ref_len, BC)) ++P.n_rescue;
     }
+}
+
+__device__ void plan_read(const RefIndex &ix, const uint32_t *reads2, const uint32_t *irr, int64_t roff, int rlen, int pass,
+                          const Record *recs, int ncand, int64_t rec_base, uint8_t *scratch, ReadPlan &P)
+{
+    if (plan_alns(recs, ncand, rec_base, rlen, P)) plan_search(ix, reads2, irr, roff, rlen, pass, scratch, P);
 }
 
 // Second half of rescue_clipped_align (:446-537) + output_results (:541-559).  rrec[s]: the record of rescue slot

@@ -175,23 +175,12 @@ __device__ void insert_loc(const RefIndex &ix, BackList *spr, int loc, int seedn
     }
 }
 
-// find_location3 (:609-693)
-__device__ int find_location3(const RefIndex &ix, const int *t_loc, const int *t_seedn, int *t_score, int64_t *loc, int k,
-                              int *rep_loc, float len, int read_len1, int64_t start_loc)
+// Second half of find_location3 (:628-693) / find_location2: t_score holds the (vote-scaled) consistency counts; picks the
+// best seed, its first and last consistent partners.  Shared by the one-thread-per-read path and the CTA path.
+__device__ int find_location_choose(const int *t_loc, const int *t_seedn, const int *t_score, int64_t *loc, int k, int *rep_loc, float len,
+                                    int read_len1)
 {
     int i, j, maxval = 0, maxi = 0, rep = 0, lasti = 0;
-    for (i = 0; i < k; i++) t_score[i] = 0;
-    for (i = 0; i < k - 1; i++)
-        for (j = i + 1; j < k; j++)
-            if (t_seedn[j] - t_seedn[i] > 0 && t_loc[j] - t_loc[i] > 0 && t_loc[j] - t_loc[i] < read_len1 &&
-                ddf_ok_f(t_loc[j] - t_loc[i], t_seedn[j] - t_seedn[i], len)) {
-                t_score[i]++;
-                t_score[j]++;
-            }
-    for (i = 0; i < k; i++) {
-        const int64_t nn = (start_loc + t_loc[i]) / ix.cbl;
-        t_score[i] = (int)fdiv_rn((float)t_score[i], ix.vote[nn]);
-    }
     for (i = 0; i < k; i++) {
         if (maxval < t_score[i]) {
             maxval = t_score[i];
@@ -245,6 +234,26 @@ __device__ int find_location3(const RefIndex &ix, const int *t_loc, const int *t
         return 1;
     }
     return 0;
+}
+
+// find_location3 (:609-693)
+__device__ int find_location3(const RefIndex &ix, const int *t_loc, const int *t_seedn, int *t_score, int64_t *loc, int k,
+                              int *rep_loc, float len, int read_len1, int64_t start_loc)
+{
+    int i, j;
+    for (i = 0; i < k; i++) t_score[i] = 0;
+    for (i = 0; i < k - 1; i++)
+        for (j = i + 1; j < k; j++)
+            if (t_seedn[j] - t_seedn[i] > 0 && t_loc[j] - t_loc[i] > 0 && t_loc[j] - t_loc[i] < read_len1 &&
+                ddf_ok_f(t_loc[j] - t_loc[i], t_seedn[j] - t_seedn[i], len)) {
+                t_score[i]++;
+                t_score[j]++;
+            }
+    for (i = 0; i < k; i++) {
+        const int64_t nn = (start_loc + t_loc[i]) / ix.cbl;
+        t_score[i] = (int)fdiv_rn((float)t_score[i], ix.vote[nn]);
+    }
+    return find_location_choose(t_loc, t_seedn, t_score, loc, k, rep_loc, len, read_len1);
 }
 
 // One seed of a read strand: the 13-mer at oriented position `start` in atct code, or -1 if it holds a base

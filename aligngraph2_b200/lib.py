@@ -31,11 +31,17 @@ class ExtendStats(C.Structure):
                                         "interior", "launches")] + [("kernel_ms", C.c_double), ("lane_chains", C.c_int64)]
 
 
+class MapStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("total_ms", "seed_ms", "extend_ms", "plan_ms", "rescue_ms", "pass2_ms", "pair_kernel_ms")] + [
+        (n, C.c_int64) for n in ("n_reads", "n_records", "n_candidates", "n_rescue", "n_pass2_reads", "seed_overflow1", "seed_overflow2",
+                                 "cells", "launches")]
+
+
 EXPORTS = [
     "ag2_device_count", "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load", "ag2_reads_load_async", "ag2_reads_wait",
     "ag2_xdrop_extend_batch", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
     "ag2_ctx_stream", "ag2_index_build", "ag2_index_fetch", "ag2_seed_candidates",
-    "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch",
+    "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch", "ag2_map_get_stats",
     "ag2_kmer_begin", "ag2_kmer_add_reads", "ag2_kmer_solid", "ag2_kmer_fetch",
 ]
 
@@ -79,6 +85,7 @@ def load() -> C.CDLL:
     L.ag2_extend_upload_from_seeds.argtypes = [vp, i32, C.POINTER(i64)]
     L.ag2_map_reads.argtypes = [vp, i32, i32, C.POINTER(i64)]
     L.ag2_map_fetch.argtypes = [vp, vp, vp, vp, i64, C.POINTER(i64)]
+    L.ag2_map_get_stats.argtypes = [vp, C.POINTER(MapStats)]
     L.ag2_kmer_begin.argtypes = [vp, i32]
     L.ag2_kmer_add_reads.argtypes = [vp]
     L.ag2_kmer_solid.argtypes = [vp, C.c_double, C.POINTER(i64), C.POINTER(i64)]

@@ -17,7 +17,7 @@ from typing import Sequence
 import numpy as np
 
 from . import lib as _lib
-from .lib import CANDIDATE_DTYPE, NCODES, RECORD_DTYPE, SEED_CAND_DTYPE, Ag2Error, ExtendStats
+from .lib import CANDIDATE_DTYPE, NCODES, RECORD_DTYPE, SEED_CAND_DTYPE, Ag2Error, ExtendStats, MapStats
 
 
 def _as_bytes_array(x) -> np.ndarray:
@@ -153,6 +153,26 @@ class Mecat2RefDevice:
         self._check(self._L.ag2_map_fetch(self._ctx, rec.ctypes.data, qa.ctypes.data, sa.ctypes.data, qa.size, C.byref(used)),
                     "ag2_map_fetch")
         return rec, qa[:used.value], sa[:used.value]
+
+    def map_reads_only(self, maxc: int = 10, num_output: int = 1) -> int:
+        """ag2_map_reads without the fetch: results stay on the device; returns the number of records."""
+        n = C.c_int64()
+        self._check(self._L.ag2_map_reads(self._ctx, maxc, num_output, C.byref(n)), "ag2_map_reads")
+        return n.value
+
+    def map_fetch_into(self, rec: np.ndarray, qaln_out=None, saln_out=None) -> int:
+        """ag2_map_fetch into caller-owned (ideally pinned) buffers; returns the bytes used per string."""
+        used = C.c_int64()
+        q = qaln_out.ctypes.data if qaln_out is not None else None
+        t = saln_out.ctypes.data if saln_out is not None else None
+        cap = qaln_out.size if qaln_out is not None else 0
+        self._check(self._L.ag2_map_fetch(self._ctx, rec.ctypes.data, q, t, cap, C.byref(used)), "ag2_map_fetch")
+        return used.value
+
+    def map_stats(self) -> dict:
+        s = MapStats()
+        self._check(self._L.ag2_map_get_stats(self._ctx, C.byref(s)), "ag2_map_get_stats")
+        return {k: getattr(s, k) for k, _ in MapStats._fields_}
 
     @staticmethod
     def write_thread_file(path: str, rec, qaln, saln, read_ids) -> None:

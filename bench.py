@@ -56,6 +56,12 @@ def parse():
     ap.add_argument("--e2e-path", default="default", choices=["default", "chunked", "streamed"],
                     help="form of the host-buffer run (AG2_E2E_PATH of ag2_xdrop_extend_batch); default = the library's own choice")
     ap.add_argument("--e2e-sweep", default="", help="tuning: ';'-separated sets of NAME=VALUE,... library knobs, each timed like e2e and reported on stderr")
+    ap.add_argument("--full-reads", type=int, default=250_000, help="reads per GPU of the full-path arm (configs[2]: 2M reads over 8 GPUs); 0 = skip")
+    ap.add_argument("--full-ref-len", type=int, default=250_000_000)
+    ap.add_argument("--full-steps", type=int, default=5, help="timed steps of the full-path arm (at most --steps)")
+    ap.add_argument("--full-cpu-reads-per-core", type=int, default=1000,
+                    help="--impl reference: reads per host core of the full-path CPU arm (the reference hands out chunks of 1000 reads)")
+    ap.add_argument("--pagraph-cpu", action="store_true", help="also time the reference classes on the A-Bruijn stage input (minutes)")
     ap.add_argument("--pagraph-reads", type=int, default=4000, help="reads of the A-Bruijn build stage line (0 = skip)")
     ap.add_argument("--pagraph-k", type=int, default=14)
     return ap.parse_args()
@@ -207,6 +213,8 @@ def pagraph_stage(args, local: int):
         job.close()
         # the CPU beside it: the unmodified reference classes when built here, else the port; one core (-t 1 is the only
         # deterministic setting of the reference)
+        if not args.pagraph_cpu:
+            return out
         from oracle import binding
         t0 = time.perf_counter()
         if os.path.exists(binding.REF_PAGRAPH_DUMP):
@@ -222,6 +230,192 @@ def pagraph_stage(args, local: int):
         return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+FULL_REF_SEED = 20261017 + 250   # the full-path reference: the same on every rank (reads are sharded, the reference is not)
+
+
+def full_path_inputs(args, rank: int, device: str, n_reads: int):
+    """configs[2]: reads of this rank against the 250 Mb reference.  The reference comes from its own generator (the same on
+    every rank); the reads from (seed, rank)."""
+    import torch
+    from aligngraph2_b200 import synth
+    g = torch.Generator(device=device)
+    g.manual_seed(FULL_REF_SEED)
+    codes = torch.randint(0, 4, (args.full_ref_len,), generator=g, device=device, dtype=torch.uint8)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=device)
+    ref = acgt[codes.long()]
+    del codes
+    d = synth.make_batch_torch(args.seed + 2500 + 1000 * rank, args.full_ref_len, n_reads, args.tlen, device=device, ref=ref)
+    return d
+
+
+def full_path_arm(args, rank, world, local, barrier, peak, peak_src):
+    """BASELINE configs[2] per GPU: the WHOLE per-read path (seeding, candidate scoring, extension of every candidate,
+    rescue, second pass, output choice = ag2_map_reads) of `--full-reads` reads against a 250 Mb reference.
+    value = sum(qe - qb) of the RETURNED records / time, inputs resident; e2e = reads up from pinned host memory +
+    ag2_map_reads + records and both alignment strings down, per step.  The index build is one-off and reported apart."""
+    import torch
+    import torch.distributed as dist
+    from aligngraph2_b200.lib import RECORD_DTYPE
+    from aligngraph2_b200.mecat2ref import Mecat2RefDevice
+    n = args.full_reads
+    K = max(1, min(args.steps, args.full_steps))
+    W = 3
+    d = full_path_inputs(args, rank, "cuda", n)
+    h_ref = d["ref"].cpu().numpy()
+    h_bases = torch.empty(d["bases"].numel(), dtype=torch.uint8, pin_memory=True)
+    h_bases.copy_(d["bases"])
+    h_off = d["offsets"].cpu().numpy()
+    del d
+    torch.cuda.empty_cache()
+    bases_np = h_bases.numpy()
+    dev = Mecat2RefDevice(local)
+    stream = torch.cuda.ExternalStream(dev.stream)
+    t0 = time.perf_counter()
+    dev.load_reference(h_ref)
+    ref_load_ms = (time.perf_counter() - t0) * 1e3
+    dev.load_reads(bases=bases_np, offsets=h_off)
+    t0 = time.perf_counter()
+    dev.build_index(200, 0.5, 2.0)
+    torch.cuda.synchronize()
+    index_ms = (time.perf_counter() - t0) * 1e3
+    for _ in range(W):
+        n_rec = dev.map_reads_only(10, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    acc = {}
+    for _ in range(K):
+        n_rec = dev.map_reads_only(10, 1)
+        for k, v in dev.map_stats().items():
+            if k.endswith("_ms"):
+                acc[k] = acc.get(k, 0.0) + v / K
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    mst = dev.map_stats()
+    rec = torch.empty(max(1, n_rec) * RECORD_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
+    rec_np = rec.numpy().view(RECORD_DTYPE)[:n_rec]
+    used = dev.map_fetch_into(rec_np)
+    aligned = float((rec_np["qe"].astype(np.int64) - rec_np["qb"].astype(np.int64)).sum())
+    t = torch.tensor([ms, 0.0], device="cuda", dtype=torch.float64)
+    a = torch.tensor([aligned, float(mst["cells"]), float(mst["n_candidates"]), float(int(h_off[-1])), float(n_rec)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(a, op=dist.ReduceOp.SUM)
+    ms_max = float(t[0].item())
+    aligned_all, cells_all, cand_all, bases_all, rec_all = (float(x) for x in a.tolist())
+    value = aligned_all * K / (ms_max * 1e-3) / 1e9
+
+    # e2e: host buffers in, host buffers out
+    h_q = torch.empty(used + 4096, dtype=torch.uint8, pin_memory=True)
+    h_s = torch.empty(used + 4096, dtype=torch.uint8, pin_memory=True)
+
+    def step():
+        dev.load_reads(bases=bases_np, offsets=h_off)
+        nr = dev.map_reads_only(10, 1)
+        return nr, dev.map_fetch_into(rec.numpy().view(RECORD_DTYPE)[:nr], h_q.numpy(), h_s.numpy())
+    step()
+    barrier()
+    e0.record(stream)
+    for _ in range(K):
+        nr, used2 = step()
+    e1.record(stream)
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2.item())
+    r2 = rec.numpy().view(RECORD_DTYPE)[:nr]
+    aligned2 = torch.tensor([float((r2["qe"].astype(np.int64) - r2["qb"].astype(np.int64)).sum())], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(aligned2, op=dist.ReduceOp.SUM)
+    ix = dev.fetch_index() if rank == 0 else None
+    dev.close()
+    if rank != 0:
+        return None
+    # algorithmic bytes of one step (SURVEY 8d): extension 3 B per DP cell + 3.6 B per aligned base; seeding 0.25 B per read
+    # base + 8 B per seed (bucket offset + count) + 4 B per index hit + 48 B per candidate -- both strands are seeded
+    lens = np.diff(h_off)
+    bc = np.minimum(20, 5 + lens // 1000)
+    seeds = 2.0 * float((np.maximum(lens - 13, 0) // bc + 1).sum()) * world   # this rank's count x ranks (same length distribution)
+    hbar = float(len(ix["pos"])) / float(1 << 26)
+    b_seed = 0.25 * bases_all + 8.0 * seeds + 4.0 * seeds * hbar + 48.0 * cand_all
+    b_ext = 3.0 * cells_all + 3.6 * aligned_all
+    step_s = ms_max / K * 1e-3
+    achieved = (b_seed + b_ext) / step_s / 1e9 / world
+    return {"workload": f"BASELINE configs[2] per GPU: {n} synthetic CLR reads/GPU ({args.tlen} bp templates, 15% error) vs {args.full_ref_len} bp "
+                        f"uniform reference, whole per-read path (ag2_map_reads: seeding, candidate scoring, extension of every candidate, "
+                        f"rescue, second pass, output choice; -n 10 -b 1 -z 200)",
+            "metric": METRIC, "unit": UNIT, "value": value, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K,
+            "aligned_bases_per_step": aligned_all, "records_per_step": rec_all, "reads_per_gpu": n,
+            "aligned_from": "sum(qe - qb) over the records ag2_map_fetch returns",
+            "e2e": {"value": float(aligned2.item()) * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": int(int(h_off[-1]) + h_off.nbytes) * world,
+                    "d2h_bytes_per_step": int(nr * RECORD_DTYPE.itemsize + 2 * used2) * world,
+                    "path": "ag2_reads_load (ASCII, pinned) + ag2_map_reads + ag2_map_fetch (records + both strings, pinned)"},
+            "stage_ms_rank0": acc, "stage_counts_rank0": {k: v for k, v in mst.items() if not k.endswith("_ms")},
+            "one_off_ms_rank0": {"ref_load": ref_load_ms, "index_build": index_ms},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "whole ag2_map_reads step (xdrop_pair_kernel + seed_cta_kernel dominate)",
+                         "algorithmic_bytes_seed": b_seed, "algorithmic_bytes_extend": b_ext, "hits_per_seed": hbar,
+                         "formula": "per GPU: (0.25 B/read base + 8 B/seed + 4 B/hit + 48 B/candidate + 3 B/DP cell + 3.6 B/aligned base) / step time",
+                         "peak_source": peak_src}}
+
+
+def full_path_reference(args, cores: int):
+    """--impl reference, full path: the UNMODIFIED reference binary (oracle/_ref/mecat2ref -t <cores>) on a prefix of the rank-0
+    full-path workload; aligned Gbp/s = sum(qe - qb) of its -p records / its own "The Mapping Time" (index builds and the
+    fixed polish_result cost excluded)."""
+    import shutil
+    import tempfile
+    from aligngraph2_b200 import synth
+    from oracle import binding
+    exe = os.path.join(ROOT, "oracle", "_ref", "mecat2ref")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/mecat2ref was not built (needs /root/reference at build time)"}
+    import torch
+    n = max(cores, cores * args.full_cpu_reads_per_core)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    d = full_path_inputs(args, 0, dev, n)
+    ref = d["ref"].cpu().numpy()
+    bases, off = d["bases"].cpu().numpy(), d["offsets"].cpu().numpy()
+    del d
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 3 * (ref.size + 2 * bases.size) else None
+    tmp = tempfile.mkdtemp(prefix="ag2_fullref_", dir=base)
+    try:
+        synth.write_fasta(os.path.join(tmp, "ref.fa"), "chr1", ref)
+        with open(os.path.join(tmp, "reads.fq"), "wb") as f:
+            for i in range(n):
+                rd = bases[off[i]:off[i + 1]].tobytes()
+                f.write(b"@r%d\n" % i + rd + b"\n+\n" + b"I" * len(rd) + b"\n")
+        t0 = time.perf_counter()
+        subprocess.run([exe, "-t", str(cores), "-d", "reads.fq", "-r", "ref.fa", "-b", "1", "-w", "./wrk", "-o", "o.txt", "-p", "p.txt",
+                        "-l", "0.5", "-u", "2.0", "-z", "200", "-y", "0.9"], cwd=tmp, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        wall = time.perf_counter() - t0
+        times = {}
+        for ln in open(os.path.join(tmp, "config.txt")):
+            if "Time" in ln and ":" in ln:
+                k, v = ln.rsplit(":", 1)
+                try:
+                    times[k.strip()] = float(v.split()[0])
+                except ValueError:
+                    pass
+        aligned, recs = 0, 0
+        with open(os.path.join(tmp, "p.txt"), "rb") as f:
+            for i, ln in enumerate(f):
+                if i % 3 == 0:
+                    t = ln.split(b"\t")
+                    aligned += int(t[5]) - int(t[4])
+                    recs += 1
+        map_s = times.get("The Mapping Time", None)
+        return {"value": aligned / map_s / 1e9 if map_s else None, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"oracle/_ref/mecat2ref -t {cores} on the first {n} reads of rank 0's full-path workload vs the {args.full_ref_len} bp "
+                          f"reference: {aligned / 1e6:.1f} Mbp aligned in {recs} records, 'The Mapping Time' {map_s} s (process wall {wall:.1f} s)",
+                "config_txt_times_s": times, "extrapolation": f"rate of a {n}-read prefix; the {args.full_reads}-read job is {args.full_reads / n:.1f}x as long"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def cbar_guard(st) -> float:
@@ -267,6 +461,11 @@ def run_reference(args):
             "config": workload_config(args, sample=n_sample), "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.full_reads > 0:
+        try:
+            line["full_path"] = full_path_reference(args, cores)
+        except Exception as e:
+            line["full_path"] = {"unavailable": repr(e)}
     print(json.dumps(line))
 
 
@@ -448,7 +647,8 @@ def main():
                   "seed_candidates_ms": timed(lambda: dev.seed_candidates(0, 10))}
         t_map = timed(map_all)
         stages.update({"map_reads_ms": t_map, "map_reads_records": int(n_rec.value),
-                       "map_reads_gbp_per_s": float(dev.stats()["cells"]) / cbar_guard(st) / (t_map * 1e-3) / 1e9,
+                       "map_reads_gbp_per_s": float(dev.stats()["cells"]) / cbar_guard(st) / (t_map * 1e-3) / 1e9, "map_reads_gbp_per_s_estimated": True,
+                       "map_stats": dev.map_stats(),
                        "note": "same batch, resident inputs: ag2_index_build (A2-A4); ag2_seed_candidates (A5-A7, incl. the D2H of the "
                                "candidates); ag2_map_reads = the whole per-read path (seed, extend every candidate, rescue, second pass, "
                                "output choice; -n 10 -b 1), its Gbp/s estimated as DP cells / cells-per-aligned-base of the extend-only run"})
@@ -459,7 +659,7 @@ def main():
         except Exception as e:  # the headline line must still print
             stages["pagraph"] = {"error": repr(e)}
 
-    # ---- roofline of the dominant kernel (xdrop_lane_kernel) ----
+    # ---- roofline of the dominant kernel (xdrop_pair_kernel) ----
     peak, peak_src = peaks()
     cbar = st["cells"] / max(1, st["aligned"])
     b_alg = 3.0 * cbar + 3.6                      # bytes per aligned base, SURVEY.md 8(d)
@@ -478,14 +678,26 @@ def main():
         ns = min(n, cores * args.cpu_sample_per_core)
         cpu = cpu_baseline(h_ref, bases_np, h_off, cand["strand"], cand["loc1"], cand["loc2"], ns, cores)
 
+    dev.close()
+    dev = None
+    del h_bases, bases_np
+    torch.cuda.empty_cache()
+    full = None
+    if args.full_reads > 0:
+        try:
+            full = full_path_arm(args, rank, world, local, barrier, peak, peak_src)
+        except Exception as e:  # the headline line must still print
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            full = {"error": repr(e)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": DTYPE, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-                "e2e": e2e, "gpu_launches": int(st["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "stages": stages,
+                "e2e": e2e, "gpu_launches": int(st["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "full_path": full, "stages": stages,
                 "stats": {k: st[k] for k in ("cells", "rows", "blocks", "aligned", "columns", "lane_chains", "wide_chains", "interior")}}
         print(json.dumps(line))
-    dev.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -153,6 +153,24 @@ int ag2_extend_upload_from_seeds(ag2_ctx *ctx, int maxc, int64_t *n_candidates);
  * exactly the sequence of output_temp_result() calls of a `-t 1` run.  ag2_record.read is the index of the read
  * in the loaded batch.  Needs ag2_index_build. */
 int ag2_map_reads(ag2_ctx *ctx, int maxc, int num_output, int64_t *n_records);
+
+/* Where the last ag2_map_reads call spent its time (host wall clock between the stages' synchronisation points) and
+ * what it processed; the counterpart of the reference's "The Mapping Time" line (mecat2ref_impl_large.cpp:2133-2138),
+ * per stage. */
+typedef struct ag2_map_stats {
+    double total_ms;
+    double seed_ms;        /* seeding + candidate scoring (A5-A7), first pass */
+    double extend_ms;      /* extend_candidate over every candidate (A8-A10) */
+    double plan_ms;        /* rescue_clipped_align's searches (A11) */
+    double rescue_ms;      /* extension of the rescue candidates, linking, output choice (A11-A12) */
+    double pass2_ms;       /* everything of the second pass (:1049-1315) */
+    double pair_kernel_ms; /* CUDA-event time of xdrop_pair_kernel, all launches of the call */
+    int64_t n_reads, n_records, n_candidates, n_rescue, n_pass2_reads;
+    int64_t seed_overflow1, seed_overflow2; /* reads handed from the first seeding launch to the second / to the thread path */
+    int64_t cells;         /* DP cells of all extensions */
+    int64_t launches;      /* kernel launches of the extension batches */
+} ag2_map_stats;
+int ag2_map_get_stats(ag2_ctx *ctx, ag2_map_stats *out);
 int ag2_map_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used);
 
 /* ---- PAGraph kmer_counter (PAGraph/src/main/kmer_counter.cpp:19-96) ----

@@ -64,6 +64,52 @@ def test_more_outputs_and_fewer_candidates(dev, tmp_path):
     assert open(out, "rb").read() == open(exp, "rb").read()
 
 
+def test_stress_fixture_through_every_seeding_tier(dev, tmp_path, monkeypatch):
+    """The CTA-per-read seeding / rescue planning hands reads that do not fit its shared memory to a second launch with a
+    larger table and, beyond that, to the one-thread-per-read path: tiny limits force reads through all three, and the
+    thread file must not change."""
+    z = np.load(os.path.join(GOLDEN, "mapper_stress.npz"))
+    golden = golden_ref_outputs()["wrk/1.r"]
+    seen = []
+    for cap, cap2 in ((64, 128), (256, 1024), (64, 14208)):
+        monkeypatch.setenv("AG2_SEED_CAP", str(cap))
+        monkeypatch.setenv("AG2_SEED_CAP2", str(cap2))
+        out = str(tmp_path / f"{cap}.r")
+        _thread_file(dev, z["genome"].tobytes(), z["bases"].tobytes(), z["offsets"].astype(np.int64), out)
+        assert open(out, "rb").read() == golden, (cap, cap2)
+        st = dev.map_stats()
+        seen.append((st["seed_overflow1"], st["seed_overflow2"]))
+    assert seen[0][1] > 0 and seen[1][0] > 0, seen      # the thread path and the second launch were really used
+
+
+def test_250mb_reference_matches_reference_binary(dev, tmp_path):
+    """BASELINE configs[2]'s reference size against the UNMODIFIED reference binary: 320 reads (CLR templates of both
+    strands, chimeras, unrelated reads, short reads) vs a seeded 250 Mb reference; `mecat2ref -t 1`'s thread file is
+    committed as digests (tests/golden/map250_ref.json, gen_map250_golden.py), inputs are regenerated from the seeds."""
+    import hashlib
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("gen_map250_golden", os.path.join(GOLDEN, "gen_map250_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = json.load(open(gen.GOLDEN_JSON))
+    ref, reads = gen.inputs(gold["seed"], gold["ref_len"], gold["n_reads"])
+    assert hashlib.sha256(b"\n".join(reads)).hexdigest() == gold["reads_sha256"]      # the generator still makes the golden's inputs
+    assert hashlib.sha256(ref.tobytes()).hexdigest() == gold["ref_sha256"]
+    offs = np.zeros(len(reads) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in reads], out=offs[1:])
+    out = str(tmp_path / "gpu.r")
+    _thread_file(dev, ref.tobytes(), b"".join(reads), offs, out)
+    tf = open(out, "rb").read()
+    got = gen.record_digest(tf)
+    assert len(got) == len(gold["records"])
+    for a, b in zip(got, gold["records"]):
+        assert a == b
+    assert hashlib.sha256(tf).hexdigest() == gold["thread_file_sha256"]
+    st = dev.map_stats()
+    assert st["n_pass2_reads"] > 0      # the golden exercises the second pass at this size (and the rescue searches: 40 clipped reads)
+
+
 def test_250mb_reference_properties(dev):
     """BASELINE configs[2] scale on the reference side: a 250 Mb reference (13-mer buckets of 3.7 positions, 1.25 M vote
     blocks, positions beyond 2^27), whole per-read path.  No oracle at this size: the reads were cut from the reference, so
