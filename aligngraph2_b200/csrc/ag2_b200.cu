@@ -31,6 +31,7 @@ namespace {
 
 constexpr int kWideK = 23;        // 736 columns: covers every possible block (N <= 718)
 constexpr int kWideWarps = 2;
+constexpr int kNarrowK = 4;       // small batches: 128 columns, rows ~5 x shorter; falls back to kWideK
 constexpr int kMaxStreamChunks = 256;
 
 // ---------------------------------------------------------------------------------------------
@@ -977,83 +978,11 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         a.ws_q = (char *)ctx->ws_q.p;
         a.ws_t = (char *)ctx->ws_t.p;
         a.counters = &sc->ctr;
-        // pair kernel over all directions of the chunk; what it hands over goes to the lane queue
-        LaneArgs pa = a;
-        pa.scratch = (uint8_t *)ctx->tb_pair.p;
-        pa.n_chains = 2 * cn;
-        // longest directions first (chain_keys_kernel): no long direction is left running alone when the queue runs dry
-        chain_keys_kernel<<<grid_for(2 * cn, 256, ctx->sm_count), 256, 0, st>>>((const ExtGeom *)ctx->geom.p + lo, 2 * cn,
-                                                                                (uint32_t *)ctx->order_keys.p, (int32_t *)ctx->order_ids.p);
-        {
-            size_t tmp = ctx->order_tmp.cap;
-            CK(cub::DeviceRadixSort::SortPairsDescending(ctx->order_tmp.p, tmp, (const uint32_t *)ctx->order_keys.p, (uint32_t *)ctx->order_keys2.p,
-                                                         (const int32_t *)ctx->order_ids.p, (int32_t *)ctx->order_queue.p, (int)(2 * cn), 0, 24, st));
-        }
-        launches += 2;
-        pa.queue = (const int32_t *)ctx->order_queue.p;
-        pa.next = &sc->next_pair;
-        pa.wide_queue = (int32_t *)ctx->lane_queue.p;
-        pa.wide_count = &sc->lane_count;
-        pa.resume = (LaneResume *)ctx->lane_resume.p;
-        pa.done_ctas = &sc->pair_done;
-        // the consumer of the hand-overs (xdrop_stream_kernel) goes first, on its own high-priority stream, once the chunk's
-        // inputs are in place: it must be resident before the pair kernel fills the SMs
-        ChainArgs cw = {};
-        cw.seqs = sq;
-        cw.cand = a.cand;
-        cw.geom = a.geom;
-        cw.res = a.res;
-        cw.ws_q = a.ws_q;
-        cw.ws_t = a.ws_t;
-        cw.tb = (uint8_t *)ctx->tb_stream.p;
-        cw.tb_stride = tbw_stride;
-        cw.queue = (const int32_t *)ctx->lane_queue.p;
-        cw.next = &sc->next_wide;
-        cw.counters = &sc->ctr;
-        CK(cudaStreamSynchronize(st));
-        if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->side_done, ctx->side_stream));
-        CK(cudaEventRecord(ctx->chain_events[ci].first, st));
-        xdrop_pair_kernel<<<pair_grid, kPairThreads, pair_smem, st>>>(pa);
-        CK(cudaEventRecord(ctx->chain_events[ci].second, st));
-        CK(cudaGetLastError());
-        CK(cudaStreamWaitEvent(st, ctx->side_done, 0));
-        unsigned int n_handed = 0, n_wide = 0;
-        unsigned long long taken = 0;
-        CK(cudaMemcpyAsync(&n_handed, &sc->lane_count, sizeof n_handed, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&taken, &sc->next_wide, sizeof taken, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        launches += 3;
-        ctx->stats_lane_chains += n_handed;
-        // [first, n_handed) was published after the consumer's last ticket: few -> wide kernel, many -> lane kernel
-        const unsigned int first = (unsigned int)std::min<unsigned long long>(taken, n_handed);
-        const unsigned int n_lane = n_handed - first;
-        ctx->stats_direct_wide += first;
-        const bool lane_path = n_lane > lane_threshold;
-        const int32_t *post_queue = (const int32_t *)ctx->lane_queue.p + first;
-        if (n_lane > 0 && !lane_path) {
-            n_wide = n_lane;
-            ctx->stats_direct_wide += n_lane;
-        }
-        if (n_lane > 0 && lane_path) {
-            // one THREAD per direction, resumed at the block the pair window could not hold
-            a.scratch = (uint8_t *)ctx->tb.p;
-            a.n_chains = n_lane;
-            a.queue = post_queue;
-            a.resume = (LaneResume *)ctx->lane_resume.p + first;
-            a.next = &sc->next_fast;
-            a.wide_queue = (int32_t *)ctx->wide_queue.p;
-            a.wide_count = &sc->wide_count;
-            xdrop_lane_kernel<<<lane_grid, kLaneThreads, lane_smem, st>>>(a);
-            CK(cudaGetLastError());
-            // directions that left the lane path too (band > 120 columns, or reservation exceeded): wide kernel
-            CK(cudaMemcpyAsync(&n_wide, &sc->wide_count, sizeof n_wide, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            post_queue = (const int32_t *)ctx->wide_queue.p;
-            ++launches;
-        }
-        if (n_wide > 0) {
+        // A handful of candidates (rescue extensions, the second pass of a few reads): a direction is a chain of ~20
+        // sequentially dependent block DPs, and on the pair kernel, built for throughput, a lone chain takes ~25 ms.  One
+        // WARP per direction (row-parallel kernel) brings that to a few ms.
+        const bool small_batch = 2 * cn <= (int64_t)wide_grid * kWideWarps * 4 && !getenv("AG2_NO_SMALL_BATCH");   // up to four waves
+        if (small_batch) {
             ChainArgs w = {};
             w.seqs = sq;
             w.cand = a.cand;
@@ -1063,15 +992,133 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             w.ws_t = a.ws_t;
             w.tb = (uint8_t *)ctx->tb_wide.p;
             w.tb_stride = tbw_stride;
-            w.n_chains = n_wide;
-            w.queue = post_queue;
+            w.n_chains = 2 * cn;
+            w.queue = nullptr;
             w.next = &sc->next_post;
-            w.wide_queue = nullptr;
-            w.wide_count = nullptr;
             w.counters = &sc->ctr;
-            xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
+            CK(cudaEventRecord(ctx->chain_events[ci].first, st));
+            CK(cudaEventRecord(ctx->chain_events[ci].second, st));
+            // first with 4 columns per lane (a 128-column window: ~5 x shorter rows than the 736-column form); the directions
+            // whose band leaves that window are rerun by the full-width form
+            w.wide_queue = (int32_t *)ctx->wide_queue.p;
+            w.wide_count = &sc->wide_count;
+            const int sgrid = (int)std::min<int64_t>(wide_grid, (2 * cn + kWideWarps - 1) / kWideWarps);
+            xdrop_chains_kernel<kNarrowK, kWideWarps><<<sgrid, kWideWarps * 32, 0, st>>>(w);
             CK(cudaGetLastError());
             ++launches;
+            unsigned int n_again = 0;
+            CK(cudaMemcpyAsync(&n_again, &sc->wide_count, sizeof n_again, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (n_again > 0) {
+                w.n_chains = n_again;
+                w.queue = (const int32_t *)ctx->wide_queue.p;
+                w.next = &sc->next_wide;
+                w.wide_queue = nullptr;
+                w.wide_count = nullptr;
+                xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
+                CK(cudaGetLastError());
+                ++launches;
+            }
+            ctx->stats_direct_wide += 2 * cn;
+        }
+        // pair kernel over all directions of the chunk; what it hands over goes to the lane queue
+        LaneArgs pa = a;
+        if (!small_batch) {
+            pa.scratch = (uint8_t *)ctx->tb_pair.p;
+            pa.n_chains = 2 * cn;
+            // longest directions first (chain_keys_kernel): no long direction is left running alone when the queue runs dry
+            chain_keys_kernel<<<grid_for(2 * cn, 256, ctx->sm_count), 256, 0, st>>>((const ExtGeom *)ctx->geom.p + lo, 2 * cn,
+                                                                                    (uint32_t *)ctx->order_keys.p, (int32_t *)ctx->order_ids.p);
+            {
+                size_t tmp = ctx->order_tmp.cap;
+                CK(cub::DeviceRadixSort::SortPairsDescending(ctx->order_tmp.p, tmp, (const uint32_t *)ctx->order_keys.p, (uint32_t *)ctx->order_keys2.p,
+                                                             (const int32_t *)ctx->order_ids.p, (int32_t *)ctx->order_queue.p, (int)(2 * cn), 0, 24, st));
+            }
+            launches += 2;
+            pa.queue = (const int32_t *)ctx->order_queue.p;
+            pa.next = &sc->next_pair;
+            pa.wide_queue = (int32_t *)ctx->lane_queue.p;
+            pa.wide_count = &sc->lane_count;
+            pa.resume = (LaneResume *)ctx->lane_resume.p;
+            pa.done_ctas = &sc->pair_done;
+            // the consumer of the hand-overs (xdrop_stream_kernel) goes first, on its own high-priority stream, once the chunk's
+            // inputs are in place: it must be resident before the pair kernel fills the SMs
+            ChainArgs cw = {};
+            cw.seqs = sq;
+            cw.cand = a.cand;
+            cw.geom = a.geom;
+            cw.res = a.res;
+            cw.ws_q = a.ws_q;
+            cw.ws_t = a.ws_t;
+            cw.tb = (uint8_t *)ctx->tb_stream.p;
+            cw.tb_stride = tbw_stride;
+            cw.queue = (const int32_t *)ctx->lane_queue.p;
+            cw.next = &sc->next_wide;
+            cw.counters = &sc->ctr;
+            CK(cudaStreamSynchronize(st));
+            if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(ctx->side_done, ctx->side_stream));
+            CK(cudaEventRecord(ctx->chain_events[ci].first, st));
+            xdrop_pair_kernel<<<pair_grid, kPairThreads, pair_smem, st>>>(pa);
+            CK(cudaEventRecord(ctx->chain_events[ci].second, st));
+            CK(cudaGetLastError());
+            CK(cudaStreamWaitEvent(st, ctx->side_done, 0));
+            unsigned int n_handed = 0, n_wide = 0;
+            unsigned long long taken = 0;
+            CK(cudaMemcpyAsync(&n_handed, &sc->lane_count, sizeof n_handed, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&taken, &sc->next_wide, sizeof taken, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            launches += 3;
+            ctx->stats_lane_chains += n_handed;
+            // [first, n_handed) was published after the consumer's last ticket: few -> wide kernel, many -> lane kernel
+            const unsigned int first = (unsigned int)std::min<unsigned long long>(taken, n_handed);
+            const unsigned int n_lane = n_handed - first;
+            ctx->stats_direct_wide += first;
+            const bool lane_path = n_lane > lane_threshold;
+            const int32_t *post_queue = (const int32_t *)ctx->lane_queue.p + first;
+            if (n_lane > 0 && !lane_path) {
+                n_wide = n_lane;
+                ctx->stats_direct_wide += n_lane;
+            }
+            if (n_lane > 0 && lane_path) {
+                // one THREAD per direction, resumed at the block the pair window could not hold
+                a.scratch = (uint8_t *)ctx->tb.p;
+                a.n_chains = n_lane;
+                a.queue = post_queue;
+                a.resume = (LaneResume *)ctx->lane_resume.p + first;
+                a.next = &sc->next_fast;
+                a.wide_queue = (int32_t *)ctx->wide_queue.p;
+                a.wide_count = &sc->wide_count;
+                xdrop_lane_kernel<<<lane_grid, kLaneThreads, lane_smem, st>>>(a);
+                CK(cudaGetLastError());
+                // directions that left the lane path too (band > 120 columns, or reservation exceeded): wide kernel
+                CK(cudaMemcpyAsync(&n_wide, &sc->wide_count, sizeof n_wide, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                post_queue = (const int32_t *)ctx->wide_queue.p;
+                ++launches;
+            }
+            if (n_wide > 0) {
+                ChainArgs w = {};
+                w.seqs = sq;
+                w.cand = a.cand;
+                w.geom = a.geom;
+                w.res = a.res;
+                w.ws_q = a.ws_q;
+                w.ws_t = a.ws_t;
+                w.tb = (uint8_t *)ctx->tb_wide.p;
+                w.tb_stride = tbw_stride;
+                w.n_chains = n_wide;
+                w.queue = post_queue;
+                w.next = &sc->next_post;
+                w.wide_queue = nullptr;
+                w.wide_count = nullptr;
+                w.counters = &sc->ctr;
+                xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
+                CK(cudaGetLastError());
+                ++launches;
+            }
+
         }
         extend_finalize_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>(
             d_cand, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p,
@@ -1683,7 +1730,7 @@ struct SeedCtl {
     unsigned pad[7];
 };
 
-constexpr int kSeedCapMax = 14208;   // events per strand that fit the 227 KB of shared memory of one CTA
+constexpr int kSeedCapMax = 13824;   // index hits per strand that fit the 227 KB of shared memory of one CTA
 
 // Events per strand the first CTA launch is sized for: seeds x (index positions per bucket + share of exact seeds of a
 // 15 %-error read), with a margin; what exceeds it goes to the second launch (kSeedCapMax), then to the thread path.
@@ -1699,7 +1746,7 @@ static int seed_cap(const ag2_ctx *ctx, int pass, int tier)
     const double bc = pass == 0 ? std::min(20.0, 5.0 + mean_len / 1000.0) : 5.0;
     const double density = (double)ctx->ix_npos / (double)kNCodes;
     const double ev = (mean_len / bc + 1.0) * (density + 0.2);
-    const int cap = ((int)(ev * 1.3) + 128 + 255) & ~255;
+    const int cap = ((int)(ev * 1.25) + 128 + 127) & ~127;
     return std::max(256, std::min(kSeedCapMax, cap));
 }
 

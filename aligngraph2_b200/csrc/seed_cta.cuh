@@ -35,10 +35,12 @@ namespace ag2 {
 #ifdef AG2_EMU
 constexpr int kSeedCtaThreads = 32;
 #else
-constexpr int kSeedCtaThreads = 128;
+constexpr int kSeedCtaThreads = 256;
 #endif
 constexpr int kSeedCtaWarps = kSeedCtaThreads / 32;
-constexpr int kSeedDigitBits = 6;                       // radix of the sort: 64 bins per warp
+constexpr int kSeedDigitBits = 9;                       // radix of the sort: 512 bins per warp -- two passes up to 262 144 blocks (250 Mb)
+constexpr int kSeedBins = 1 << kSeedDigitBits;
+constexpr int kNullBlock = 0x7fffff;                    // block field of a hit that is not an event (not the first of its seed in its block)
 constexpr int kSeedMaxCap = 32768;                      // the serial number of an event has 15 bits
 constexpr int kHeavyWords = kSM;                        // pool entry of a heavy block: its 20 surviving (seed, offset) pairs
 
@@ -79,8 +81,7 @@ struct SeedCtaSmem {
     uint16_t *run_start;           // [nruns + 1]
     int16_t *run_score;            // [nruns]  the block's `score` (the scan zeroes it)
     uint32_t *qin, *qout;          // blocks above the threshold: (first serial << 15) | run
-    uint32_t *hist;                // [64][warps]
-    uint32_t *t_off, *t_hb;        // seed tile: bucket start, hit prefix
+    uint16_t *hist;                // [512][warps]
     uint32_t *wsum;                // block_scan scratch
     int *misc;
     int *tl_loc, *tl_seed, *tl_score;
@@ -89,8 +90,7 @@ struct SeedCtaSmem {
 
 __host__ __device__ __forceinline__ size_t seed_cta_smem_bytes(int cap)
 {
-    return (size_t)cap * 16 + 64 * kSeedCtaWarps * 4 + (2 * kSeedCtaThreads + 2) * 4 + 40 * 4 + 32 * 4 + 3 * 2 * kSM * 4 +
-           (kMaxCand + 1) * sizeof(SeedCand) + 64;
+    return (size_t)cap * 16 + kSeedBins * kSeedCtaWarps * 2 + 40 * 4 + 32 * 4 + 3 * 2 * kSM * 4 + (kMaxCand + 1) * sizeof(SeedCand) + 64;
 }
 
 __device__ __forceinline__ SeedCtaSmem seed_cta_carve(uint8_t *p, int cap)
@@ -101,12 +101,8 @@ __device__ __forceinline__ SeedCtaSmem seed_cta_carve(uint8_t *p, int cap)
     uint8_t *q = reinterpret_cast<uint8_t *>(s.aux + cap);
     s.cands = reinterpret_cast<SeedCand *>(q);
     q += (kMaxCand + 1) * sizeof(SeedCand);
-    s.hist = reinterpret_cast<uint32_t *>(q);
-    q += 64 * kSeedCtaWarps * 4;
-    s.t_off = reinterpret_cast<uint32_t *>(q);
-    q += kSeedCtaThreads * 4;
-    s.t_hb = reinterpret_cast<uint32_t *>(q);
-    q += (kSeedCtaThreads + 2) * 4;
+    s.hist = reinterpret_cast<uint16_t *>(q);
+    q += kSeedBins * kSeedCtaWarps * 2;
     s.wsum = reinterpret_cast<uint32_t *>(q);
     q += 40 * 4;
     s.misc = reinterpret_cast<int *>(q);
@@ -172,57 +168,69 @@ inline unsigned __brev(unsigned v)
 #endif
 
 // Stable LSD radix sort of src[0..n) by bits [lo, hi) of the 64-bit words; returns the buffer that holds the result.
-// Every warp owns a contiguous quarter of the array and a histogram of its own; inside a batch of 32 the rank of an
-// element among equals is its lane order (match.any), so equal keys keep their order.
-__device__ uint64_t *sort_events(uint64_t *src, uint64_t *dst, int n, int lo, int hi, uint32_t *hist, uint32_t *wsum)
+// Every warp owns a contiguous part of the array and a histogram of its own; inside a batch of 32 the rank of an element
+// among equals is its lane order (match.any), so equal keys keep their order.  Two batches are in flight per step (their
+// loads and match.any do not depend on each other; only the histogram updates are ordered).
+__device__ uint64_t *sort_events(uint64_t *src, uint64_t *dst, int n, int lo, int hi, uint16_t *hist, uint32_t *wsum)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = ((n + kSeedCtaWarps - 1) / kSeedCtaWarps + 31) & ~31;
+    const int per = ((n + kSeedCtaWarps - 1) / kSeedCtaWarps + 63) & ~63;
     const int seg_lo = min(n, warp * per), seg_hi = min(n, seg_lo + per);
     const unsigned lt = (1u << lane) - 1u;
-    for (int shift = lo; shift < hi; shift += kSeedDigitBits) {
-        const int bits = min(kSeedDigitBits, hi - shift);
+    const int passes = (hi - lo + kSeedDigitBits - 1) / kSeedDigitBits;
+    const int width = (hi - lo + passes - 1) / passes;           // digits of equal width: fewer bins to scan
+    for (int shift = lo; shift < hi; shift += width) {
+        const int bits = min(width, hi - shift);
         const unsigned dmask = (1u << bits) - 1u;
-        for (int i = tid; i < 64 * kSeedCtaWarps; i += kSeedCtaThreads) hist[i] = 0;
+        const int nbins = 1 << bits;
+        for (int i = tid; i < nbins * kSeedCtaWarps; i += kSeedCtaThreads) hist[i] = 0;
         __syncthreads();
-        for (int b = seg_lo; b < seg_hi; b += 32) {
-            const int i = b + lane;
-            const bool valid = i < seg_hi;
-            const unsigned d = valid ? (unsigned)(src[i] >> shift) & dmask : 64u;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            if (valid && (peers & lt) == 0) hist[d * kSeedCtaWarps + warp] += (unsigned)__popc(peers);
+        for (int b = seg_lo; b < seg_hi; b += 64) {
+            const int i0 = b + lane, i1 = b + 32 + lane;
+            const bool v0 = i0 < seg_hi, v1 = i1 < seg_hi;
+            const unsigned d0 = v0 ? (unsigned)(src[i0] >> shift) & dmask : (unsigned)kSeedBins;
+            const unsigned d1 = v1 ? (unsigned)(src[i1] >> shift) & dmask : (unsigned)kSeedBins;
+            const unsigned p0 = __match_any_sync(0xffffffffu, d0), p1 = __match_any_sync(0xffffffffu, d1);
+            if (v0 && (p0 & lt) == 0) hist[d0 * kSeedCtaWarps + warp] += (uint16_t)__popc(p0);
+            __syncwarp();
+            if (v1 && (p1 & lt) == 0) hist[d1 * kSeedCtaWarps + warp] += (uint16_t)__popc(p1);
             __syncwarp();
         }
         __syncthreads();
-        {   // exclusive scan in (digit, warp) order: 64 * warps entries, two per thread at 4 warps
-            constexpr int kPer = 64 * kSeedCtaWarps / kSeedCtaThreads;
-            unsigned loc[kPer], sum = 0;
-#pragma unroll
-            for (int q = 0; q < kPer; ++q) {
-                loc[q] = hist[tid * kPer + q];
-                sum += loc[q];
-            }
+        {   // exclusive scan in (digit, warp) order
+            const int per_t = (nbins * kSeedCtaWarps + kSeedCtaThreads - 1) / kSeedCtaThreads;   // <= 16
+            const int e_lo = min(nbins * kSeedCtaWarps, tid * per_t), e_hi = min(nbins * kSeedCtaWarps, e_lo + per_t);
+            unsigned sum = 0;
+            for (int q = e_lo; q < e_hi; ++q) sum += hist[q];
             int total;
             unsigned run = (unsigned)block_scan_excl((int)sum, total, wsum);
-#pragma unroll
-            for (int q = 0; q < kPer; ++q) {
-                hist[tid * kPer + q] = run;
-                run += loc[q];
+            for (int q = e_lo; q < e_hi; ++q) {
+                const unsigned c = hist[q];
+                hist[q] = (uint16_t)run;
+                run += c;
             }
         }
         __syncthreads();
-        for (int b = seg_lo; b < seg_hi; b += 32) {
-            const int i = b + lane;
-            const bool valid = i < seg_hi;
-            const uint64_t x = valid ? src[i] : 0;
-            const unsigned d = valid ? (unsigned)(x >> shift) & dmask : 64u;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+        for (int b = seg_lo; b < seg_hi; b += 64) {
+            const int i0 = b + lane, i1 = b + 32 + lane;
+            const bool v0 = i0 < seg_hi, v1 = i1 < seg_hi;
+            const uint64_t x0 = v0 ? src[i0] : 0, x1 = v1 ? src[i1] : 0;
+            const unsigned d0 = v0 ? (unsigned)(x0 >> shift) & dmask : (unsigned)kSeedBins;
+            const unsigned d1 = v1 ? (unsigned)(x1 >> shift) & dmask : (unsigned)kSeedBins;
+            const unsigned p0 = __match_any_sync(0xffffffffu, d0), p1 = __match_any_sync(0xffffffffu, d1);
             unsigned off = 0;
-            if (valid) off = hist[d * kSeedCtaWarps + warp];
+            if (v0) off = hist[d0 * kSeedCtaWarps + warp];
             __syncwarp();
-            if (valid) {
-                dst[off + (unsigned)__popc(peers & lt)] = x;
-                if ((peers & lt) == 0) hist[d * kSeedCtaWarps + warp] = off + (unsigned)__popc(peers);
+            if (v0) {
+                dst[off + (unsigned)__popc(p0 & lt)] = x0;
+                if ((p0 & lt) == 0) hist[d0 * kSeedCtaWarps + warp] = (uint16_t)(off + (unsigned)__popc(p0));
+            }
+            __syncwarp();
+            if (v1) off = hist[d1 * kSeedCtaWarps + warp];
+            __syncwarp();
+            if (v1) {
+                dst[off + (unsigned)__popc(p1 & lt)] = x1;
+                if ((p1 & lt) == 0) hist[d1 * kSeedCtaWarps + warp] = (uint16_t)(off + (unsigned)__popc(p1));
             }
             __syncwarp();
         }
@@ -318,7 +326,12 @@ __device__ int seed_cta_build(const RefIndex &ix, const uint32_t *reads2, const 
     int n_ev = 0;
     bool overflow = false;
     uint64_t *ev = sm.ev;
-    // 1. events
+    // 1. events: every thread expands the bucket of its seed in place; a hit that is not the first of its seed in its
+    //    block stays in the stream as a null event (it sorts behind everything and the serial numbers keep their order)
+    if (tid == 0) sm.misc[4] = 0;     // null events
+    __syncthreads();
+    const uint32_t zv32 = (uint32_t)zv;
+    int nulls = 0;
     for (int k0 = 0; k0 < cleave_num && !overflow; k0 += kSeedCtaThreads) {
         const int k = k0 + tid;
         uint32_t o0 = 0, cnt = 0;
@@ -330,52 +343,31 @@ __device__ int seed_cta_build(const RefIndex &ix, const uint32_t *reads2, const 
             }
         }
         int total;
-        const int hb = block_scan_excl((int)cnt, total, sm.wsum);
-        sm.t_off[tid] = o0;
-        sm.t_hb[tid] = (uint32_t)hb;
-        if (tid == 0) sm.t_hb[kSeedCtaThreads] = (uint32_t)total;
-        __syncthreads();
-        for (int h0 = 0; h0 < total; h0 += kSeedCtaThreads) {
-            const int h = h0 + tid;
-            bool acc = false;
-            uint32_t pos = 0;
-            int s = 0;
-            if (h < total) {
-                int lo = 0, hi = kSeedCtaThreads;    // last seed of the tile with t_hb <= h
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (sm.t_hb[mid] <= (uint32_t)h) lo = mid;
-                    else hi = mid;
-                }
-                s = lo;
-                const int i = h - (int)sm.t_hb[s];
-                const uint32_t *p = ix.pos + sm.t_off[s] + i;
-                pos = *p;
-                acc = i == 0 || (int64_t)p[-1] / zv != (int64_t)pos / zv;   // first hit of this seed in this block
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, acc);
-            if (lane == 0) sm.wsum[warp] = (uint32_t)__popc(bal);
-            __syncthreads();
-            int base = n_ev, tot = 0;
-#pragma unroll
-            for (int w = 0; w < kSeedCtaWarps; ++w) {
-                const int c = (int)sm.wsum[w];
-                if (w < warp) base += c;
-                tot += c;
-            }
-            if (n_ev + tot > cap) overflow = true;
-            else if (acc) {
-                const int e = base + __popc(bal & ((1u << lane) - 1u));
-                ev[e] = ev_pack((uint32_t)((int64_t)pos / zv), k0 + s + 1, (int)((int64_t)pos % zv), e);
-            }
-            n_ev += tot;
-            __syncthreads();
-            if (overflow) break;
+        const int hb = n_ev + block_scan_excl((int)cnt, total, sm.wsum);
+        if (n_ev + total > cap) {
+            overflow = true;
+            break;
         }
+        const uint32_t *p = ix.pos + o0;
+        uint32_t prev_blk = 0xffffffffu;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const uint32_t pos = p[i];
+            const uint32_t blk = zv32 == 1000u ? pos / 1000u : pos / 2000u;
+            const uint32_t u = pos - blk * zv32;
+            const bool acc = blk != prev_blk;         // a bucket is ascending: the first hit of this seed in this block (:853)
+            prev_blk = blk;
+            ev[hb + (int)i] = acc ? ev_pack(blk, k + 1, (int)u, hb + (int)i) : ev_pack((uint32_t)kNullBlock, 0, 0, hb + (int)i);
+            nulls += acc ? 0 : 1;
+        }
+        n_ev += total;
     }
+    if (nulls) atomicAdd(reinterpret_cast<unsigned *>(&sm.misc[4]), (unsigned)nulls);
+    __syncthreads();
     if (overflow) return -1;
+    const int n_all = n_ev;
+    n_ev -= sm.misc[4];
     // 2. sort by block; the runs
-    ev = sort_events(sm.ev, sm.aux, n_ev, 41, 41 + block_bits, sm.hist, sm.wsum);
+    ev = sort_events(sm.ev, sm.aux, n_all, 41, 41 + block_bits, sm.hist, sm.wsum);   // the null events end up behind n_ev
     uint64_t *free_buf = ev == sm.ev ? sm.aux : sm.ev;
     sm.ev = ev;
     sm.aux = free_buf;

@@ -18,6 +18,13 @@ def dev():
     d.close()
 
 
+@pytest.fixture(autouse=True)
+def pair_path(monkeypatch):
+    """These tests are about the pair / lane / wide kernels: keep small candidate batches away from the low-latency
+    row-parallel path the library picks for them (covered by test_small_batches_take_the_row_parallel_path)."""
+    monkeypatch.setenv("AG2_NO_SMALL_BATCH", "1")
+
+
 def _strings(rec, qa, sa):
     o, n = int(rec["aln_off"]), int(rec["aln_len"])
     return qa[o:o + n].tobytes(), sa[o:o + n].tobytes()
@@ -99,9 +106,8 @@ def test_ragged_and_edge_candidates(dev, oracle):
     _check_against_oracle(dev, oracle, ref, np.concatenate(reads), off, cand)
 
 
-def test_repeats_and_wide_bands(dev, oracle):
-    # tandem repeats make the band outgrow the 128-column fast window: the wide kernel must take over
-    rng = np.random.default_rng(3)
+def _repeat_case(dev, seed=3):
+    rng = np.random.default_rng(seed)
     unit = synth.make_reference(rng, 7)
     ref = np.concatenate([synth.make_reference(rng, 5000), np.tile(unit, 600), synth.make_reference(rng, 5000)])
     reads, cands = [], []
@@ -113,9 +119,28 @@ def test_repeats_and_wide_bands(dev, oracle):
     off = np.zeros(len(reads) + 1, dtype=np.int64)
     np.cumsum([len(r) for r in reads], out=off[1:])
     c = np.array(cands)
-    cand = dev.make_candidates(c[:, 0], c[:, 1], c[:, 2], c[:, 3])
-    st = _check_against_oracle(dev, oracle, ref, np.concatenate(reads), off, cand)
+    return ref, np.concatenate(reads), off, dev.make_candidates(c[:, 0], c[:, 1], c[:, 2], c[:, 3])
+
+
+def test_repeats_and_wide_bands(dev, oracle):
+    # tandem repeats make the band outgrow the 128-column fast window: the wide kernel must take over
+    ref, bases, off, cand = _repeat_case(dev)
+    st = _check_against_oracle(dev, oracle, ref, bases, off, cand)
     assert st["wide_chains"] > 0 or st["interior"] > 0
+
+
+def test_small_batches_take_the_row_parallel_path(dev, oracle, monkeypatch):
+    """A handful of candidates (rescue extensions, second pass) runs one warp per direction with a 128-column window, and
+    what leaves that window on the full-width form: same records, same strings, same cell count."""
+    monkeypatch.delenv("AG2_NO_SMALL_BATCH")
+    d = synth.make_batch_torch(4242, 400_000, 24, 6000)
+    ref, bases, off = d["ref"].numpy(), d["bases"].numpy(), d["offsets"].numpy()
+    cand = dev.make_candidates(np.arange(24), d["strand"].numpy(), d["loc1"].numpy(), d["loc2"].numpy())
+    st = _check_against_oracle(dev, oracle, ref, bases, off, cand)
+    assert st["lane_chains"] == 0 and st["wide_chains"] >= 48      # nothing went through the pair kernel
+    # tandem repeats: bands wider than 128 columns fall back to the 736-column form
+    ref, bases, off, cand = _repeat_case(dev, seed=4)
+    _check_against_oracle(dev, oracle, ref, bases, off, cand)
 
 
 def test_invalid_candidates_are_not_ok(dev):

@@ -66,8 +66,10 @@ def test_other_parameters(dev):
 
 
 def test_seeding_in_many_launches(dev, monkeypatch):
-    # the per-read block tables of one seeding launch share a scratch arena; a small arena cuts the batch into many launches
-    # (a few reads each), which must not change any candidate
+    # reads that overflow both CTA-per-read launches take the one-thread-per-read path, whose block tables share a scratch
+    # arena; a small arena cuts them into many launches (a few reads each), which must not change any candidate
+    monkeypatch.setenv("AG2_SEED_CAP", "64")
+    monkeypatch.setenv("AG2_SEED_CAP2", "64")
     monkeypatch.setenv("AG2_SEED_SCRATCH", str(300_000))
     d = synth.make_batch_torch(123, 1_000_000, 60, 10000)
     _check(dev, d["ref"].numpy().tobytes(), d["bases"].numpy().tobytes(), d["offsets"].numpy(), cbl=200, passes=(0, 1))

@@ -71,7 +71,7 @@ def test_stress_fixture_through_every_seeding_tier(dev, tmp_path, monkeypatch):
     z = np.load(os.path.join(GOLDEN, "mapper_stress.npz"))
     golden = golden_ref_outputs()["wrk/1.r"]
     seen = []
-    for cap, cap2 in ((64, 128), (256, 1024), (64, 14208)):
+    for cap, cap2 in ((64, 128), (256, 1024), (64, 13824)):
         monkeypatch.setenv("AG2_SEED_CAP", str(cap))
         monkeypatch.setenv("AG2_SEED_CAP2", str(cap2))
         out = str(tmp_path / f"{cap}.r")
