@@ -421,7 +421,7 @@ struct ag2_ctx {
     DevBuf out_q, out_t;                // dense output strings
     int64_t out_total = 0;
     DevBuf tb, tb_wide, tb_pair;
-    DevBuf wide_queue, lane_queue, lane_resume;
+    DevBuf wide_queue, lane_queue, lane_resume, defer_queue, defer_resume;
     DevBuf tb_stream;                   // traceback scratch of the consumer kernel's warps
     cudaEvent_t side_done = nullptr;
     DevBuf order_keys, order_keys2, order_ids, order_queue, order_tmp;   // longest-first queue of the pair kernel
@@ -471,6 +471,7 @@ struct Scalars {
     unsigned long long next_fast, next_wide, next_pair, next_post;
     unsigned int wide_count, lane_count, stream_error, pad_;
     unsigned int pair_done, pair_started;   // adjacent: the pair kernel gets &pair_done and raises pair_done[1] when its first CTA runs
+    unsigned int defer_ctl[4];              // deferred long last blocks of the pair kernel: slots reserved, slots claimed, warps in their main phase
     unsigned long long aligned, columns;
 };
 
@@ -634,7 +635,7 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
                      &ctx->km_out, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
-                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->scalars,
+                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->defer_queue, &ctx->defer_resume, &ctx->scalars,
                      &ctx->order_keys, &ctx->order_keys2, &ctx->order_ids, &ctx->order_queue, &ctx->order_tmp, &ctx->tb_stream,
                      &ctx->piece_flag, &ctx->piece_end, &ctx->chunk_count};
     for (DevBuf *b : all)
@@ -845,6 +846,11 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
     RESERVE(ctx->lane_queue, ((size_t)n * 2 + 1024) * 4);   // + one unpublished ticket per consumer warp
     RESERVE(ctx->lane_resume, (size_t)n * 2 * sizeof(LaneResume));
+    static const bool defer_on = getenv("AG2_NO_DEFER") == nullptr;   // A/B knob
+    if (defer_on) {
+        RESERVE(ctx->defer_queue, (size_t)n * 2 * 4);
+        RESERVE(ctx->defer_resume, (size_t)n * 2 * sizeof(LaneResume));
+    }
 
     // pair kernel: the band window of 128 directions per CTA in shared memory
     int pocc = 0;
@@ -967,7 +973,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         }
         set_slots_kernel<<<grid_for(cn, 256, ctx->sm_count), 256, 0, st>>>((ExtGeom *)ctx->geom.p, (const int64_t *)ctx->prefix.p,
                                                                            (const int64_t *)ctx->meta_prefix.p, lo, cn);
-        CK(cudaMemsetAsync(&sc->next_fast, 0, 4 * sizeof(unsigned long long) + 6 * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(&sc->next_fast, 0, 4 * sizeof(unsigned long long) + 10 * sizeof(unsigned int), st));
         CK(cudaMemsetAsync(ctx->lane_queue.p, 0xff, ((size_t)cn * 2 + 1024) * 4, st));   // -1 = not published
         LaneArgs a = {};
         a.seqs = sq;
@@ -1041,6 +1047,12 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             pa.wide_count = &sc->lane_count;
             pa.resume = (LaneResume *)ctx->lane_resume.p;
             pa.done_ctas = &sc->pair_done;
+            if (defer_on) {   // long last blocks are set aside and run together at the end of the launch (xdrop_pair.cuh)
+                CK(cudaMemsetAsync(ctx->defer_queue.p, 0xff, (size_t)cn * 2 * 4, st));
+                pa.defer_queue = (int32_t *)ctx->defer_queue.p;
+                pa.defer_resume = (LaneResume *)ctx->defer_resume.p;
+                pa.defer_ctl = sc->defer_ctl;
+            }
             // the consumer of the hand-overs (xdrop_stream_kernel) goes first, on its own high-priority stream, once the chunk's
             // inputs are in place: it must be resident before the pair kernel fills the SMs
             ChainArgs cw = {};

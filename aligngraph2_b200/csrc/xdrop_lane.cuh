@@ -76,6 +76,11 @@ struct LaneArgs {
     unsigned int *wide_count;
     ChainCounters *counters;
     unsigned int *done_ctas; // pair kernel: every CTA adds 1 when it has published all its hand-overs (may be null); done_ctas[1] is raised when the first CTA starts
+    // pair kernel: directions whose LAST block is longer than a normal one are set aside and run together at the end
+    // (xdrop_pair.cuh); all null = off
+    int32_t *defer_queue;    // preset to -1
+    LaneResume *defer_resume;
+    unsigned int *defer_ctl; // [0] slots reserved, [1] slots claimed, [2] warps in their main phase
 };
 
 // Hand a direction over: the payload first, then -- fenced -- the queue entry, which a concurrently running consumer

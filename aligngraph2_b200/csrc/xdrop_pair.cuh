@@ -581,17 +581,45 @@ __device__ void pair_prepare(const LaneArgs &g, const LaneChain &s, const PairSc
         ps.tcodes[w] = fetch16(g.seqs.ref2, 0, g.seqs.ref_len, s.t0 + (int64_t)s.inc * (s.tidx + 16 * w), s.inc);
 }
 
+__device__ __forceinline__ unsigned pair_vol_u32(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }
+__device__ __forceinline__ void pair_pause()
+{
+#ifndef AG2_EMU
+    __nanosleep(500);
+#endif
+}
+
 // Body of xdrop_pair_kernel.  Every thread holds two directions; the warp advances all of them by one block per round
 // (stage -> pair_dp in lock step -> per direction: walk and align_ex's bookkeeping), refilling finished ones from the queue.
 // g.wide_queue / g.wide_count receive the directions handed to the lane kernel.
+//
+// A round lasts as long as its longest block.  Blocks are 500 rows except the LAST block of a direction, which has up to
+// 599 (MC/gapalign.cpp:24-31), and with 64 directions per warp nearly every round held one: ~10 % of the row slots ran
+// empty.  So a direction that reaches such a block (g.defer_queue set) is saved and put on a second queue, and the warps
+// take that queue when their main work is done: rounds of long last blocks only, one block per direction -- which also
+// makes the end of the launch fine-grained.  A warp takes deferred work only once none of its lanes can still produce
+// some (no waiting inside a warp on its own lanes), and never blocks: an entry is claimed by compare-and-swap once it is
+// published, otherwise looked at again in the next round.
 __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8_t *scratch)
 {
     LaneChain s[2];
     s[0].chain = s[1].chain = -1;
     const PairScratch ps[2] = {pair_scratch(scratch, tid, 0), pair_scratch(scratch, tid, 1)}; // scratch = the CTA's
     unsigned long long cells = 0, rows = 0, blocks = 0, handed = 0;
-    bool drained = false;
+    bool drained = false, drained2 = g.defer_queue == nullptr, warp_main_done = false;
+    unsigned from_defer = 0;            // bit h: slot h runs a deferred direction
+    if (g.defer_queue && (tid & 31) == 0) atomicAdd(g.defer_ctl + 2, 1u);   // one more warp in its main phase
     for (;;) {
+        if (!warp_main_done && g.defer_queue) {
+            const bool mine = drained && (s[0].chain < 0 || (from_defer & 1u)) && (s[1].chain < 0 || (from_defer & 2u));
+            if (__all_sync(kFull, mine)) {   // this warp will defer nothing more
+                warp_main_done = true;
+                if ((tid & 31) == 0) {
+                    __threadfence();        // its deferrals are published before it is counted out
+                    atomicSub(g.defer_ctl + 2, 1u);
+                }
+            }
+        }
         PairIO io;
         PairBlk blk[2];
 #pragma unroll 1
@@ -599,22 +627,41 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
             io.M[h] = io.N[h] = 0;
             io.ae[h] = io.be[h] = io.nshift[h] = io.bail[h] = 0;
             io.cells[h] = io.rows[h] = 0;
-            if (s[h].chain < 0 && !drained) {
-                const unsigned long long t = atomicAdd(g.next, 1ull);
-                if ((int64_t)t < g.n_chains) {
-                    lane_start_chain(g, g.queue ? (int64_t)g.queue[t] : (int64_t)t, s[h]);
-                    if (s[h].ge.valid && !wait_for_read(g.sig, s[h].c.read)) s[h].ge.valid = 0; // streamed run: its read is still on the way
-                    if (!s[h].ge.valid) {
-                        const ChainResult out = {0, 0, 0, -1, 0, 0, 0, 0};
-                        g.res[s[h].chain] = out;
-                        signal_direction_done(g.sig, s[h].chain);
-                        s[h].chain = -1;
+            for (int attempt = 0; attempt < 3; ++attempt) {
+                if (s[h].chain < 0 && !drained) {
+                    const unsigned long long t = atomicAdd(g.next, 1ull);
+                    if ((int64_t)t < g.n_chains) {
+                        lane_start_chain(g, g.queue ? (int64_t)g.queue[t] : (int64_t)t, s[h]);
+                        from_defer &= ~(1u << h);
+                        if (s[h].ge.valid && !wait_for_read(g.sig, s[h].c.read)) s[h].ge.valid = 0; // streamed run: its read is still on the way
+                        if (!s[h].ge.valid) {
+                            const ChainResult out = {0, 0, 0, -1, 0, 0, 0, 0};
+                            g.res[s[h].chain] = out;
+                            signal_direction_done(g.sig, s[h].chain);
+                            s[h].chain = -1;
+                        }
+                    } else {
+                        drained = true;
                     }
-                } else {
-                    drained = true;
+                } else if (s[h].chain < 0 && warp_main_done && !drained2) {
+                    // claim the next deferred direction if one is there (no ticket is taken in advance: a warp that leaves
+                    // holds nothing back).  Nothing there and no warp of the launch in its main phase: this thread is done --
+                    // CTAs that start later, should the grid not be resident at once, serve their own deferrals.
+                    const unsigned t = pair_vol_u32(g.defer_ctl + 1);
+                    if (t < pair_vol_u32(g.defer_ctl)) {
+                        const int32_t ch = *reinterpret_cast<const volatile int32_t *>(g.defer_queue + t);
+                        if (ch >= 0 && atomicCAS(g.defer_ctl + 1, t, t + 1u) == t) {      // published, and ours
+                            __threadfence();
+                            lane_start_chain(g, ch, s[h]);
+                            lane_resume(s[h], g.defer_resume[t]);
+                            from_defer |= 1u << h;
+                        }
+                    } else if (pair_vol_u32(g.defer_ctl + 2) == 0) {
+                        __threadfence();
+                        if (pair_vol_u32(g.defer_ctl + 1) >= pair_vol_u32(g.defer_ctl)) drained2 = true;
+                    }
                 }
-            }
-            if (s[h].chain >= 0) {
+                if (s[h].chain < 0) break;
                 pair_prepare(g, s[h], ps[h], blk[h]);
                 if (blk[h].qblk > 0 && blk[h].tblk > 0) {
                     if (blk[h].tblk < kPairMinN) { // the reference's row 0 may reach column N here: lane kernel
@@ -623,17 +670,25 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
                         publish_chain(g.wide_queue, slot, s[h].chain);
                         ++handed;
                         s[h].chain = -1;
+                    } else if (g.defer_queue && !(from_defer & (1u << h)) && blk[h].last_block && blk[h].qblk > kBlk) {
+                        const unsigned slot = atomicAdd(g.defer_ctl, 1u);
+                        g.defer_resume[slot] = lane_save(s[h]);
+                        publish_chain(g.defer_queue, slot, s[h].chain);
+                        s[h].chain = -1;
+                        continue;           // the slot is free again: take another direction for this round
                     } else {
                         io.M[h] = blk[h].qblk;
                         io.N[h] = blk[h].tblk;
                     }
                 }
+                break;
             }
         }
-        if (!__any_sync(kFull, s[0].chain >= 0 || s[1].chain >= 0 || !drained)) break;
+        if (!__any_sync(kFull, s[0].chain >= 0 || s[1].chain >= 0 || !drained || !drained2)) break;
         PES(if (tid == 0) g_pes.rounds++;
             g_pes.dir_rounds += (io.M[0] > 0) + (io.M[1] > 0);)
         if (__any_sync(kFull, io.M[0] > 0 || io.M[1] > 0)) pair_dp(sm, tid, ps[0], ps[1], io);
+        else if (!__any_sync(kFull, s[0].chain >= 0 || s[1].chain >= 0)) pair_pause();   // waiting for deferred work of other warps
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) { // not unrolled: the chain state is indexed, so it lives in local memory, not in registers
             LaneChain &c = s[h];

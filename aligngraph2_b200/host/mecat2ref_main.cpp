@@ -152,20 +152,80 @@ int convert_to_fq(const char *in_path, const std::string &out_path)
         fprintf(ot, "%d\t%d\t%s\n", kk - 1, (int)one.size(), one.c_str());
     } else {
         fseek(fp, 0L, SEEK_SET);
-        char *line = nullptr;
-        size_t cap = 0;
-        // name line, sequence token, '+' line, quality token (the reference's fscanf("%[^\n]s") / fscanf("%s\n") pairs)
-        for (;;) {
-            if (getline(&line, &cap, fp) < 0) break;             // @name
-            ssize_t n = getline(&line, &cap, fp);                 // sequence
-            if (n < 0) break;
-            std::string seq(line, (size_t)n);
-            while (!seq.empty() && (seq.back() == '\n' || seq.back() == '\r')) seq.pop_back();
-            if (getline(&line, &cap, fp) < 0) break;             // +
-            if (getline(&line, &cap, fp) < 0) break;             // quality
-            fprintf(ot, "%d\t%d\t%s\n", ++kk, (int)seq.size(), seq.c_str());
+        // The reference reads a record with fscanf("%[^\n]s") / fscanf("%s\n") pairs (mecat2ref.cpp:317): the name and '+'
+        // lines up to the newline, the sequence and the quality as ONE whitespace-delimited token each, all whitespace after
+        // a token (blank lines included) swallowed.  Lines are read whole (getline) while a record is "clean" -- then both
+        // readings agree -- and from the first record that is not (leading / inner blanks, blank lines) the rest of the file
+        // goes through scan_line / scan_token, which are those two conversions character by character.
+        auto is_ws = [](int c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r'; };
+        auto scan_line = [&]() -> int {           // "%[^\n]": 1 = matched, 0 = the next character is a newline (left unread), EOF
+            int c = getc_unlocked(fp);
+            if (c == EOF) return EOF;
+            if (c == '\n') {
+                ungetc(c, fp);
+                return 0;
+            }
+            while (c != EOF && c != '\n') c = getc_unlocked(fp);
+            if (c == '\n') ungetc(c, fp);
+            return 1;
+        };
+        auto scan_token = [&](std::string &out) -> int {   // "%s\n"
+            int c;
+            do c = getc_unlocked(fp);
+            while (c != EOF && is_ws(c));
+            if (c == EOF) return EOF;
+            out.clear();
+            while (c != EOF && !is_ws(c)) {
+                out.push_back((char)c);
+                c = getc_unlocked(fp);
+            }
+            while (c != EOF && is_ws(c)) c = getc_unlocked(fp);
+            if (c != EOF) ungetc(c, fp);
+            return 1;
+        };
+        // token + trailing blanks + newline, nothing else; *len = token length
+        auto clean_token_line = [&](const char *l, ssize_t n, size_t *len) {
+            ssize_t p = 0;
+            while (p < n && !is_ws((unsigned char)l[p])) ++p;
+            *len = (size_t)p;
+            if (p == 0) return false;
+            for (ssize_t q = p; q < n; ++q)
+                if (!is_ws((unsigned char)l[q])) return false;
+            return n > 0 && l[n - 1] == '\n';
+        };
+        char *l1 = nullptr, *l2 = nullptr, *l3 = nullptr, *l4 = nullptr;
+        size_t c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+        bool clean = true;
+        while (clean) {
+            const long at = ftell(fp);
+            const ssize_t n1 = getline(&l1, &c1, fp), n2 = n1 < 0 ? -1 : getline(&l2, &c2, fp), n3 = n2 < 0 ? -1 : getline(&l3, &c3, fp),
+                          n4 = n3 < 0 ? -1 : getline(&l4, &c4, fp);
+            size_t slen = 0, qlen = 0;
+            bool ok = n4 >= 0 && n1 > 0 && l1[n1 - 1] == '\n' && clean_token_line(l2, n2, &slen) && n3 > 0 && !is_ws((unsigned char)l3[0]) &&
+                      l3[n3 - 1] == '\n' && clean_token_line(l4, n4, &qlen);
+            if (ok) {   // the token's trailing skip must stop at the first character of the next record
+                const int c = getc_unlocked(fp);
+                if (c != EOF) {
+                    ungetc(c, fp);
+                    if (is_ws(c)) ok = false;
+                }
+            }
+            if (!ok) {
+                fseek(fp, at, SEEK_SET);
+                clean = false;
+                break;
+            }
+            fprintf(ot, "%d\t%d\t", ++kk, (int)slen);
+            fwrite(l2, 1, slen, ot);
+            fputc('\n', ot);
         }
-        free(line);
+        free(l1);
+        free(l2);
+        free(l3);
+        free(l4);
+        std::string seq, qual;
+        while (scan_line() != EOF && scan_token(seq) != EOF && scan_line() != EOF && scan_token(qual) != EOF)
+            fprintf(ot, "%d\t%d\t%s\n", ++kk, (int)seq.size(), seq.c_str());
     }
     fclose(fp);
     fclose(ot);
@@ -504,7 +564,8 @@ double now_sec()
 void die_ag2(ag2_ctx *ctx, const char *what, int rc)
 {
     fprintf(stderr, "mecat2ref (aligngraph2_b200): %s failed (%d): %s\n", what, rc, ag2_last_error(ctx));
-    exit(1);
+    fflush(stderr);
+    _exit(1);   // not exit(): the read-ahead thread may be inside getline on a FILE that exit()'s stdio teardown would touch
 }
 
 // The GPUs the mapping runs on (reads shard across the GPUs of one box, no data-path collective): all visible
@@ -551,13 +612,16 @@ template <class F> void on_every_device(std::vector<DeviceShard> &sh, F f)
 void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
 {
     const std::vector<int> devs = device_list();
-    std::vector<DeviceShard> sh(devs.size());
-    for (size_t k = 0; k < devs.size(); ++k) {
-        const int rc = ag2_ctx_create(devs[k], &sh[k].ctx);
+    std::vector<DeviceShard> sh;
+    for (size_t k = 0; k < devs.size(); ++k) {   // the devices that initialise are used; the run fails only if none does
+        ag2_ctx *ctx = nullptr;
+        const int rc = ag2_ctx_create(devs[k], &ctx);
         if (rc != AG2_OK) {
-            sh.clear();
-            break;
+            fprintf(stderr, "mecat2ref (aligngraph2_b200): device %d is not usable (%d), going on without it\n", devs[k], rc);
+            continue;
         }
+        sh.emplace_back();
+        sh.back().ctx = ctx;
     }
     if (sh.empty()) {
         fprintf(stderr, "mecat2ref (aligngraph2_b200): no usable CUDA device; there is no CPU path\n");

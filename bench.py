@@ -665,7 +665,12 @@ def main():
     b_alg = 3.0 * cbar + 3.6                      # bytes per aligned base, SURVEY.md 8(d)
     kern_s = kernel_ms / args.steps * 1e-3
     achieved = b_alg * st["aligned"] / kern_s / 1e9
+    traffic_bytes = TRAFFIC_BYTES_PER_ALIGNED_BASE * st["aligned"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "achieved_is": "ALGORITHMIC bytes (SURVEY 8d: 3 B per DP cell + 3.6 B per aligned base) / kernel time -- not DRAM utilisation",
+                "limiter": "instruction issue (ALU pipe ~70 %, issue slots ~72 % busy, DRAM ~16 %: profiles/kernel_r01h_pair.md); the score band "
+                           "never leaves the SM, what reaches DRAM is the 4-bit traceback",
+                "dram_gbs_measured": traffic_bytes / kern_s / 1e9,
                 "traffic": TRAFFIC_BYTES_PER_ALIGNED_BASE * st["aligned"], "traffic_note": TRAFFIC_NOTE,
                 "kernel": "xdrop_pair_kernel", "kernel_ms_per_launch": kernel_ms / args.steps,
                 "algorithmic_bytes_per_aligned_base": b_alg, "cells_per_aligned_base": cbar,

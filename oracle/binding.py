@@ -17,7 +17,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ORACLE_SO = os.path.join(HERE, "libag2_oracle.so")
+ORACLE_SO = os.environ.get("AG2_ORACLE_SO") or os.path.join(HERE, "libag2_oracle.so")   # the override is for the sanitizer build (oracle/asan_check.sh)
 REF_SO = os.path.join(HERE, "_ref", "libref_mecat.so")
 REF_BIN = os.path.join(HERE, "_ref", "mecat2ref")
 REF_KMER_COUNTER = os.path.join(HERE, "_ref", "kmer_counter")

@@ -152,6 +152,7 @@ int emu_extend(int K, const char *ref, long ref_len, const char *read, int read_
 // setup_one -> lane_kernel_body (+ wide rerun of handed-over directions) -> finalize_one -> assemble_record.
 // reads: concatenated ASCII with offs[n+1]; cand: n x (read, strand, loc1, loc2).  Outputs per candidate:
 // rec[8] = ok qb qe sb se aln_len mode_left mode_right; strings concatenated into qaln/taln at aoff[i].
+static int g_emu_defer = 0;
 static int batch_impl(bool pair, const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
                       int n, long *rec, long *aoff, char *qaln, char *taln, long *stats /* cells wide handed */)
 {
@@ -211,6 +212,14 @@ static int batch_impl(bool pair, const char *ref, long ref_len, const char *read
         std::vector<int32_t> lane_queue(2 * n + 1);
         std::vector<LaneResume> lane_resume(2 * n + 1);
         LaneArgs pa = a;
+        std::vector<int32_t> defer_queue(2 * n + 1, -1);
+        std::vector<LaneResume> defer_resume(2 * n + 1);
+        unsigned int defer_ctl[4] = {0, 0, 0, 0};
+        if (g_emu_defer) {   // long last blocks set aside and run at the end (one emulated warp = the whole launch)
+            pa.defer_queue = defer_queue.data();
+            pa.defer_resume = defer_resume.data();
+            pa.defer_ctl = defer_ctl;
+        }
         pa.scratch = (uint8_t *)(((uintptr_t)pscratch.data() + 15) & ~(uintptr_t)15);
         pa.wide_queue = lane_queue.data();
         pa.wide_count = &handed;
@@ -282,6 +291,8 @@ static int batch_impl(bool pair, const char *ref, long ref_len, const char *read
     stats[2] = (long)handed;
     return 0;
 }
+
+void emu_set_defer(int on) { g_emu_defer = on; }
 
 int emu_lane_batch(const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
                    int n, long *rec, long *aoff, char *qaln, char *taln, long *stats)

@@ -195,6 +195,18 @@ inline unsigned atomicAdd(unsigned *p, unsigned v)
     *p = o + v;
     return o;
 }
+inline unsigned atomicSub(unsigned *p, unsigned v)
+{
+    const unsigned o = *p;
+    *p = o - v;
+    return o;
+}
+inline unsigned atomicCAS(unsigned *p, unsigned cmp, unsigned val)
+{
+    const unsigned o = *p;
+    if (o == cmp) *p = val;
+    return o;
+}
 using std::max;
 inline void __threadfence() {}                 // one emulated warp: program order is memory order
 using std::min;

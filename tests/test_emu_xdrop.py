@@ -172,18 +172,25 @@ def test_emulated_lane_path_matches_oracle(emu, oracle):
     assert wide > 0, "no direction was handed to the wide path: that hand-over is part of this test"
 
 
-def test_emulated_pair_path_matches_oracle(emu, oracle):
+@pytest.mark.parametrize("defer", [0, 1])
+def test_emulated_pair_path_matches_oracle(emu, oracle, defer):
     # the pair path (two directions per lane, packed 16-bit DP) in front of the lane path: same stress batch, more
     # directions than the 64 the emulated warp holds (refill), target blocks shorter than 32 and unrelated extensions
     # (handed to the lane kernel, then to the wide kernel)
+    # defer = 1: directions whose last block is longer than 500 rows are set aside and run at the end of the launch
     ref, reads, cands, exp, cells = _stress_batch(oracle, 22, 80)
-    got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
+    emu.emu_set_defer(defer)
+    try:
+        got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
+    finally:
+        emu.emu_set_defer(0)
     _check(exp, got)
     assert got_cells == cells
     assert handed > 0 and handed < len(cands), "the pair kernel must keep most directions and hand some over"
 
 
-def test_emulated_pair_path_long_reads(emu, oracle):
+@pytest.mark.parametrize("defer", [0, 1])
+def test_emulated_pair_path_long_reads(emu, oracle, defer):
     # full-length blocks (500 x 500), window moves, several blocks per direction
     d = synth.make_batch_torch(77, 150_000, 24, 4000)
     ref, bases, off = d["ref"].numpy(), d["bases"].numpy(), d["offsets"].numpy()
@@ -194,6 +201,10 @@ def test_emulated_pair_path_long_reads(emu, oracle):
         a = oracle.extend(ref.tobytes(), synth.orient(reads[i], cands[i][1]), cands[i][2], cands[i][3])
         exp.append(a)
         cells += a["cells"]
-    got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
+    emu.emu_set_defer(defer)
+    try:
+        got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
+    finally:
+        emu.emu_set_defer(0)
     _check(exp, got)
     assert got_cells == cells

@@ -161,3 +161,74 @@ def test_more_than_one_load_fastq_batch(binary, tmp_path):
     assert r.returncode == 0, r.stderr.decode()
     for name in ("wrk/1.r", "o.txt", "p.txt"):
         assert (b / name).read_bytes() == (c / name).read_bytes(), name
+
+
+def _records(path):
+    """multiset of 3-line records of a ref-format / thread file"""
+    lines = open(path, "rb").read().split(b"\n")
+    return sorted(b"\n".join(lines[k:k + 3]) for k in range(0, len(lines) - 2, 3))
+
+
+@pytest.mark.gpu
+def test_baseline_config0_against_reference_t1_and_t8(binary, tmp_path):
+    """BASELINE configs[0] exactly: 1 000 synthetic CLR reads (10 kb templates, 15 % error) vs a 1 Mb reference, seed
+    20261017, `-z 200`.  The drop-in executable's `-p` / `-o` files, as multisets of records, must equal what the
+    UNMODIFIED reference binary writes with `-t 1` AND with `-t 8` (per-read results do not depend on -t, only
+    the order of the records does), and byte for byte what `-t 1` writes; running ours with `-t 8` changes nothing."""
+    from oracle import binding
+    if not os.path.exists(binding.REF_BIN):
+        pytest.skip("oracle/_ref/mecat2ref not built on this box")
+    from aligngraph2_b200 import synth
+    ref, reads, _ = synth.make_dataset(20261017, 1_000_000, 1000, 10000)
+    dirs = {k: tmp_path / k for k in ("ref1", "ref8", "gpu1", "gpu8")}
+    for d in dirs.values():
+        d.mkdir()
+        synth.write_fasta(str(d / "ref.fa"), "chr1", ref)
+        synth.write_fastq(str(d / "reads.fq"), reads)
+    subprocess.run([binding.REF_BIN, "-t", "1"] + ARGS, cwd=dirs["ref1"], check=True, capture_output=True)
+    subprocess.run([binding.REF_BIN, "-t", "8"] + ARGS, cwd=dirs["ref8"], check=True, capture_output=True)
+    for k, t in (("gpu1", "1"), ("gpu8", "8")):
+        r = subprocess.run([binary, "-t", t] + ARGS, cwd=dirs[k], capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()
+    want_p, want_o = _records(dirs["ref1"] / "p.txt"), _records(dirs["ref1"] / "o.txt")
+    assert len(want_p) >= 990
+    assert _records(dirs["ref8"] / "p.txt") == want_p and _records(dirs["ref8"] / "o.txt") == want_o     # F6 holds on this input
+    for k in ("gpu1", "gpu8"):
+        assert _records(dirs[k] / "p.txt") == want_p, k
+        assert _records(dirs[k] / "o.txt") == want_o, k
+        for name in ("wrk/0.fq", "wrk/ref.fq", "wrk/chrindex.txt", "wrk/1.r", "o.txt", "p.txt"):
+            assert (dirs["ref1"] / name).read_bytes() == (dirs[k] / name).read_bytes(), (k, name)
+
+
+def test_fastq_token_semantics_match_reference(binary, tmp_path):
+    """The reference reads FASTQ with fscanf("%[^\\n]s") / fscanf("%s\\n") pairs (mecat2ref.cpp:317): sequence and quality are
+    whitespace-delimited TOKENS and all whitespace behind them, blank lines included, is swallowed.  <wrk>/0.fq (ids and
+    lengths) of the drop-in executable must equal the reference binary's on a file with CRLF line ends, trailing blanks,
+    blank lines between records, a leading blank before a sequence, and no newline at the end."""
+    from oracle import binding
+    if not os.path.exists(binding.REF_BIN):
+        pytest.skip("oracle/_ref/mecat2ref not built on this box")
+    rng = np.random.default_rng(11)
+    seq = lambda n: bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), size=n))
+    recs = [b"@r0 first\n" + seq(300) + b"\n+\n" + b"I" * 300 + b"\n",                       # clean
+            b"@r1\r\n" + seq(250) + b"\r\n+\r\n" + b"I" * 250 + b"\r\n",                      # CRLF
+            b"@r2\n" + seq(200) + b"  \t\n+r2\n" + b"I" * 200 + b" \n",                       # trailing blanks
+            b"\n\n@r3\n" + seq(180) + b"\n+\n" + b"I" * 180 + b"\n\n\n",                      # blank lines around the record
+            b"@r4\n  " + seq(150) + b"\n+\n" + b"I" * 150 + b"\n",                            # leading blanks before the sequence
+            b"@r5\n" + seq(120) + b"\n\n+\n" + b"I" * 120 + b"\n",                            # blank line inside the record
+            b"@r6\n" + seq(100) + b"\n+\n" + b"I" * 100]                                      # no newline at the end of the file
+    ref = b">chr1\n" + seq(5000) + b"\n"
+    outs = {}
+    for who, exe, env in (("ref", binding.REF_BIN, os.environ), ("ours", binary, dict(os.environ, AG2_SKIP_MAP="1"))):
+        d = tmp_path / who
+        d.mkdir()
+        (d / "ref.fa").write_bytes(ref)
+        (d / "reads.fq").write_bytes(b"".join(recs))
+        if who == "ours":
+            (d / "wrk").mkdir()
+            (d / "wrk" / "1.r").write_bytes(b"")
+        r = subprocess.run([exe, "-t", "1"] + ARGS, cwd=d, env=env, capture_output=True)
+        assert r.returncode == 0, r.stderr.decode()
+        outs[who] = (d / "wrk" / "0.fq").read_bytes()
+    assert outs["ours"] == outs["ref"]
+    assert outs["ref"].count(b"\n") == 7
