@@ -262,6 +262,30 @@ __global__ void assemble_kernel(Record *rec, const ExtGeom *geom, const ChainRes
     }
 }
 
+// Alignment columns as 2-bit ops, 16 per word (column j of the dense pool at bits 2 * (j % 16) of word j / 16): 0 = a base of
+// both, 1 = '-' in the read string, 2 = '-' in the reference string.  With the read and the reference the caller has, this
+// is the whole content of the two ASCII strings at an eighth of the bytes (ag2_expand_alignments rebuilds them).
+__global__ void pack_ops_kernel(const char *__restrict__ q, const char *__restrict__ t, int64_t w_lo, int64_t w_hi, int64_t col_end,
+                                uint32_t *__restrict__ ops)
+{
+    for (int64_t w = w_lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < w_hi; w += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c0 = w << 4;
+        uint32_t v = 0;
+        if (c0 + 16 <= col_end) {
+            const uint4 a = *reinterpret_cast<const uint4 *>(q + c0), b = *reinterpret_cast<const uint4 *>(t + c0);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t qc = (aw[k >> 2] >> (8 * (k & 3))) & 0xffu, tc = (bw[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                v |= (qc == '-' ? 1u : tc == '-' ? 2u : 0u) << (2 * k);
+            }
+        } else {
+            for (int k = 0; k < 16 && c0 + k < col_end; ++k) v |= (q[c0 + k] == '-' ? 1u : t[c0 + k] == '-' ? 2u : 0u) << (2 * k);
+        }
+        ops[w] = v;
+    }
+}
+
 // Wide path (any band a block can have): the int32 row kernel with K columns per lane.
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
@@ -419,6 +443,7 @@ struct ag2_ctx {
     std::vector<int64_t> h_prefix, h_meta_prefix;
     DevBuf ws_q, ws_t;                  // workspace strings (one chunk of candidates)
     DevBuf out_q, out_t;                // dense output strings
+    DevBuf out_ops;                     // the same as 2-bit ops (packed output)
     int64_t out_total = 0;
     DevBuf tb, tb_wide, tb_pair;
     DevBuf wide_queue, lane_queue, lane_resume, defer_queue, defer_resume;
@@ -611,6 +636,7 @@ int ag2_ctx_create(int device, ag2_ctx **out)
     carve_ok = carve_ok && cudaSuccess == (cudaFuncSetAttribute(extend_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     carve_ok = carve_ok && cudaSuccess == (cudaFuncSetAttribute(scan_chunk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     carve_ok = carve_ok && cudaSuccess == (cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    carve_ok = carve_ok && cudaSuccess == (cudaFuncSetAttribute(pack_ops_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
     if (!carve_ok) {
         ag2_ctx_destroy(ctx);
@@ -635,7 +661,7 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
                      &ctx->km_out, &ctx->ascii, &ctx->ref2, &ctx->reads2, &ctx->reads_irr, &ctx->read_off, &ctx->read_len,
                      &ctx->ascii_offs, &ctx->cand, &ctx->geom, &ctx->caps, &ctx->prefix, &ctx->nmeta, &ctx->meta_prefix, &ctx->meta, &ctx->res, &ctx->rec,
                      &ctx->str_begin, &ctx->ok_len, &ctx->dense_off, &ctx->ws_q, &ctx->ws_t, &ctx->out_q,
-                     &ctx->out_t, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->defer_queue, &ctx->defer_resume, &ctx->scalars,
+                     &ctx->out_t, &ctx->out_ops, &ctx->tb, &ctx->tb_wide, &ctx->tb_pair, &ctx->wide_queue, &ctx->lane_queue, &ctx->lane_resume, &ctx->defer_queue, &ctx->defer_resume, &ctx->scalars,
                      &ctx->order_keys, &ctx->order_keys2, &ctx->order_ids, &ctx->order_queue, &ctx->order_tmp, &ctx->tb_stream,
                      &ctx->piece_flag, &ctx->piece_end, &ctx->chunk_count};
     for (DevBuf *b : all)
@@ -822,8 +848,42 @@ struct HostSink { // caller-owned host buffers that receive each chunk's results
     ag2_record *rec = nullptr;
     char *q = nullptr, *t = nullptr;
     int64_t cap = 0;
+    uint32_t *ops = nullptr;   // packed form: 2-bit ops instead of the two strings (cap = columns); chunks start on word boundaries
     bool overflow = false;
 };
+
+// A chunk's share of the dense pool [base, base + total) goes home: both strings, or their 2-bit ops.
+static int sink_copy_chunk(ag2_ctx *ctx, HostSink *sink, int64_t dense_base, int64_t chunk_total, cudaStream_t compute, cudaStream_t copy,
+                           cudaEvent_t ev, int *launches)
+{
+    if (sink->ops) {
+        if (dense_base + chunk_total > sink->cap) {
+            sink->overflow = true;
+            return AG2_OK;
+        }
+        const int64_t w_lo = dense_base >> 4, w_hi = (dense_base + chunk_total + 15) >> 4;   // out_ops was sized by the caller
+        if (w_hi > w_lo) {
+            pack_ops_kernel<<<grid_for(w_hi - w_lo, 128, ctx->sm_count), 128, 0, compute>>>((const char *)ctx->out_q.p, (const char *)ctx->out_t.p, w_lo, w_hi,
+                                                                                         dense_base + chunk_total, (uint32_t *)ctx->out_ops.p);
+            CK(cudaGetLastError());
+            ++*launches;
+        }
+        CK(cudaEventRecord(ev, compute));
+        CK(cudaStreamWaitEvent(copy, ev, 0));
+        if (w_hi > w_lo)
+            CK(cudaMemcpyAsync(sink->ops + w_lo, (uint32_t *)ctx->out_ops.p + w_lo, (size_t)(w_hi - w_lo) * 4, cudaMemcpyDeviceToHost, copy));
+        return AG2_OK;
+    }
+    CK(cudaEventRecord(ev, compute));
+    CK(cudaStreamWaitEvent(copy, ev, 0));
+    if (sink->q && sink->t && dense_base + chunk_total <= sink->cap) {
+        CK(cudaMemcpyAsync(sink->q + dense_base, (char *)ctx->out_q.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, copy));
+        CK(cudaMemcpyAsync(sink->t + dense_base, (char *)ctx->out_t.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, copy));
+    } else if (sink->q || sink->t) {
+        sink->overflow = true;
+    }
+    return AG2_OK;
+}
 
 static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record *d_rec, int64_t dense_base_in, int64_t *dense_base_out,
                         bool fresh_stats, HostSink *sink = nullptr, const ag2_candidate *h_cand = nullptr)
@@ -846,7 +906,10 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     RESERVE(ctx->wide_queue, (size_t)n * 2 * 4);
     RESERVE(ctx->lane_queue, ((size_t)n * 2 + 1024) * 4);   // + one unpublished ticket per consumer warp
     RESERVE(ctx->lane_resume, (size_t)n * 2 * sizeof(LaneResume));
-    static const bool defer_on = getenv("AG2_NO_DEFER") == nullptr;   // A/B knob
+    // Opt-in experiment (AG2_DEFER=1): long last blocks set aside and run together at the end of the launch.  Measured on
+    // configs[1]: no gain (pair kernel 385 -> 389 ms, step +17 ms) -- the longest-first queue already gives a warp
+    // directions of equal length, so their last blocks fall into the same round (profiles/defer_r02.md).
+    static const bool defer_on = getenv("AG2_DEFER") != nullptr;
     if (defer_on) {
         RESERVE(ctx->defer_queue, (size_t)n * 2 * 4);
         RESERVE(ctx->defer_resume, (size_t)n * 2 * sizeof(LaneResume));
@@ -945,11 +1008,14 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     RESERVE(ctx->order_tmp, order_tmp_bytes + 16);
     // upper bound of the dense strings: every column consumes a base of the read or of its window
     {
-        int rk = reserve_keep(ctx, ctx->out_q, (size_t)(dense_base_in + pf[n]) + 64, (size_t)dense_base_in);
+        const size_t pad = 64 + 16 * chunks.size();   // packed output rounds every chunk up to 16 columns
+        int rk = reserve_keep(ctx, ctx->out_q, (size_t)(dense_base_in + pf[n]) + pad, (size_t)dense_base_in);
         if (rk != AG2_OK) return rk;
-        rk = reserve_keep(ctx, ctx->out_t, (size_t)(dense_base_in + pf[n]) + 64, (size_t)dense_base_in);
+        rk = reserve_keep(ctx, ctx->out_t, (size_t)(dense_base_in + pf[n]) + pad, (size_t)dense_base_in);
         if (rk != AG2_OK) return rk;
     }
+    // packed output: one word per 16 columns, every chunk rounded up to a word
+    if (sink && sink->ops) RESERVE(ctx->out_ops, ((size_t)(dense_base_in + pf[n]) / 16 + chunks.size() + 8) * 4);
     while (ctx->chain_events.size() < chunks.size()) {
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
@@ -1147,18 +1213,13 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             (char *)ctx->out_q.p, (char *)ctx->out_t.p, &sc->aligned, &sc->columns);
         ++launches;
         CK(cudaGetLastError());
-        if (sink) { // this chunk's records and strings go home on the copy stream while the next chunk computes
-            CK(cudaEventRecord(ctx->chunk_done, st));
-            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_done, 0));
+        if (sink) { // this chunk's records and strings (or their ops) go home on the copy stream while the next chunk computes
+            const int rc = sink_copy_chunk(ctx, sink, dense_base, chunk_total, st, ctx->copy_stream, ctx->chunk_done, &launches);
+            if (rc != AG2_OK) return rc;
             CK(cudaMemcpyAsync(sink->rec + lo, d_rec + lo, (size_t)cn * sizeof(Record), cudaMemcpyDeviceToHost, ctx->copy_stream));
-            if (sink->q && sink->t && dense_base + chunk_total <= sink->cap) {
-                CK(cudaMemcpyAsync(sink->q + dense_base, (char *)ctx->out_q.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
-                CK(cudaMemcpyAsync(sink->t + dense_base, (char *)ctx->out_t.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            } else if (sink->q || sink->t) {
-                sink->overflow = true;
-            }
         }
         dense_base += chunk_total;
+        if (sink && sink->ops) dense_base = (dense_base + 15) & ~(int64_t)15;   // the next chunk's ops start on a word of their own
     }
     CK(cudaStreamSynchronize(st));
     if (sink) CK(cudaStreamSynchronize(ctx->copy_stream));
@@ -1259,7 +1320,11 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     RESERVE(ctx->tb_stream, tbw_stride * std::max(1, stream_grid) * kWideWarps);
     // every pair CTA resident from the start (a consumer CTA takes one pair CTA's place): nothing of this launch is left
     // pending in front of the small kernels that have to run beside it
-    const int pair_grid = std::max(1, pair_full - stream_grid);
+    // AG2_STREAM_FREE_CTAS (tuning knob): CTAs left out of the grid on top of the consumer's, so that as many SMs keep a free
+    // slot for the small kernels without every SM giving one up (with AG2_STREAM_CTAS_PER_SM=7)
+    int free_ctas = 0;
+    if (const char *e = getenv("AG2_STREAM_FREE_CTAS")) free_ctas = std::max(0, atoi(e));
+    const int pair_grid = std::max(1, pair_full - stream_grid - free_ctas);
 
     const PackedSeqs sq = seqs_of(ctx);
     Scalars *sc = (Scalars *)ctx->scalars.p;
@@ -1286,8 +1351,9 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     RESERVE(ctx->ws_q, (size_t)ws_total + 64);
     RESERVE(ctx->ws_t, (size_t)ws_total + 64);
     RESERVE(ctx->meta, ((size_t)meta_total + 16) * 4);
-    RESERVE(ctx->out_q, (size_t)ws_total + 64);   // upper bound of the dense strings: every column consumes a base of the read or of its window
-    RESERVE(ctx->out_t, (size_t)ws_total + 64);
+    RESERVE(ctx->out_q, (size_t)ws_total + 64 + 16 * kMaxStreamChunks);   // upper bound of the dense strings: every column consumes a base of the read or of its window
+    RESERVE(ctx->out_t, (size_t)ws_total + 64 + 16 * kMaxStreamChunks);
+    if (sink->ops) RESERVE(ctx->out_ops, ((size_t)ws_total / 16 + kMaxStreamChunks + 8) * 4);
 
     // output chunks: equal candidate counts, about ws_limit_streamed bytes of workspace string each
     int64_t want = (int64_t)std::min<size_t>(kMaxStreamChunks, std::max<size_t>(1, ((size_t)ws_total + ctx->ws_call - 1) / ctx->ws_call));
@@ -1475,16 +1541,13 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
             &sc->columns);
         ++launches;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->post_done, post));
-        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->post_done, 0));
-        CK(cudaMemcpyAsync(sink->rec + lo, d_rec + lo, (size_t)cn * sizeof(Record), cudaMemcpyDeviceToHost, ctx->copy_stream));
-        if (sink->q && sink->t && dense_base + chunk_total <= sink->cap) {
-            CK(cudaMemcpyAsync(sink->q + dense_base, (char *)ctx->out_q.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            CK(cudaMemcpyAsync(sink->t + dense_base, (char *)ctx->out_t.p + dense_base, (size_t)chunk_total, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        } else if (sink->q || sink->t) {
-            sink->overflow = true;
+        {
+            const int rc = sink_copy_chunk(ctx, sink, dense_base, chunk_total, post, ctx->copy_stream, ctx->post_done, &launches);
+            if (rc != AG2_OK) return rc;
         }
+        CK(cudaMemcpyAsync(sink->rec + lo, d_rec + lo, (size_t)cn * sizeof(Record), cudaMemcpyDeviceToHost, ctx->copy_stream));
         dense_base += chunk_total;
+        if (sink->ops) dense_base = (dense_base + 15) & ~(int64_t)15;
     }
     if (!post_ran) {   // nothing was missing for any chunk; the bookkeeping of the hand-overs is still due
         const int rc = post_pass();
@@ -1564,19 +1627,13 @@ int ag2_extend_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *sa
     return rc;
 }
 
-int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out, char *qaln_out,
-                           char *saln_out, int64_t aln_cap, int64_t *aln_used)
+static int extend_batch_host(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, HostSink &sink, int64_t *aln_used, const char *who)
 {
     int r = ag2_extend_upload(ctx, cand, n);
     if (r != AG2_OK) return r;
-    if (!rec_out) return fail(ctx, AG2_EINVAL, "ag2_xdrop_extend_batch: rec_out is required");
+    if (!sink.rec) return fail(ctx, AG2_EINVAL, "%s: rec_out is required", who);
     CK(cudaSetDevice(ctx->device));
     RESERVE(ctx->rec, (size_t)n * sizeof(Record));
-    HostSink sink;
-    sink.rec = rec_out;
-    sink.q = qaln_out;
-    sink.t = saln_out;
-    sink.cap = aln_cap;
     int64_t total = 0;
     // Two forms of the host-buffer run: "chunked" = one pair-kernel launch per output chunk, the chunk's results copied home
     // while the next chunk computes; "streamed" = ONE launch for the whole batch with flags per output chunk
@@ -1603,10 +1660,123 @@ int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, a
     ctx->out_total = total;
     ctx->ran = true;
     if (aln_used) *aln_used = total;
-    if (sink.overflow) return fail(ctx, AG2_ECAP, "ag2_xdrop_extend_batch: need %ld bytes per string, have %ld", (long)total, (long)aln_cap);
+    if (sink.overflow) return fail(ctx, AG2_ECAP, "%s: need room for %ld alignment columns, have %ld", who, (long)total, (long)sink.cap);
     return AG2_OK;
 }
 
+int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out, char *qaln_out,
+                           char *saln_out, int64_t aln_cap, int64_t *aln_used)
+{
+    HostSink sink;
+    sink.rec = rec_out;
+    sink.q = qaln_out;
+    sink.t = saln_out;
+    sink.cap = aln_cap;
+    return extend_batch_host(ctx, cand, n, sink, aln_used, "ag2_xdrop_extend_batch");
+}
+
+int ag2_xdrop_extend_batch_packed(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out, uint32_t *ops_out,
+                                  int64_t cap_columns, int64_t *columns_used)
+{
+    if (!ops_out) return fail(ctx, AG2_EINVAL, "ag2_xdrop_extend_batch_packed: ops_out is required");
+    HostSink sink;
+    sink.rec = rec_out;
+    sink.ops = ops_out;
+    sink.cap = cap_columns & ~(int64_t)15;
+    return extend_batch_host(ctx, cand, n, sink, columns_used, "ag2_xdrop_extend_batch_packed");
+}
+
+// The 2-bit ops of the dense pool of the last run (resident results): the packed counterpart of ag2_extend_fetch.
+int ag2_extend_fetch_packed(ag2_ctx *ctx, ag2_record *rec_out, uint32_t *ops_out, int64_t cap_columns, int64_t *columns_used)
+{
+    if (!ctx || !rec_out) return fail(ctx, AG2_EINVAL, "ag2_extend_fetch_packed: bad argument");
+    if (!ctx->ran) return fail(ctx, AG2_ESTATE, "ag2_extend_fetch_packed: call ag2_extend_run first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = ctx->n_cand, total = ctx->out_total, words = (total + 15) >> 4;
+    CK(cudaMemcpyAsync(rec_out, ctx->rec.p, (size_t)n * sizeof(Record), cudaMemcpyDeviceToHost, st));
+    if (columns_used) *columns_used = total;
+    int rc = AG2_OK;
+    if (ops_out && cap_columns >= total) {
+        RESERVE(ctx->out_ops, (size_t)(words + 8) * 4);
+        if (words > 0) {
+            pack_ops_kernel<<<grid_for(words, 256, ctx->sm_count), 256, 0, st>>>((const char *)ctx->out_q.p, (const char *)ctx->out_t.p, 0, words, total,
+                                                                                (uint32_t *)ctx->out_ops.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(ops_out, ctx->out_ops.p, (size_t)words * 4, cudaMemcpyDeviceToHost, st));
+        }
+    } else if (ops_out) {
+        rc = fail(ctx, AG2_ECAP, "ag2_extend_fetch_packed: need room for %ld columns, have %ld", (long)total, (long)cap_columns);
+    }
+    CK(cudaStreamSynchronize(st));
+    return rc;
+}
+
+// ---- host side of the packed output: the two ASCII strings of every record from the ops, the reads and the reference ----
+// code_char(get_dna_encode_table(c)) (MC/defs.cpp:3-36 + mecat2ref_aux.cpp:195-197): ACGT / acgt -> "ACGT", anything else -> 'A'
+static inline char expand_base(unsigned char c)
+{
+    switch (c) {
+    case 'A': case 'a': return 'A';
+    case 'C': case 'c': return 'C';
+    case 'G': case 'g': return 'G';
+    case 'T': case 't': return 'T';
+    default: return 'A';
+    }
+}
+// the read as reference_mapping hands it to extend_candidate on strand R (impl_large.cpp:799-833): reversed, upper-case ACGT
+// complemented, everything else as it is
+static inline char expand_base_rc(unsigned char c)
+{
+    switch (c) {
+    case 'A': return 'T';
+    case 'C': return 'G';
+    case 'G': return 'C';
+    case 'T': return 'A';
+    default: return expand_base(c);
+    }
+}
+
+int ag2_expand_alignments(const ag2_record *rec, int64_t n, const uint32_t *ops, const char *read_bases, const int64_t *read_offs,
+                          const char *ref, char *qaln_out, char *saln_out, int threads)
+{
+    if (!rec || n < 0 || !ops || !read_bases || !read_offs || !ref || !qaln_out || !saln_out) return AG2_EINVAL;
+    if (threads < 1) threads = 1;
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; ++k) {
+            const ag2_record &r = rec[k];
+            if (!r.ok) continue;
+            const char *rd = read_bases + read_offs[r.read];
+            const int64_t rlen = read_offs[r.read + 1] - read_offs[r.read];
+            int64_t qi = r.qb, ti = r.sb;
+            char *q = qaln_out + r.aln_off, *t = saln_out + r.aln_off;
+            for (int64_t c = 0; c < r.aln_len; ++c) {
+                const int64_t col = r.aln_off + c;
+                const unsigned op = (ops[col >> 4] >> (2 * (col & 15))) & 3u;
+                if (op == 1) {
+                    q[c] = '-';
+                } else {
+                    q[c] = r.strand ? expand_base_rc((unsigned char)rd[rlen - 1 - qi]) : expand_base((unsigned char)rd[qi]);
+                    ++qi;
+                }
+                if (op == 2) {
+                    t[c] = '-';
+                } else {
+                    t[c] = expand_base((unsigned char)ref[ti]);
+                    ++ti;
+                }
+            }
+        }
+    };
+    if (threads == 1 || n < 2 * threads) {
+        work(0, n);
+    } else {
+        std::vector<std::thread> th;
+        for (int w = 0; w < threads; ++w) th.emplace_back(work, n * w / threads, n * (w + 1) / threads);
+        for (auto &x : th) x.join();
+    }
+    return AG2_OK;
+}
 
 // ---- index (A2-A4) ------------------------------------------------------------------------------
 static int scan_counts(ag2_ctx *ctx, const int32_t *cnt, uint32_t *off, int64_t *total_out)
@@ -2144,6 +2314,32 @@ int ag2_map_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_
         rc = fail(ctx, AG2_ECAP, "ag2_map_fetch: need %ld bytes per string, have %ld", (long)ctx->out_total, (long)aln_cap);
     }
     CK(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+// ag2_map_fetch with the alignments as 2-bit ops (see ag2_xdrop_extend_batch_packed)
+int ag2_map_fetch_packed(ag2_ctx *ctx, ag2_record *rec_out, uint32_t *ops_out, int64_t cap_columns, int64_t *columns_used)
+{
+    if (!ctx || !rec_out) return fail(ctx, AG2_EINVAL, "ag2_map_fetch_packed: bad argument");
+    if (!ctx->mapped) return fail(ctx, AG2_ESTATE, "ag2_map_fetch_packed: call ag2_map_reads first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t total = ctx->out_total, words = (total + 15) >> 4;
+    CK(cudaMemcpyAsync(rec_out, ctx->map_out_rec.p, (size_t)ctx->map_n_out * sizeof(Record), cudaMemcpyDeviceToHost, st));
+    if (columns_used) *columns_used = total;
+    int rc = AG2_OK;
+    if (ops_out && cap_columns >= total) {
+        RESERVE(ctx->out_ops, (size_t)(words + 8) * 4);
+        if (words > 0) {
+            pack_ops_kernel<<<grid_for(words, 256, ctx->sm_count), 256, 0, st>>>((const char *)ctx->out_q.p, (const char *)ctx->out_t.p, 0, words, total,
+                                                                                (uint32_t *)ctx->out_ops.p);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(ops_out, ctx->out_ops.p, (size_t)words * 4, cudaMemcpyDeviceToHost, st));
+        }
+    } else if (ops_out) {
+        rc = fail(ctx, AG2_ECAP, "ag2_map_fetch_packed: need room for %ld columns, have %ld", (long)total, (long)cap_columns);
+    }
+    CK(cudaStreamSynchronize(st));
     return rc;
 }
 

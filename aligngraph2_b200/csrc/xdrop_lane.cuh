@@ -80,7 +80,7 @@ struct LaneArgs {
     // (xdrop_pair.cuh); all null = off
     int32_t *defer_queue;    // preset to -1
     LaneResume *defer_resume;
-    unsigned int *defer_ctl; // [0] slots reserved, [1] slots claimed, [2] warps in their main phase
+    unsigned int *defer_ctl; // [0] slots reserved, [1] tickets taken, [2] warps in their main phase
 };
 
 // Hand a direction over: the payload first, then -- fenced -- the queue entry, which a concurrently running consumer

@@ -598,16 +598,18 @@ __device__ __forceinline__ void pair_pause()
 // empty.  So a direction that reaches such a block (g.defer_queue set) is saved and put on a second queue, and the warps
 // take that queue when their main work is done: rounds of long last blocks only, one block per direction -- which also
 // makes the end of the launch fine-grained.  A warp takes deferred work only once none of its lanes can still produce
-// some (no waiting inside a warp on its own lanes), and never blocks: an entry is claimed by compare-and-swap once it is
-// published, otherwise looked at again in the next round.
+// some (no waiting inside a warp on its own lanes), and never blocks on a ticket: what is not published yet is looked at
+// again in the next round.
 __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8_t *scratch)
 {
     LaneChain s[2];
     s[0].chain = s[1].chain = -1;
     const PairScratch ps[2] = {pair_scratch(scratch, tid, 0), pair_scratch(scratch, tid, 1)}; // scratch = the CTA's
     unsigned long long cells = 0, rows = 0, blocks = 0, handed = 0;
-    bool drained = false, drained2 = g.defer_queue == nullptr, warp_main_done = false;
+    bool drained = false, warp_main_done = false;
     unsigned from_defer = 0;            // bit h: slot h runs a deferred direction
+    unsigned done2 = g.defer_queue ? 0u : 3u;   // bit h: slot h will get nothing more from the deferred queue
+    long long ticket[2] = {-1, -1};     // ticket of the deferred queue not yet served
     if (g.defer_queue && (tid & 31) == 0) atomicAdd(g.defer_ctl + 2, 1u);   // one more warp in its main phase
     for (;;) {
         if (!warp_main_done && g.defer_queue) {
@@ -643,22 +645,24 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
                     } else {
                         drained = true;
                     }
-                } else if (s[h].chain < 0 && warp_main_done && !drained2) {
-                    // claim the next deferred direction if one is there (no ticket is taken in advance: a warp that leaves
-                    // holds nothing back).  Nothing there and no warp of the launch in its main phase: this thread is done --
-                    // CTAs that start later, should the grid not be resident at once, serve their own deferrals.
-                    const unsigned t = pair_vol_u32(g.defer_ctl + 1);
-                    if (t < pair_vol_u32(g.defer_ctl)) {
-                        const int32_t ch = *reinterpret_cast<const volatile int32_t *>(g.defer_queue + t);
-                        if (ch >= 0 && atomicCAS(g.defer_ctl + 1, t, t + 1u) == t) {      // published, and ours
+                } else if (s[h].chain < 0 && warp_main_done && !(done2 & (1u << h))) {
+                    // A ticket of the deferred queue (fetch-and-add: compare-and-swap claims serialised the 130 000 resident
+                    // threads on one word -- 385 -> 633 ms).  The ticket is kept until its entry is published or until it is
+                    // known to lie behind the last entry: no warp of the launch in its main phase (the main queue is empty
+                    // by then -- this warp drained it -- so a CTA that starts later cannot defer anything).
+                    if (ticket[h] < 0) ticket[h] = (long long)atomicAdd(g.defer_ctl + 1, 1u);
+                    if ((unsigned long long)ticket[h] < pair_vol_u32(g.defer_ctl)) {
+                        const int32_t ch = *reinterpret_cast<const volatile int32_t *>(g.defer_queue + ticket[h]);
+                        if (ch >= 0) {      // published
                             __threadfence();
                             lane_start_chain(g, ch, s[h]);
-                            lane_resume(s[h], g.defer_resume[t]);
+                            lane_resume(s[h], g.defer_resume[ticket[h]]);
                             from_defer |= 1u << h;
+                            ticket[h] = -1;
                         }
                     } else if (pair_vol_u32(g.defer_ctl + 2) == 0) {
                         __threadfence();
-                        if (pair_vol_u32(g.defer_ctl + 1) >= pair_vol_u32(g.defer_ctl)) drained2 = true;
+                        if ((unsigned long long)ticket[h] >= pair_vol_u32(g.defer_ctl)) done2 |= 1u << h;
                     }
                 }
                 if (s[h].chain < 0) break;
@@ -684,7 +688,7 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
                 break;
             }
         }
-        if (!__any_sync(kFull, s[0].chain >= 0 || s[1].chain >= 0 || !drained || !drained2)) break;
+        if (!__any_sync(kFull, s[0].chain >= 0 || s[1].chain >= 0 || !drained || done2 != 3u)) break;
         PES(if (tid == 0) g_pes.rounds++;
             g_pes.dir_rounds += (io.M[0] > 0) + (io.M[1] > 0);)
         if (__any_sync(kFull, io.M[0] > 0 || io.M[1] > 0)) pair_dp(sm, tid, ps[0], ps[1], io);

@@ -39,9 +39,9 @@ class MapStats(C.Structure):
 
 EXPORTS = [
     "ag2_device_count", "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load", "ag2_reads_load_async", "ag2_reads_wait",
-    "ag2_xdrop_extend_batch", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
+    "ag2_xdrop_extend_batch", "ag2_xdrop_extend_batch_packed", "ag2_extend_fetch_packed", "ag2_expand_alignments", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
     "ag2_ctx_stream", "ag2_index_build", "ag2_index_fetch", "ag2_seed_candidates",
-    "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch", "ag2_map_get_stats",
+    "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch", "ag2_map_fetch_packed", "ag2_map_get_stats",
     "ag2_kmer_begin", "ag2_kmer_add_reads", "ag2_kmer_solid", "ag2_kmer_fetch",
 ]
 
@@ -75,6 +75,9 @@ def load() -> C.CDLL:
     L.ag2_reads_load_async.argtypes = [vp, vp, vp, i64]
     L.ag2_reads_wait.argtypes = [vp]
     L.ag2_xdrop_extend_batch.argtypes = [vp, vp, i64, vp, vp, vp, i64, C.POINTER(i64)]
+    L.ag2_xdrop_extend_batch_packed.argtypes = [vp, vp, i64, vp, vp, i64, C.POINTER(i64)]
+    L.ag2_extend_fetch_packed.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
+    L.ag2_expand_alignments.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i32]
     L.ag2_extend_upload.argtypes = [vp, vp, i64]
     L.ag2_extend_run.argtypes = [vp]
     L.ag2_extend_fetch.argtypes = [vp, vp, vp, vp, i64, C.POINTER(i64)]
@@ -85,6 +88,7 @@ def load() -> C.CDLL:
     L.ag2_extend_upload_from_seeds.argtypes = [vp, i32, C.POINTER(i64)]
     L.ag2_map_reads.argtypes = [vp, i32, i32, C.POINTER(i64)]
     L.ag2_map_fetch.argtypes = [vp, vp, vp, vp, i64, C.POINTER(i64)]
+    L.ag2_map_fetch_packed.argtypes = [vp, vp, vp, i64, C.POINTER(i64)]
     L.ag2_map_get_stats.argtypes = [vp, C.POINTER(MapStats)]
     L.ag2_kmer_begin.argtypes = [vp, i32]
     L.ag2_kmer_add_reads.argtypes = [vp]

@@ -169,6 +169,13 @@ class Mecat2RefDevice:
         self._check(self._L.ag2_map_fetch(self._ctx, rec.ctypes.data, q, t, cap, C.byref(used)), "ag2_map_fetch")
         return used.value
 
+    def map_fetch_packed_into(self, rec: np.ndarray, ops_out: np.ndarray) -> int:
+        """ag2_map_fetch_packed into caller-owned buffers (ops_out: uint32 words, 16 columns each); returns the columns used."""
+        used = C.c_int64()
+        self._check(self._L.ag2_map_fetch_packed(self._ctx, rec.ctypes.data, ops_out.ctypes.data, ops_out.size * 16, C.byref(used)),
+                    "ag2_map_fetch_packed")
+        return used.value
+
     def map_stats(self) -> dict:
         s = MapStats()
         self._check(self._L.ag2_map_get_stats(self._ctx, C.byref(s)), "ag2_map_get_stats")
@@ -231,6 +238,36 @@ class Mecat2RefDevice:
                                                    qaln_out.ctypes.data, saln_out.ctypes.data, qaln_out.size,
                                                    C.byref(used)), "ag2_xdrop_extend_batch")
         return used.value
+
+    def extend_batch_packed_into(self, cand: np.ndarray, rec: np.ndarray, ops_out: np.ndarray) -> int:
+        """ag2_xdrop_extend_batch_packed: records + 2-bit alignment ops (uint32 words, 16 columns each) into caller-owned host
+        buffers; returns the columns used."""
+        used = C.c_int64()
+        self._check(self._L.ag2_xdrop_extend_batch_packed(self._ctx, cand.ctypes.data, cand.size, rec.ctypes.data, ops_out.ctypes.data,
+                                                          ops_out.size * 16, C.byref(used)), "ag2_xdrop_extend_batch_packed")
+        return used.value
+
+    def fetch_packed(self, n: int):
+        """ag2_extend_fetch_packed after run(): (records, ops words, columns)."""
+        rec = np.zeros(n, dtype=RECORD_DTYPE)
+        used = C.c_int64()
+        self._check(self._L.ag2_extend_fetch_packed(self._ctx, rec.ctypes.data, None, 0, C.byref(used)), "ag2_extend_fetch_packed")
+        ops = np.zeros((used.value + 15) // 16 + 1, dtype=np.uint32)
+        self._check(self._L.ag2_extend_fetch_packed(self._ctx, rec.ctypes.data, ops.ctypes.data, ops.size * 16, C.byref(used)),
+                    "ag2_extend_fetch_packed")
+        return rec, ops, used.value
+
+    def expand_alignments(self, rec: np.ndarray, ops: np.ndarray, bases: np.ndarray, offsets: np.ndarray, ref: np.ndarray, columns: int,
+                          threads: int = 4):
+        """ag2_expand_alignments (host only): the two ASCII strings of every ok record from the ops."""
+        qa = np.zeros(max(columns, 1), dtype=np.uint8)
+        sa = np.zeros(max(columns, 1), dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        rc = self._L.ag2_expand_alignments(rec.ctypes.data, rec.size, ops.ctypes.data, bases.ctypes.data, offsets.ctypes.data,
+                                           ref.ctypes.data, qa.ctypes.data, sa.ctypes.data, threads)
+        if rc != 0:
+            raise Ag2Error(f"ag2_expand_alignments: {_lib.ERRORS.get(rc, rc)}")
+        return qa, sa
 
     def upload_candidates(self, cand: np.ndarray) -> None:
         cand = np.ascontiguousarray(cand, dtype=CANDIDATE_DTYPE)

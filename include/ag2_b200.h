@@ -110,6 +110,20 @@ int ag2_reads_wait(ag2_ctx *ctx);
 int ag2_xdrop_extend_batch(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out,
                            char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used);
 
+/* The same call with the alignments as 2-BIT OPS instead of two ASCII strings: column j of the pool is bits 2 * (j % 16) of
+ * ops_out[j / 16]; 0 = a base of both sequences, 1 = '-' in the read string, 2 = '-' in the reference string.  Together with
+ * the read and the reference (which the caller has) this is the whole content of TempResult::qmap / smap at an eighth of
+ * the bytes that cross PCIe; ag2_expand_alignments rebuilds the strings on the host when they are needed (bit-identical to
+ * what ag2_xdrop_extend_batch returns).  cap_columns = capacity of ops_out in columns (16 per word); aln_off of the
+ * records indexes columns; output chunks start on word boundaries, so *columns_used includes a little padding. */
+int ag2_xdrop_extend_batch_packed(ag2_ctx *ctx, const ag2_candidate *cand, int64_t n, ag2_record *rec_out, uint32_t *ops_out,
+                                  int64_t cap_columns, int64_t *columns_used);
+int ag2_extend_fetch_packed(ag2_ctx *ctx, ag2_record *rec_out, uint32_t *ops_out, int64_t cap_columns, int64_t *columns_used);
+/* Host-only (no GPU work): qaln_out / saln_out [aln_off, aln_off + aln_len) of every ok record from the ops, the ASCII reads
+ * of the batch (as given to ag2_reads_load) and the reference (as given to ag2_ref_load); `threads` host threads. */
+int ag2_expand_alignments(const ag2_record *rec, int64_t n, const uint32_t *ops, const char *read_bases, const int64_t *read_offs,
+                          const char *ref, char *qaln_out, char *saln_out, int threads);
+
 /* Split form of the same call for callers that keep inputs resident in HBM:
  * _upload copies candidates, _run launches the kernels on resident data (no host traffic),
  * _fetch copies records and strings back. */
@@ -172,6 +186,8 @@ typedef struct ag2_map_stats {
 } ag2_map_stats;
 int ag2_map_get_stats(ag2_ctx *ctx, ag2_map_stats *out);
 int ag2_map_fetch(ag2_ctx *ctx, ag2_record *rec_out, char *qaln_out, char *saln_out, int64_t aln_cap, int64_t *aln_used);
+/* the same with the alignments as 2-bit ops (see ag2_xdrop_extend_batch_packed, ag2_expand_alignments) */
+int ag2_map_fetch_packed(ag2_ctx *ctx, ag2_record *rec_out, uint32_t *ops_out, int64_t cap_columns, int64_t *columns_used);
 
 /* ---- PAGraph kmer_counter (PAGraph/src/main/kmer_counter.cpp:19-96) ----
  * ag2_kmer_begin zeroes the 4^k abundance table (k <= 15); ag2_kmer_add_reads adds every k-mer of the loaded read

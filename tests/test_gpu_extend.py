@@ -233,3 +233,41 @@ def test_async_read_load_and_streamed_chunks(dev, monkeypatch, order, path):
         dev2.wait_reads()
     finally:
         dev2.close()
+
+
+@pytest.mark.parametrize("path", ["streamed", "chunked"])
+def test_packed_ops_expand_to_the_same_strings(dev, monkeypatch, path):
+    """ag2_xdrop_extend_batch_packed returns the alignments as 2-bit ops (an eighth of the bytes of the two ASCII strings);
+    ag2_expand_alignments rebuilds the strings on the host from the ops, the reads and the reference.  Both forms of the
+    host-buffer run, many output chunks, reads of both strands with soft-masked and N bases: the rebuilt strings must be the
+    strings of the plain call, byte for byte; so must the ops fetched after a resident run."""
+    from aligngraph2_b200.lib import RECORD_DTYPE
+    d = synth.make_batch_torch(77, 300_000, 300, 3000)
+    ref, bases, off = d["ref"].numpy(), d["bases"].numpy().copy(), d["offsets"].numpy()
+    rng = np.random.default_rng(2)
+    for k in rng.integers(0, bases.size, size=400):     # lower case and N: the reverse strand must not complement them
+        bases[k] = ord("N") if rng.random() < 0.3 else bases[k] | 0x20
+    cand = dev.make_candidates(np.arange(300), d["strand"].numpy(), d["loc1"].numpy(), d["loc2"].numpy(), score=3)
+    dev.load_reference(ref)
+    dev.load_reads(bases=bases, offsets=off)
+    rec, qa, sa = dev.extend(cand)
+    assert rec["ok"].mean() > 0.9
+    # resident run -> packed fetch
+    rec_p, ops_p, cols = dev.fetch_packed(300)
+    assert cols == qa.size and np.array_equal(rec_p, rec)
+    q2, s2 = dev.expand_alignments(rec_p, ops_p, bases, off, ref, cols)
+    assert np.array_equal(q2[:cols], qa) and np.array_equal(s2[:cols], sa)
+    # host-buffer run, packed
+    monkeypatch.setenv("AG2_E2E_PATH", path)
+    monkeypatch.setenv("AG2_WS_STREAMED", str(300_000))
+    rec3 = np.zeros(300, RECORD_DTYPE)
+    ops3 = np.zeros(qa.size // 16 + 4096, np.uint32)
+    dev.load_reads_async(bases, off)
+    used = dev.extend_batch_packed_into(cand, rec3, ops3)
+    assert used >= qa.size and used < qa.size + 16 * 300
+    same = [k for k in RECORD_DTYPE.names if k != "aln_off"]
+    assert all(np.array_equal(rec3[k], rec[k]) for k in same)       # chunks start on word boundaries: only aln_off may differ
+    q3, s3 = dev.expand_alignments(rec3, ops3, bases, off, ref, used, threads=3)
+    for i in np.nonzero(rec["ok"])[0]:
+        o, o3, m = int(rec[i]["aln_off"]), int(rec3[i]["aln_off"]), int(rec[i]["aln_len"])
+        assert q3[o3:o3 + m].tobytes() == qa[o:o + m].tobytes() and s3[o3:o3 + m].tobytes() == sa[o:o + m].tobytes(), i
