@@ -2378,6 +2378,40 @@ int ag2_kmer_add_reads(ag2_ctx *ctx)
     return AG2_OK;
 }
 
+// The histogram merge of the multi-GPU kmer_counter: every GPU counts the k-mers of its read batches into
+// its own 4^k table; dst += src, the kernel on dst's GPU reading src's table over NVLink peer memory (through a staging
+// copy when the two devices cannot access each other, a plain read when both contexts share a GPU).
+int ag2_kmer_merge(ag2_ctx *dst, ag2_ctx *src)
+{
+    ag2_ctx *ctx = dst;
+    if (!dst || !src || dst == src) return fail(ctx, AG2_EINVAL, "ag2_kmer_merge: bad argument");
+    if (!dst->km_k || dst->km_k != src->km_k) return fail(ctx, AG2_ESTATE, "ag2_kmer_merge: both contexts need ag2_kmer_begin with the same k");
+    const int64_t nbins = 1ll << (2 * dst->km_k);
+    CK(cudaSetDevice(src->device));
+    CK(cudaStreamSynchronize(src->stream));
+    CK(cudaSetDevice(dst->device));
+    const uint32_t *from = (const uint32_t *)src->km_table.p;
+    DevBuf stage;
+    if (src->device != dst->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, dst->device, src->device));
+        if (can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, AG2_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        } else {
+            CK(cudaMalloc(&stage.p, (size_t)nbins * 4));
+            CK(cudaMemcpyPeerAsync(stage.p, dst->device, src->km_table.p, src->device, (size_t)nbins * 4, dst->stream));
+            from = (const uint32_t *)stage.p;
+        }
+    }
+    kmer_table_add_kernel<<<grid_for(nbins / 4, 256, dst->sm_count), 256, 0, dst->stream>>>((uint32_t *)dst->km_table.p, from, nbins);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(dst->stream));
+    if (stage.p) cudaFree(stage.p);
+    return AG2_OK;
+}
+
 int ag2_kmer_solid(ag2_ctx *ctx, double threshold, int64_t *min_abundance, int64_t *n_solid)
 {
     if (!ctx || !ctx->km_k) return fail(ctx, AG2_ESTATE, "ag2_kmer_solid: call ag2_kmer_begin first");

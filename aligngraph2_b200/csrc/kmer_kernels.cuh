@@ -82,4 +82,17 @@ __global__ void solid_scatter_kernel(const int32_t *__restrict__ flags, const ui
         if (flags[i]) out[out_base + offs[i]] = (uint64_t)(first + i);
 }
 
+// dst[i] += src[i]: the sum of the per-GPU abundance tables; src may be peer memory
+__global__ void kmer_table_add_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int64_t n)
+{
+    const int64_t n4 = n >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 a = reinterpret_cast<uint4 *>(dst)[i];
+        const uint4 b = reinterpret_cast<const uint4 *>(src)[i];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        reinterpret_cast<uint4 *>(dst)[i] = a;
+    }
+    for (int64_t i = (n4 << 2) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
 } // namespace ag2

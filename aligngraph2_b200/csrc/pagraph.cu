@@ -830,6 +830,177 @@ int ag2_pg_import_dev(ag2_pg* pg, int64_t n_tuples, void* const* tuple_dev3, int
     return AG2_OK;
 }
 
+// The one exchange step of the graph build between the GPUs of ONE process: every handle has extracted the
+// tuples and edges of its contiguous read range; each stream is partitioned stably by the owner of its vertex and every
+// (rank, owner) segment is copied straight into the owner's receive buffer at its place in rank order -- peer copies over
+// NVLink (cudaMemcpyPeerAsync; a plain device copy when two handles share a GPU), no host staging, no collective library.
+// Rank order is the global read order, so the owner's first-fit join sees the items as the one-GPU build does.
+int ag2_pg_group_exchange(ag2_pg* const* pgs, int n)
+{
+    if (!pgs || n < 1) return AG2_EINVAL;
+    for (int r = 0; r < n; ++r)
+        if (!pgs[r] || !pgs[r]->have_streams) return fail(pgs[r], AG2_ESTATE, "ag2_pg_group_exchange: handle %d has no streams (call ag2_pg_extract)", r);
+    if (n == 1) return AG2_OK;
+    ag2_pg* pg = pgs[0];   // errors are reported on the first handle
+    std::vector<std::vector<int64_t>> counts((size_t)n, std::vector<int64_t>(2 * (size_t)n));
+    for (int r = 0; r < n; ++r) {
+        const int rc = ag2_pg_partition(pgs[r], n, counts[(size_t)r].data());
+        if (rc != AG2_OK) {
+            if (r) fail(pg, rc, "ag2_pg_group_exchange: partition on handle %d: %s", r, pgs[r]->err.c_str());
+            return rc;
+        }
+    }
+    for (int a = 0; a < n; ++a)       // peer access both ways between distinct devices
+        for (int b = 0; b < n; ++b) {
+            if (pgs[a]->device == pgs[b]->device) continue;
+            int can = 0;
+            PG_CUDA(cudaDeviceCanAccessPeer(&can, pgs[a]->device, pgs[b]->device));
+            if (!can) continue;       // cudaMemcpyPeerAsync then stages through the host by itself
+            PG_CUDA(cudaSetDevice(pgs[a]->device));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(pgs[b]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(pg, AG2_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    struct Recv {
+        Dev<uint32_t> a, b, c, d, e;
+        Dev<int32_t> f;
+        int64_t nt = 0, ne = 0;
+    };
+    std::vector<Recv> recv((size_t)n);
+    for (int o = 0; o < n; ++o) {
+        Recv& R = recv[(size_t)o];
+        for (int r = 0; r < n; ++r) {
+            R.nt += counts[(size_t)r][(size_t)o];
+            R.ne += counts[(size_t)r][(size_t)(n + o)];
+        }
+        if (R.nt >= 0xffffffffll || R.ne >= 0xffffffffll) return fail(pg, AG2_ECAP, "ag2_pg_group_exchange: streams exceed the 32-bit index");
+        PG_CUDA(cudaSetDevice(pgs[o]->device));
+        PG_CUDA(R.a.alloc(R.nt));
+        PG_CUDA(R.b.alloc(R.nt));
+        PG_CUDA(R.c.alloc(R.nt));
+        PG_CUDA(R.d.alloc(R.ne));
+        PG_CUDA(R.e.alloc(R.ne));
+        PG_CUDA(R.f.alloc(R.ne));
+    }
+    for (int r = 0; r < n; ++r) {     // rank r pushes its segments, on its own stream
+        ag2_pg* S = pgs[r];
+        PG_CUDA(cudaSetDevice(S->device));
+        int64_t st = 0, se = 0;       // start of owner o's segment in r's partitioned streams
+        for (int o = 0; o < n; ++o) {
+            const int64_t ct = counts[(size_t)r][(size_t)o], ce = counts[(size_t)r][(size_t)(n + o)];
+            int64_t dt = 0, de = 0;   // its place in the owner's buffers: behind the lower ranks
+            for (int q = 0; q < r; ++q) {
+                dt += counts[(size_t)q][(size_t)o];
+                de += counts[(size_t)q][(size_t)(n + o)];
+            }
+            Recv& R = recv[(size_t)o];
+            const int dd = pgs[o]->device, sd = S->device;
+            if (ct) {
+                PG_CUDA(cudaMemcpyPeerAsync(R.a.p + dt, dd, S->t_vertex.p + st, sd, (size_t)ct * 4, S->stream));
+                PG_CUDA(cudaMemcpyPeerAsync(R.b.p + dt, dd, S->t_ctg.p + st, sd, (size_t)ct * 4, S->stream));
+                PG_CUDA(cudaMemcpyPeerAsync(R.c.p + dt, dd, S->t_ref.p + st, sd, (size_t)ct * 4, S->stream));
+            }
+            if (ce) {
+                PG_CUDA(cudaMemcpyPeerAsync(R.d.p + de, dd, S->e_from.p + se, sd, (size_t)ce * 4, S->stream));
+                PG_CUDA(cudaMemcpyPeerAsync(R.e.p + de, dd, S->e_to.p + se, sd, (size_t)ce * 4, S->stream));
+                PG_CUDA(cudaMemcpyPeerAsync(R.f.p + de, dd, S->e_step.p + se, sd, (size_t)ce * 4, S->stream));
+            }
+            st += ct;
+            se += ce;
+        }
+    }
+    for (int r = 0; r < n; ++r) {
+        PG_CUDA(cudaSetDevice(pgs[r]->device));
+        PG_CUDA(cudaStreamSynchronize(pgs[r]->stream));
+    }
+    for (int o = 0; o < n; ++o) {     // the received streams replace the extracted ones
+        ag2_pg* D = pgs[o];
+        Recv& R = recv[(size_t)o];
+        PG_CUDA(cudaSetDevice(D->device));
+        D->t_vertex.swap(R.a);
+        D->t_ctg.swap(R.b);
+        D->t_ref.swap(R.c);
+        D->e_from.swap(R.d);
+        D->e_to.swap(R.e);
+        D->e_step.swap(R.f);
+        D->n_tuples = R.nt;
+        D->n_edges = R.ne;
+        D->have_graph = false;
+        R.a.release(); R.b.release(); R.c.release(); R.d.release(); R.e.release(); R.f.release();   // on D's device
+    }
+    return AG2_OK;
+}
+
+// The merge of the per-GPU vertex tables before the traversal, into handle 0: every handle holds the CSR of the
+// vertices it owns (the others empty), owner ranges ascend with the handle index, so the merged payload is the
+// concatenation in handle order and the merged offsets are the element-wise sums -- peer copies over NVLink plus one add
+// kernel per array, no host staging.  Handle 0 then answers ag2_pg_graph_fetch / ag2_pg_job_travel / ag2_pg_job_dump for
+// the whole graph.
+int ag2_pg_group_gather(ag2_pg* const* pgs, int n)
+{
+    if (!pgs || n < 1 || !pgs[0]) return AG2_EINVAL;
+    ag2_pg* pg = pgs[0];
+    for (int r = 0; r < n; ++r)
+        if (!pgs[r] || !pgs[r]->have_graph) return fail(pg, AG2_ESTATE, "ag2_pg_group_gather: handle %d has no graph (call ag2_pg_join)", r);
+    if (n == 1) return AG2_OK;
+    const int64_t nv = pg->n_vertices;
+    int64_t npos = 0, nedge = 0;
+    for (int r = 0; r < n; ++r) {
+        if (pgs[r]->n_vertices != nv) return fail(pg, AG2_EINVAL, "ag2_pg_group_gather: handles differ in their vertex sets");
+        npos += pgs[r]->g_npos;
+        nedge += pgs[r]->g_nedge;
+    }
+    for (int r = 0; r < n; ++r) {   // the payload copies read what the join of every handle wrote
+        PG_CUDA(cudaSetDevice(pgs[r]->device));
+        PG_CUDA(cudaStreamSynchronize(pgs[r]->stream));
+    }
+    PG_CUDA(cudaSetDevice(pg->device));
+    Dev<uint32_t> ctg, ref, eto;
+    Dev<uint16_t> cnt;
+    Dev<int32_t> estep;
+    Dev<unsigned long long> tmp;
+    PG_CUDA(ctg.alloc(npos));
+    PG_CUDA(ref.alloc(npos));
+    PG_CUDA(cnt.alloc(npos));
+    PG_CUDA(eto.alloc(nedge));
+    PG_CUDA(estep.alloc(nedge));
+    PG_CUDA(tmp.alloc(nv + 1));
+    int64_t bp = 0, be = 0;
+    for (int r = 0; r < n; ++r) {
+        ag2_pg* S = pgs[r];
+        const int sd = S->device, dd = pg->device;
+        if (S->g_npos) {
+            PG_CUDA(cudaMemcpyPeerAsync(ctg.p + bp, dd, S->g_ctg.p, sd, (size_t)S->g_npos * 4, pg->stream));
+            PG_CUDA(cudaMemcpyPeerAsync(ref.p + bp, dd, S->g_ref.p, sd, (size_t)S->g_npos * 4, pg->stream));
+            PG_CUDA(cudaMemcpyPeerAsync(cnt.p + bp, dd, S->g_cnt.p, sd, (size_t)S->g_npos * 2, pg->stream));
+        }
+        if (S->g_nedge) {
+            PG_CUDA(cudaMemcpyPeerAsync(eto.p + be, dd, S->g_edge_to.p, sd, (size_t)S->g_nedge * 4, pg->stream));
+            PG_CUDA(cudaMemcpyPeerAsync(estep.p + be, dd, S->g_edge_step.p, sd, (size_t)S->g_nedge * 4, pg->stream));
+        }
+        bp += S->g_npos;
+        be += S->g_nedge;
+        if (r > 0) {
+            PG_CUDA(cudaMemcpyPeerAsync(tmp.p, dd, S->g_pos_off.p, sd, (size_t)(nv + 1) * 8, pg->stream));
+            pg_add_u64_kernel<<<grid_for(nv + 1), 256, 0, pg->stream>>>(pg->g_pos_off.p, tmp.p, nv + 1);
+            PG_CUDA(cudaMemcpyPeerAsync(tmp.p, dd, S->g_edge_off.p, sd, (size_t)(nv + 1) * 8, pg->stream));
+            pg_add_u64_kernel<<<grid_for(nv + 1), 256, 0, pg->stream>>>(pg->g_edge_off.p, tmp.p, nv + 1);
+        }
+    }
+    PG_CUDA(cudaStreamSynchronize(pg->stream));
+    PG_CUDA(cudaGetLastError());
+    pg->g_ctg.swap(ctg);
+    pg->g_ref.swap(ref);
+    pg->g_cnt.swap(cnt);
+    pg->g_edge_to.swap(eto);
+    pg->g_edge_step.swap(estep);
+    pg->g_npos = npos;
+    pg->g_nedge = nedge;
+    pg->stats.positions = npos;
+    pg->stats.edges = nedge;
+    return AG2_OK;
+}
+
 int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
 {
     if (!pg || !params) return fail(pg, AG2_EINVAL, "ag2_pg_join: bad arguments");

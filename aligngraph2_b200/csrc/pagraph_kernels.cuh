@@ -511,6 +511,12 @@ __global__ void pg_edge_scatter_kernel(const unsigned long long* __restrict__ fr
 }
 
 // ---- multi-GPU: owner of a vertex, gathers ------------------------------------------------------------------------------
+// acc[i] += add[i] (offset arrays of the per-GPU tables: element-wise sums are the merged offsets)
+__global__ void pg_add_u64_kernel(unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ add, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc[i] += add[i];
+}
+
 __global__ void pg_owner_kernel(const uint32_t* __restrict__ vertex, int64_t n, uint32_t per_owner, uint32_t* __restrict__ owner,
                                 uint32_t* __restrict__ index, unsigned long long* __restrict__ hist)
 {

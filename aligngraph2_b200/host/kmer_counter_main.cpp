@@ -6,6 +6,7 @@
 // thread-strided order; the only consumer, FileKmerIterator -> PABruijnGraph, sorts it).  -t, -p and -s are accepted
 // and have no effect here.  No CPU fallback: without a GPU the program exits 1.
 #include "../../include/ag2_b200.h"
+#include "shard_split.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -79,26 +80,47 @@ int main(int argc, char **argv)
         usage();
         return 1;
     }
-    ag2_ctx *ctx = nullptr;
-    int rc = ag2_ctx_create(0, &ctx);
-    if (rc != AG2_OK) {
+    // The GPUs the counting runs on: all visible devices or the list AG2_DEVICES names; every read batch
+    // goes to the next device in turn, each device counts into its own 4^k table, the tables are summed on the first
+    // (ag2_kmer_merge, NVLink peer reads) before the cut.
+    std::vector<int> devs;
+    if (const char *e = getenv("AG2_DEVICES")) {
+        devs = ag2host::parse_device_list(e);
+    } else {
+        int nd = 0;
+        if (ag2_device_count(&nd) == AG2_OK)
+            for (int d = 0; d < nd; ++d) devs.push_back(d);
+    }
+    std::vector<ag2_ctx *> ctxs;
+    int rc = AG2_OK;
+    for (int d : devs) {
+        ag2_ctx *c = nullptr;
+        if ((rc = ag2_ctx_create(d, &c)) == AG2_OK) ctxs.push_back(c);
+    }
+    if (ctxs.empty()) {
         fprintf(stderr, "kmer_counter (aligngraph2_b200): no usable CUDA device (%d); there is no CPU path\n", rc);
         return 1;
     }
-    if ((rc = ag2_kmer_begin(ctx, (int)a.k)) != AG2_OK) die(ctx, "ag2_kmer_begin", rc);
+    ag2_ctx *ctx = ctxs[0];
+    for (ag2_ctx *c : ctxs)
+        if ((rc = ag2_kmer_begin(c, (int)a.k)) != AG2_OK) die(c, "ag2_kmer_begin", rc);
+    size_t turn = 0;
 
     // SeqHelper::autoLoadFromFile (PAGraph/src/tools/seq/SeqHelper.cpp:8-97): type from the first character
     Batch b;
+    size_t batch_bytes = (size_t)1 << 30;
+    if (const char *e = getenv("AG2_KMER_BATCH_BYTES")) batch_bytes = (size_t)std::max(1ll, atoll(e));   // test knob: many small batches
     auto flush = [&]() {
         if (b.empty()) return;
-        if ((rc = ag2_reads_load(ctx, b.bases.data(), b.offs.data(), (int64_t)b.offs.size() - 1)) != AG2_OK) die(ctx, "ag2_reads_load", rc);
-        if ((rc = ag2_kmer_add_reads(ctx)) != AG2_OK) die(ctx, "ag2_kmer_add_reads", rc);
+        ag2_ctx *c = ctxs[turn++ % ctxs.size()];
+        if ((rc = ag2_reads_load(c, b.bases.data(), b.offs.data(), (int64_t)b.offs.size() - 1)) != AG2_OK) die(c, "ag2_reads_load", rc);
+        if ((rc = ag2_kmer_add_reads(c)) != AG2_OK) die(c, "ag2_kmer_add_reads", rc);
         b.clear();
     };
     auto add = [&](const std::string &seq) {
         if (seq.empty()) return;
         b.add(seq);
-        if (b.bases.size() >= ((size_t)1 << 30)) flush();
+        if (b.bases.size() >= batch_bytes) flush();
     };
     {
         std::ifstream in(a.in);
@@ -130,6 +152,8 @@ int main(int argc, char **argv)
         }
     }
     flush();
+    for (size_t i = 1; i < ctxs.size(); ++i)
+        if ((rc = ag2_kmer_merge(ctx, ctxs[i])) != AG2_OK) die(ctx, "ag2_kmer_merge", rc);
     int64_t cut = 0, n = 0;
     if ((rc = ag2_kmer_solid(ctx, a.threshold, &cut, &n)) != AG2_OK) die(ctx, "ag2_kmer_solid", rc);
     std::vector<uint64_t> codes((size_t)n + 1);
@@ -139,6 +163,6 @@ int main(int argc, char **argv)
     of.write(reinterpret_cast<const char *>(&k), sizeof(size_t));
     of.write(reinterpret_cast<const char *>(codes.data()), (std::streamsize)((size_t)n * sizeof(uint64_t)));
     of.close();
-    ag2_ctx_destroy(ctx);
+    for (ag2_ctx *c : ctxs) ag2_ctx_destroy(c);
     return 0;
 }

@@ -10,11 +10,15 @@
 #include "../../include/ag2_b200.h"
 #include "../../include/ag2_pagraph.h"
 
+#include "shard_split.h"
+
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <vector>
 
 namespace {
 
@@ -69,13 +73,45 @@ int main(int argc, char** argv)
         usage();
         return 1;
     }
-    ag2_pg_job* job = nullptr;
-    int rc = ag2_pg_job_open(0, kmer.c_str(), ctg.c_str(), ref.c_str(), pre.c_str(), aln.c_str(), &job);
-    if (rc != AG2_OK) {
-        fprintf(stderr, "pagraph (aligngraph2_b200): %s (%d)\n", ag2_pg_job_error(job), rc);
-        ag2_pg_job_close(job);
-        return 1;
+    // The GPUs the graph build runs on: all visible devices, or the list AG2_DEVICES names (a device may be
+    // named twice: that is how the sharding is tested on a one-GPU box).  One job (its own copy of the inputs, one handle)
+    // per device; the reads of a block are sharded contiguously over them, ag2_pg_group_exchange moves the vertex tuples to
+    // their owners over NVLink, ag2_pg_group_gather merges the tables into the first job, which traverses.
+    std::vector<int> devs;
+    if (const char* e = getenv("AG2_DEVICES")) {
+        devs = ag2host::parse_device_list(e);
+    } else {
+        int nd = 0;
+        if (ag2_device_count(&nd) == AG2_OK)
+            for (int d = 0; d < nd; ++d) devs.push_back(d);
     }
+    if (devs.empty()) devs.push_back(0);   // ag2_pg_job_open then reports the missing device
+    const int world = (int)devs.size();
+    std::vector<ag2_pg_job*> jobs((size_t)world, nullptr);
+    std::vector<int> rcs((size_t)world, AG2_OK);
+    auto on_all = [&](auto f) {
+        if (world == 1) {
+            f(0);
+            return;
+        }
+        std::vector<std::thread> th;
+        for (int r = 0; r < world; ++r) th.emplace_back([&f, r] { f(r); });
+        for (auto& t : th) t.join();
+    };
+    auto close_all = [&] {
+        for (ag2_pg_job* j : jobs) ag2_pg_job_close(j);
+    };
+    on_all([&](int r) { rcs[(size_t)r] = ag2_pg_job_open(devs[(size_t)r], kmer.c_str(), ctg.c_str(), ref.c_str(), pre.c_str(), aln.c_str(), &jobs[(size_t)r]); });
+    int rc = AG2_OK;
+    for (int r = 0; r < world; ++r)
+        if (rcs[(size_t)r] != AG2_OK) {
+            fprintf(stderr, "pagraph (aligngraph2_b200): %s (%d)\n", ag2_pg_job_error(jobs[(size_t)r]), rcs[(size_t)r]);
+            close_all();
+            return 1;
+        }
+    ag2_pg_job* job = jobs[0];
+    std::vector<ag2_pg*> handles;
+    for (ag2_pg_job* j : jobs) handles.push_back(ag2_pg_job_handle(j));
     ag2_pg_params bp;
     ag2_pg_params_default(&bp);
     bp.epsilon = (int64_t)eps;
@@ -87,23 +123,43 @@ int main(int argc, char** argv)
     tp.threads = (int32_t)threads;
     auto fail = [&](const char* what) {
         fprintf(stderr, "pagraph (aligngraph2_b200): %s failed (%d): %s\n", what, rc, ag2_pg_job_error(job));
-        ag2_pg_job_close(job);
+        close_all();
         return 1;
+    };
+    auto fail_pg = [&](const char* what, int r) {
+        fprintf(stderr, "pagraph (aligngraph2_b200): %s failed on device %d (%d): %s\n", what, devs[(size_t)r], rcs[(size_t)r], ag2_pg_last_error(handles[(size_t)r]));
+        close_all();
+        return 1;
+    };
+    auto first_bad = [&] {
+        for (int r = 0; r < world; ++r)
+            if (rcs[(size_t)r] != AG2_OK) return r;
+        return -1;
     };
     for (int b = 0; b < ag2_pg_job_blocks(job); ++b) {
         std::cout << "Use Ref: " << ag2_pg_job_block_ref(job, b) << std::endl;
-        if ((rc = ag2_pg_job_load_block(job, b, 0, 1)) != AG2_OK) return fail("ag2_pg_job_load_block");
-        if ((rc = ag2_pg_build(ag2_pg_job_handle(job), &bp)) != AG2_OK) {
-            fprintf(stderr, "pagraph (aligngraph2_b200): ag2_pg_build failed (%d): %s\n", rc, ag2_pg_last_error(ag2_pg_job_handle(job)));
-            ag2_pg_job_close(job);
-            return 1;
+        on_all([&](int r) { rcs[(size_t)r] = ag2_pg_job_load_block(jobs[(size_t)r], b, r, world); });
+        if (int r = first_bad(); r >= 0) {
+            rc = rcs[(size_t)r];
+            job = jobs[(size_t)r];
+            return fail("ag2_pg_job_load_block");
+        }
+        if (world == 1) {
+            if ((rcs[0] = ag2_pg_build(handles[0], &bp)) != AG2_OK) return fail_pg("ag2_pg_build", 0);
+        } else {
+            on_all([&](int r) { rcs[(size_t)r] = ag2_pg_extract(handles[(size_t)r], &bp); });
+            if (int r = first_bad(); r >= 0) return fail_pg("ag2_pg_extract", r);
+            if ((rcs[0] = ag2_pg_group_exchange(handles.data(), world)) != AG2_OK) return fail_pg("ag2_pg_group_exchange", 0);
+            on_all([&](int r) { rcs[(size_t)r] = ag2_pg_join(handles[(size_t)r], &bp); });
+            if (int r = first_bad(); r >= 0) return fail_pg("ag2_pg_join", r);
+            if ((rcs[0] = ag2_pg_group_gather(handles.data(), world)) != AG2_OK) return fail_pg("ag2_pg_group_gather", 0);
         }
         ag2_pg_stats st;
-        ag2_pg_get_stats(ag2_pg_job_handle(job), &st);
+        ag2_pg_get_stats(handles[0], &st);
         std::cout << "\tmerge edge = " << st.edges << "\n\tmerge pos = " << st.positions << std::endl;
         if ((rc = ag2_pg_job_travel(job, b, &tp, out.c_str())) != AG2_OK) return fail("ag2_pg_job_travel");
     }
     if ((rc = ag2_pg_job_write_contig_list(job, out.c_str())) != AG2_OK) return fail("ag2_pg_job_write_contig_list");
-    ag2_pg_job_close(job);
+    close_all();
     return 0;
 }

@@ -42,7 +42,7 @@ EXPORTS = [
     "ag2_xdrop_extend_batch", "ag2_xdrop_extend_batch_packed", "ag2_extend_fetch_packed", "ag2_expand_alignments", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
     "ag2_ctx_stream", "ag2_index_build", "ag2_index_fetch", "ag2_seed_candidates",
     "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch", "ag2_map_fetch_packed", "ag2_map_get_stats",
-    "ag2_kmer_begin", "ag2_kmer_add_reads", "ag2_kmer_solid", "ag2_kmer_fetch",
+    "ag2_kmer_begin", "ag2_kmer_add_reads", "ag2_kmer_merge", "ag2_kmer_solid", "ag2_kmer_fetch",
 ]
 
 
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     L.ag2_map_get_stats.argtypes = [vp, C.POINTER(MapStats)]
     L.ag2_kmer_begin.argtypes = [vp, i32]
     L.ag2_kmer_add_reads.argtypes = [vp]
+    L.ag2_kmer_merge.argtypes = [vp, vp]
     L.ag2_kmer_solid.argtypes = [vp, C.c_double, C.POINTER(i64), C.POINTER(i64)]
     L.ag2_kmer_fetch.argtypes = [vp, vp, i64]
     L.ag2_ctx_stream.argtypes = [vp]

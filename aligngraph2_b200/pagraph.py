@@ -51,7 +51,7 @@ assert ALN_DTYPE.itemsize == 72
 EXPORTS = [
     "ag2_pg_create", "ag2_pg_destroy", "ag2_pg_last_error", "ag2_pg_params_default", "ag2_pg_set_kmers", "ag2_pg_fetch_codes",
     "ag2_pg_set_targets", "ag2_pg_set_reads", "ag2_pg_set_alignments", "ag2_pg_set_filters", "ag2_pg_build", "ag2_pg_extract",
-    "ag2_pg_partition", "ag2_pg_stream_dev", "ag2_pg_import_dev", "ag2_pg_join", "ag2_pg_get_stats", "ag2_pg_graph_fetch",
+    "ag2_pg_partition", "ag2_pg_stream_dev", "ag2_pg_import_dev", "ag2_pg_join", "ag2_pg_group_exchange", "ag2_pg_group_gather", "ag2_pg_get_stats", "ag2_pg_graph_fetch",
     "ag2_pg_stream", "ag2_pg_job_open", "ag2_pg_job_close", "ag2_pg_job_error", "ag2_pg_job_blocks", "ag2_pg_job_block_ref",
     "ag2_pg_job_handle", "ag2_pg_job_load_block", "ag2_pg_job_dump",
     "ag2_pg_travel_params_default", "ag2_pg_travel", "ag2_pg_job_travel", "ag2_pg_job_write_contig_list",
@@ -84,6 +84,8 @@ def _L():
     L.ag2_pg_partition.argtypes = [vp, i32, vp]
     L.ag2_pg_stream_dev.argtypes = [vp, C.POINTER(i64), vp, C.POINTER(i64), vp]
     L.ag2_pg_import_dev.argtypes = [vp, i64, vp, i64, vp]
+    L.ag2_pg_group_exchange.argtypes = [vp, i32]
+    L.ag2_pg_group_gather.argtypes = [vp, i32]
     L.ag2_pg_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.ag2_pg_graph_fetch.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, i64]
     L.ag2_pg_stream.argtypes = [vp]
@@ -330,6 +332,44 @@ def build_distributed(job: Job, block: int, params: Params, group=None) -> Stats
     torch.cuda.synchronize()
     job.import_streams(tup[0].numel(), [t.data_ptr() for t in tup], edg[0].numel(), [t.data_ptr() for t in edg])
     return job.join(params)
+
+
+def build_group(jobs, block: int, params: Params):
+    """The graph build over the GPUs of ONE process: jobs[r] (one per device; a device may appear twice) takes the r-th
+    contiguous range of the block's reads, extracts, and ag2_pg_group_exchange moves every (rank, owner) segment straight
+    into the owner's buffer with peer copies over NVLink; then every job joins its vertex range.  Returns the jobs' Stats."""
+    n = len(jobs)
+    for r, j in enumerate(jobs):
+        j.load_block(block, r, n)
+        j.extract(params)
+    if n > 1:
+        L = _L()
+        arr = (C.c_void_p * n)(*[j.pg for j in jobs])
+        rc = L.ag2_pg_group_exchange(arr, n)
+        if rc != 0:
+            raise _lib.Ag2Error(f"ag2_pg_group_exchange: {_lib.ERRORS.get(rc, rc)}: {L.ag2_pg_last_error(jobs[0].pg).decode(errors='replace')}")
+    return [j.join(params) for j in jobs]
+
+
+def gather_group(jobs) -> None:
+    """ag2_pg_group_gather: the per-GPU vertex tables merged into jobs[0] on the device (peer copies + offset sums)."""
+    n = len(jobs)
+    L = _L()
+    arr = (C.c_void_p * n)(*[j.pg for j in jobs])
+    rc = L.ag2_pg_group_gather(arr, n)
+    if rc != 0:
+        raise _lib.Ag2Error(f"ag2_pg_group_gather: {_lib.ERRORS.get(rc, rc)}: {L.ag2_pg_last_error(jobs[0].pg).decode(errors='replace')}")
+
+
+def merge_graphs(graphs) -> Graph:
+    """Graphs of the jobs of build_group / build_distributed (each holds the vertices its rank owns, the others empty):
+    owner ranges ascend with the rank, so the merged payload is the rank-order concatenation and the merged per-vertex
+    sizes are the element-wise sums."""
+    pos_n = sum(np.diff(g.pos_off) for g in graphs)
+    edge_n = sum(np.diff(g.edge_off) for g in graphs)
+    cat = lambda name: np.concatenate([getattr(g, name) for g in graphs])
+    return Graph(np.concatenate(([0], np.cumsum(pos_n))).astype(np.int64), cat("ctg"), cat("ref"), cat("count"),
+                 np.concatenate(([0], np.cumsum(edge_n))).astype(np.int64), cat("edge_to"), cat("edge_step"))
 
 
 def gather_graph(job: Job, group=None) -> Graph:

@@ -197,6 +197,9 @@ int ag2_map_fetch_packed(ag2_ctx *ctx, ag2_record *rec_out, uint32_t *ops_out, i
  * the order `kmer_counter -t 1` writes. */
 int ag2_kmer_begin(ag2_ctx *ctx, int k);
 int ag2_kmer_add_reads(ag2_ctx *ctx);
+/* dst's table += src's table (both after ag2_kmer_begin with the same k): the merge of the per-GPU histograms when the read
+ * batches were spread over several GPUs; reads src's table over NVLink peer memory. */
+int ag2_kmer_merge(ag2_ctx *dst, ag2_ctx *src);
 int ag2_kmer_solid(ag2_ctx *ctx, double threshold, int64_t *min_abundance, int64_t *n_solid);
 int ag2_kmer_fetch(ag2_ctx *ctx, uint64_t *codes_out, int64_t cap);
 

@@ -118,6 +118,15 @@ int ag2_pg_partition(ag2_pg *pg, int n_owners, int64_t *counts);
 int ag2_pg_stream_dev(ag2_pg *pg, int64_t *n_tuples, void **tuple_dev3, int64_t *n_edges, void **edge_dev3);
 int ag2_pg_import_dev(ag2_pg *pg, int64_t n_tuples, void *const *tuple_dev3, int64_t n_edges, void *const *edge_dev3);
 int ag2_pg_join(ag2_pg *pg, const ag2_pg_params *params);
+/* partition + exchange + import for the n handles of ONE process (one per GPU, reads sharded contiguously in handle
+ * order): every (rank, owner) segment goes straight into the owner's buffer by a peer copy over NVLink, no host staging.
+ * Then ag2_pg_join on every handle; handle o ends up with the vertices it owns, the others empty in its CSR.  (Across
+ * processes the same exchange is one NCCL all-to-all per array: aligngraph2_b200/pagraph.py::build_distributed.) */
+int ag2_pg_group_exchange(ag2_pg *const *pgs, int n);
+/* after ag2_pg_join on every handle: the merge of the per-GPU vertex tables into handle 0 (the all-gather before the
+ * traversal of SURVEY 8e, to the one rank that traverses): payload concatenated in handle order by peer copies, offsets
+ * summed.  Handle 0 then holds the whole graph; the others keep their part. */
+int ag2_pg_group_gather(ag2_pg *const *pgs, int n);
 
 int ag2_pg_get_stats(ag2_pg *pg, ag2_pg_stats *out);
 

@@ -120,6 +120,35 @@ def test_read_sharded_ranks_cover_the_graph(small):
     assert got == want, _explain(got, want)
 
 
+@pytest.mark.parametrize("n_handles", [2, 3])
+def test_group_exchange_in_one_process(small, n_handles):
+    """ag2_pg_group_exchange: the reads sharded over n handles of ONE process (one per visible GPU, round robin -- on a
+    one-GPU box they share the device and the peer copies are device copies), segments pushed straight into the owner's
+    buffers, every handle joins its vertex range; the merged tables must be the reference's dump."""
+    import torch
+    from aligngraph2_b200 import pagraph
+    want = open(os.path.join(small, "graph.txt"), "rb").read()
+    p = pagraph.default_params(10, 2)
+    ndev = max(1, torch.cuda.device_count())
+    j = lambda n: os.path.join(small, n)
+    jobs = [pagraph.Job(j("solid.bin"), j("ctg.fasta"), j("ref.fasta"), small, j("c2r.ref"), device=r % ndev) for r in range(n_handles)]
+    codes = jobs[0].codes()
+    got = b""
+    for b in range(jobs[0].n_blocks):
+        stats = pagraph.build_group(jobs, b, p)
+        assert sum(1 for st in stats if st.positions > 0) >= 2          # more than one owner really holds vertices
+        g = pagraph.merge_graphs([job.graph() for job in jobs])
+        got += pagraph.graph_dump_text(g, codes, b, jobs[0].block_ref(b))
+        # the same merge on the device, into handle 0 (what the multi-GPU `pagraph` executable traverses)
+        pagraph.gather_group(jobs)
+        jobs[0].dump(b, os.path.join(small, f"group{n_handles}.txt"), append=b > 0)
+    for job in jobs:
+        job.close()
+    assert got == want, _explain(got, want)
+    got2 = open(os.path.join(small, f"group{n_handles}.txt"), "rb").read()
+    assert got2 == want, _explain(got2, want)
+
+
 def test_two_gpus_nccl_exchange(small):
     """Reads sharded over 2 GPUs, NCCL all-to-all of the vertex tuples by owner, all-gather of the merged tables:
     the dump rank 0 writes equals the reference's.  Needs a 2-GPU box (gpurun --gpus 2)."""
@@ -185,6 +214,26 @@ def test_chain_fixture_graph_equals_reference_dump(chain):
     want = open(os.path.join(chain, "graph.txt"), "rb").read()
     got, _ = _gpu_dump(chain, "gpu.txt", 10, 2)
     assert got == want, _explain(got, want)
+
+
+@pytest.mark.parametrize("devices", ["0,0,0", None])
+def test_drop_in_pagraph_executable_sharded_over_devices(chain, devices):
+    """The same executable with the graph build sharded over several handles (AG2_DEVICES names GPU 0 three times on a
+    one-GPU box; None = every visible GPU): reads cut into contiguous ranges, ag2_pg_group_exchange, per-range joins,
+    ag2_pg_group_gather into the first handle, traversal there -- no file may differ from the one-GPU run's."""
+    import subprocess
+    from aligngraph2_b200 import build
+    build.build()
+    exe = build.build_host(name="pagraph")
+    out = os.path.join(chain, "exe_dev" + (devices or "all").replace(",", ""))
+    os.makedirs(out, exist_ok=True)
+    env = {k: v for k, v in os.environ.items() if k != "AG2_DEVICES"}
+    if devices:
+        env["AG2_DEVICES"] = devices
+    r = subprocess.run([exe, "-t", "1", "-r", "dummy", "-k", "solid.bin", "-c", "ctg.fasta", "-R", "ref.fasta", "-p", ".", "-a", "c2r.ref",
+                        "-o", out, "-r", "50", "--epsilon", "10", "-v", "2"], cwd=chain, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-2000:]
+    assert _compare_dirs(out, os.path.join(chain, "t1")) == []
 
 
 @pytest.mark.parametrize("threads", [1, 8])

@@ -88,3 +88,26 @@ def test_dropin_binary_matches_reference_binary(tmp_path):
     r = subprocess.run([exe, "-t", "8", "--in", "r.fq", "-o", "gpu.bin", "-k12"], cwd=tmp_path, capture_output=True)
     assert r.returncode == 0, r.stderr.decode()
     assert (tmp_path / "ref.bin").read_bytes() == (tmp_path / "gpu.bin").read_bytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0,0", None])
+def test_dropin_binary_sharded_over_devices(tmp_path, devices):
+    """the read batches go round robin over several contexts (AG2_DEVICES names GPU 0 three times on a one-GPU
+    box; None = every visible GPU), each counts into its own 4^k table, ag2_kmer_merge sums them over peer memory before the
+    cut.  The file must be the reference binary's."""
+    from aligngraph2_b200 import build
+    from oracle import binding
+    if not os.path.exists(binding.REF_KMER_COUNTER):
+        pytest.skip("oracle/_ref/kmer_counter not built on this box")
+    exe = build.build_host(name="kmer_counter")
+    bases, offs = _reads(seed=9, n=400, tl=4000)
+    _write_fastq(tmp_path / "r.fq", bases, offs)
+    subprocess.run([binding.REF_KMER_COUNTER, "-t", "1", "-i", "r.fq", "-o", "ref.bin", "-k", "12"], cwd=tmp_path, check=True)
+    env = {k: v for k, v in os.environ.items() if k != "AG2_DEVICES"}
+    env["AG2_KMER_BATCH_BYTES"] = "100000"      # ~ 25 reads per batch: every context gets several
+    if devices:
+        env["AG2_DEVICES"] = devices
+    r = subprocess.run([exe, "-t", "8", "-i", "r.fq", "-o", "gpu.bin", "-k", "12"], cwd=tmp_path, env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    assert (tmp_path / "ref.bin").read_bytes() == (tmp_path / "gpu.bin").read_bytes()
