@@ -1935,7 +1935,9 @@ static int seed_cap(const ag2_ctx *ctx, int pass, int tier)
 static int seed_cta_config(ag2_ctx *ctx, const void *kernel, int cap, size_t *smem_out, int *grid_out)
 {
     const size_t smem = seed_cta_smem_bytes(cap);
-    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the limit of the function, not of this launch: it is per-device state that the contexts of other host threads set too
+    // (the executables run one context per thread, possibly several on one GPU), so it is always the largest any launch asks for
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_cta_smem_bytes(kSeedCapMax)));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSeedCtaThreads, smem));
     if (occ < 1) return fail(ctx, AG2_ECUDA, "seeding kernel does not fit an SM (cap %d)", cap);

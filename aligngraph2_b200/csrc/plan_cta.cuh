@@ -108,6 +108,14 @@ __device__ void plan_cta_body(const PlanCtaArgs &a, uint8_t *smem)
     const int64_t zv = a.pass == 0 ? 1000 : 2000;
     const int block_bits = seed_block_bits(a.ix.ref_len, zv);
     uint32_t *pool = a.heavy_pool + (size_t)blockIdx.x * (a.cap / (kSM + 1) + 1) * kHeavyWords;
+    {
+        SeedCtaSmem sm = seed_cta_carve(smem, a.cap);
+        if (tid == 0) {
+            stage_barrier_init(sm.bar);
+            sm.misc[5] = 0;           // phase of the staging barrier
+        }
+        __syncthreads();
+    }
     for (;;) {
         SeedCtaSmem sm0 = seed_cta_carve(smem, a.cap);
         if (tid == 0) sm0.misc[3] = (int)atomicAdd(a.next, 1u);

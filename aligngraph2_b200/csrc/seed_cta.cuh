@@ -86,11 +86,12 @@ struct SeedCtaSmem {
     int *misc;
     int *tl_loc, *tl_seed, *tl_score;
     SeedCand *cands;
+    uint64_t *bar;                 // mbarrier of the read staging (TMA bulk copy)
 };
 
 __host__ __device__ __forceinline__ size_t seed_cta_smem_bytes(int cap)
 {
-    return (size_t)cap * 16 + kSeedBins * kSeedCtaWarps * 2 + 40 * 4 + 32 * 4 + 3 * 2 * kSM * 4 + (kMaxCand + 1) * sizeof(SeedCand) + 64;
+    return (size_t)cap * 16 + kSeedBins * kSeedCtaWarps * 2 + 40 * 4 + 32 * 4 + 3 * 2 * kSM * 4 + (kMaxCand + 1) * sizeof(SeedCand) + 16 + 64;
 }
 
 __device__ __forceinline__ SeedCtaSmem seed_cta_carve(uint8_t *p, int cap)
@@ -101,6 +102,8 @@ __device__ __forceinline__ SeedCtaSmem seed_cta_carve(uint8_t *p, int cap)
     uint8_t *q = reinterpret_cast<uint8_t *>(s.aux + cap);
     s.cands = reinterpret_cast<SeedCand *>(q);
     q += (kMaxCand + 1) * sizeof(SeedCand);
+    s.bar = reinterpret_cast<uint64_t *>(q);
+    q += 16;
     s.hist = reinterpret_cast<uint16_t *>(q);
     q += kSeedBins * kSeedCtaWarps * 2;
     s.wsum = reinterpret_cast<uint32_t *>(q);
@@ -242,18 +245,64 @@ __device__ uint64_t *sort_events(uint64_t *src, uint64_t *dst, int n, int lo, in
     return src;
 }
 
+// ---- the read's 2-bit codes and its "irregular base" mask, staged in shared memory by the TMA (1-D bulk copies that
+// complete on an mbarrier: one thread issues them, nobody's registers are involved) ----
+__device__ __forceinline__ void stage_barrier_init(uint64_t *bar)
+{
+#ifndef AG2_EMU
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+    *bar = 0;
+#endif
+}
+// thread 0: both copies, `bytes2` + `bytesi` (multiples of 16) expected on the barrier
+__device__ __forceinline__ void stage_issue(uint64_t *bar, void *dst2, const void *src2, unsigned bytes2, void *dsti, const void *srci, unsigned bytesi)
+{
+#ifndef AG2_EMU
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer was last written by ordinary stores (the previous sort)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes2 + bytesi) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(dst2)),
+                 "l"(src2), "r"(bytes2), "r"(b)
+                 : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"((unsigned)__cvta_generic_to_shared(dsti)),
+                 "l"(srci), "r"(bytesi), "r"(b)
+                 : "memory");
+#else
+    memcpy(dst2, src2, bytes2);
+    memcpy(dsti, srci, bytesi);
+    (void)bar;
+#endif
+}
+__device__ __forceinline__ void stage_wait(uint64_t *bar, unsigned parity)
+{
+#ifndef AG2_EMU
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tSTAGE_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra STAGE_WAIT;\n\t}" ::"r"(b), "r"(parity)
+                 : "memory");
+#else
+    (void)bar;
+    (void)parity;
+#endif
+}
+
 // 13 bases at oriented positions start .. start + 12 of a read strand as a seed code (atcttrans: A0 T1 C2 G3, first base
 // most significant), or -1 if one of them is not upper-case ACGT or lies behind the read (transnum_buchang :95-121).
-__device__ __forceinline__ int seed_code_fast(const uint32_t *reads2, const uint32_t *irr, int64_t roff, int rlen, int strand, int start)
+// roff2 / roffi: position of the read's first base in the `reads2` / `irr` arrays handed in (global: the same packed
+// offset; staged: the few bases the 16-byte aligned copies start early).
+__device__ __forceinline__ int seed_code_fast(const uint32_t *reads2, const uint32_t *irr, int64_t roff2, int64_t roffi, int rlen, int strand, int start)
 {
     if (start + kSeedLen > rlen) return -1;
-    const int64_t f0 = roff + (strand ? rlen - start - kSeedLen : start);   // lowest file position of the window
+    const int lo = strand ? rlen - start - kSeedLen : start;   // lowest file position of the window
     {
+        const int64_t f0 = roffi + lo;
         const int64_t w = f0 >> 5;
         const int sh = (int)(f0 & 31);
         const uint64_t bits = ((uint64_t)irr[w + 1] << 32 | irr[w]) >> sh;
         if (bits & 0x1fffu) return -1;
     }
+    const int64_t f0 = roff2 + lo;
     const int64_t w = f0 >> 4;
     const int sh = 2 * (int)(f0 & 15);
     uint32_t x = (uint32_t)((((uint64_t)reads2[w + 1] << 32) | reads2[w]) >> sh) & 0x3ffffffu;   // base f0 in bits 1:0
@@ -264,8 +313,8 @@ __device__ __forceinline__ int seed_code_fast(const uint32_t *reads2, const uint
         x = ((x & 0x1555555u) << 1) | ((x >> 1) & 0x1555555u);   // ... with the bits of every pair back in order
     }
     // A0 C1 G2 T3 -> A0 T1 C2 G3: (hi, lo) -> (hi ^ lo, hi)
-    const uint32_t hi = (x >> 1) & 0x1555555u, lo = x & 0x1555555u;
-    return (int)(((hi ^ lo) << 1) | hi);
+    const uint32_t hi = (x >> 1) & 0x1555555u, lo2 = x & 0x1555555u;
+    return (int)(((hi ^ lo2) << 1) | hi);
 }
 
 // find_location3's votes (:614-627) for entry x of the pooled list, by the thread that owns x
@@ -329,6 +378,28 @@ __device__ int seed_cta_build(const RefIndex &ix, const uint32_t *reads2, const 
     // 1. events: every thread expands the bucket of its seed in place; a hit that is not the first of its seed in its
     //    block stays in the stream as a null event (it sorts behind everything and the serial numbers keep their order)
     if (tid == 0) sm.misc[4] = 0;     // null events
+    // the read's codes and mask go to shared memory first (into the sort's second buffer, idle until the events are
+    // complete) when they fit: one TMA bulk copy each, 16-byte aligned start and length
+    const uint32_t *codes = reads2, *mask = irr;
+    int64_t roff2 = roff, roffi = roff;
+    {
+        const int64_t a2 = roff & ~(int64_t)63, ai = roff & ~(int64_t)127;      // 64 bases = 16 bytes of codes, 128 bases = 16 bytes of mask
+        const unsigned bytes2 = (unsigned)(((roff + rlen - a2 + 15) / 16 * 4 + 8 + 15) & ~15), bytesi = (unsigned)(((roff + rlen - ai + 31) / 32 * 4 + 8 + 15) & ~15);
+        if ((size_t)bytes2 + bytesi <= (size_t)cap * 8) {
+            uint8_t *dst2 = reinterpret_cast<uint8_t *>(sm.aux), *dsti = dst2 + bytes2;
+            const unsigned parity = (unsigned)sm.misc[5] & 1u;
+            __syncthreads();          // everybody is done with what the buffer held
+            if (tid == 0) {
+                stage_issue(sm.bar, dst2, reads2 + (a2 >> 4), bytes2, dsti, irr + (ai >> 5), bytesi);
+                sm.misc[5] = (int)(parity ^ 1u);
+            }
+            stage_wait(sm.bar, parity);
+            codes = reinterpret_cast<const uint32_t *>(dst2);
+            mask = reinterpret_cast<const uint32_t *>(dsti);
+            roff2 = roff - a2;
+            roffi = roff - ai;
+        }
+    }
     __syncthreads();
     const uint32_t zv32 = (uint32_t)zv;
     int nulls = 0;
@@ -336,7 +407,7 @@ __device__ int seed_cta_build(const RefIndex &ix, const uint32_t *reads2, const 
         const int k = k0 + tid;
         uint32_t o0 = 0, cnt = 0;
         if (k < cleave_num) {
-            const int code = seed_code_fast(reads2, irr, roff, rlen, strand, k * BC);
+            const int code = seed_code_fast(codes, mask, roff2, roffi, rlen, strand, k * BC);
             if (code >= 0) {
                 o0 = ix.off[code];
                 cnt = ix.off[code + 1] - o0;      // the CSR is built from the masked counts: 0 for a bucket above 128
@@ -595,6 +666,14 @@ __device__ void seed_cta_body(const SeedCtaArgs &a, uint8_t *smem)
     const int thresh = a.pass == 0 ? 6 : 4;
     const int block_bits = seed_block_bits(a.ix.ref_len, zv);
     uint32_t *pool = a.heavy_pool + (size_t)blockIdx.x * (a.cap / (kSM + 1) + 1) * kHeavyWords;
+    {
+        SeedCtaSmem sm = seed_cta_carve(smem, a.cap);
+        if (tid == 0) {
+            stage_barrier_init(sm.bar);
+            sm.misc[5] = 0;           // phase of the staging barrier
+        }
+        __syncthreads();
+    }
     for (;;) {
         SeedCtaSmem sm = seed_cta_carve(smem, a.cap);
         if (tid == 0) sm.misc[3] = (int)atomicAdd(a.next, 1u);

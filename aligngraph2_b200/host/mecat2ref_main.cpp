@@ -36,6 +36,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -334,32 +337,64 @@ bool load_temp_result(TempResult &r, FILE *in, char *&line, size_t &cap) // outp
     return true;
 }
 
-void output_cigar(int qstart, int qend, int qsize, const std::string &qmap, const std::string &smap, FILE *out)
+// One record as the writers see it: TempResult without owning its strings (they stay in the buffers the GPU results
+// came home in, or in the TempResult a thread file line was parsed into).
+struct RecView {
+    int read_id = 0, vscore = 0, qb = 0, qe = 0, qs = 0;
+    char read_dir = 0;
+    long sb = 0, se = 0;
+    const char *qmap = nullptr, *smap = nullptr;
+    int len = 0;
+};
+
+RecView view_of(const TempResult &r)
 {
-    if (qstart) fprintf(out, "%dH", qstart);
+    RecView v;
+    v.read_id = r.read_id, v.vscore = r.vscore, v.qb = r.qb, v.qe = r.qe, v.qs = r.qs;
+    v.read_dir = r.read_dir;
+    v.sb = r.sb, v.se = r.se;
+    v.qmap = r.qmap.data(), v.smap = r.smap.data();
+    v.len = (int)r.qmap.size();
+    return v;
+}
+
+void append_fmt(std::string &out, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+void append_fmt(std::string &out, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    const int n = vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    out.append(buf, (size_t)std::min<int>(n, (int)sizeof buf - 1));
+}
+
+void append_cigar(const RecView &r, std::string &out)
+{
+    if (r.qb) append_fmt(out, "%dH", r.qb);
     int i = 0, j;
-    const int n = (int)qmap.size();
+    const int n = r.len;
     while (i < n) {
-        if (qmap[i] == '-') {
+        if (r.qmap[i] == '-') {
             j = i + 1;
-            while (j < n && qmap[j] == '-') ++j;
-            fprintf(out, "%dD", j - i);
-        } else if (smap[i] == '-') {
+            while (j < n && r.qmap[j] == '-') ++j;
+            append_fmt(out, "%dD", j - i);
+        } else if (r.smap[i] == '-') {
             j = i + 1;
-            while (j < n && smap[j] == '-') ++j;
-            fprintf(out, "%dI", j - i);
+            while (j < n && r.smap[j] == '-') ++j;
+            append_fmt(out, "%dI", j - i);
         } else {
             j = i + 1;
-            while (j < n && qmap[j] != '-' && smap[j] != '-') ++j;
-            fprintf(out, "%dM", j - i);
+            while (j < n && r.qmap[j] != '-' && r.smap[j] != '-') ++j;
+            append_fmt(out, "%dM", j - i);
         }
         i = j;
     }
-    if (qend != qsize) fprintf(out, "%dH", qsize - qend);
+    if (r.qe != r.qs) append_fmt(out, "%dH", r.qs - r.qe);
 }
 
-// output_one_result (output.cpp:6-43 ref, :45-88 m4, :150-186 sam)
-void output_one(const TempResult &r, const ChrInfo &c, int format, FILE *out)
+// output_one_result (output.cpp:6-43 ref, :45-88 m4, :150-186 sam), appended to a buffer
+void format_one(const RecView &r, const ChrInfo &c, int format, std::string &out)
 {
     const long sstart = r.sb - c.start, send = r.se - c.start;
     int qb = r.qb, qe = r.qe;
@@ -368,29 +403,43 @@ void output_one(const TempResult &r, const ChrInfo &c, int format, FILE *out)
             qb = r.qs - r.qe;
             qe = r.qs - r.qb;
         }
-        fprintf(out, "%d\t%s\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld\t%ld\n%s\n%s\n", r.read_id, c.name, r.read_dir == 'R' ? 'R' : 'F', r.vscore, qb, qe,
-                r.qs, sstart, send, c.size, r.qmap.c_str(), r.smap.c_str());
+        append_fmt(out, "%d\t%s\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld\t%ld\n", r.read_id, c.name, r.read_dir == 'R' ? 'R' : 'F', r.vscore, qb, qe, r.qs,
+                   sstart, send, c.size);
+        out.append(r.qmap, (size_t)r.len);
+        out.push_back('\n');
+        out.append(r.smap, (size_t)r.len);
+        out.push_back('\n');
     } else if (format == 1) {
         if (r.read_dir == 'R') {
             qb = r.qs - r.qe;
             qe = r.qs - r.qb;
         }
         double ident = 0.0;
-        const int n = (int)r.qmap.size();
+        const int n = r.len;
         for (int i = 0; i < n; ++i)
             if (r.qmap[i] == r.smap[i]) ident += 1.0;
         ident = ident / n;
         ident *= 100.0;
-        fprintf(out, "%d\t%s\t%.4f\t%d\t%d\t%d\t%d\t%d\t0\t%ld\t%ld\t%ld\n", r.read_id, c.name, ident, r.vscore, r.read_dir == 'F' ? 0 : 1, qb,
-                qe, r.qs, sstart, send, c.size);
+        append_fmt(out, "%d\t%s\t%.4f\t%d\t%d\t%d\t%d\t%d\t0\t%ld\t%ld\t%ld\n", r.read_id, c.name, ident, r.vscore, r.read_dir == 'F' ? 0 : 1, qb,
+                   qe, r.qs, sstart, send, c.size);
     } else if (format == 2) {
-        fprintf(out, "%d\t%d\t%s\t%ld\t255\t", r.read_id, r.read_dir == 'R' ? 0x10 : 0, c.name, sstart + 1);
-        output_cigar(r.qb, r.qe, r.qs, r.qmap, r.smap, out);
-        fprintf(out, "\t*\t0\t0\t");
-        for (char ch : r.qmap)
-            if (ch != '-') fputc(ch, out);
-        fprintf(out, "\t*\n");
+        append_fmt(out, "%d\t%d\t%s\t%ld\t255\t", r.read_id, r.read_dir == 'R' ? 0x10 : 0, c.name, sstart + 1);
+        append_cigar(r, out);
+        out.append("\t*\t0\t0\t");
+        for (int i = 0; i < r.len; ++i)
+            if (r.qmap[i] != '-') out.push_back(r.qmap[i]);
+        out.append("\t*\n");
     }
+}
+
+// output_temp_result (output.cpp:237-251): the `<wrk>/N.r` text of one record
+void format_temp(const RecView &r, std::string &out)
+{
+    append_fmt(out, "%d\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld\n", r.read_id, r.read_dir, r.vscore, r.qb, r.qe, r.qs, r.sb, r.se);
+    out.append(r.qmap, (size_t)r.len);
+    out.push_back('\n');
+    out.append(r.smap, (size_t)r.len);
+    out.push_back('\n');
 }
 
 void sam_header(const std::vector<ChrInfo> &chr, int argc, char **argv, FILE *out)
@@ -402,16 +451,88 @@ void sam_header(const std::vector<ChrInfo> &chr, int argc, char **argv, FILE *ou
     fprintf(out, "\tPN:mecat2ref\n");
 }
 
-void output_query_results(const std::vector<ChrInfo> &chr, const std::vector<const TempResult *> &p, int num_output, int format, FILE *out)
+void format_query_results(const std::vector<ChrInfo> &chr, const std::vector<const RecView *> &p, int num_output, int format, std::string &out)
 {
     int cnt = 0;
-    for (const TempResult *r : p) { // mecat2ref.cpp:499-520
-        output_one(*r, chr[(size_t)get_chr_id(chr, r->sb)], format, out);
+    for (const RecView *r : p) { // mecat2ref.cpp:499-520
+        format_one(*r, chr[(size_t)get_chr_id(chr, r->sb)], format, out);
         if (++cnt == num_output) break;
     }
 }
 
-// result_combine (mecat2ref.cpp:523-599): thread files -> -o, grouped by read id, first num_output of a group
+// The co-linearity vote of polish_result over one read group (mecat2ref.cpp:746-848): which records are written, in order.
+void polish_group(const std::vector<RecView> &pptr, const std::vector<ChrInfo> &chr, double delta, std::vector<const RecView *> &outp)
+{
+    int vote[16] = {0}, mark[16] = {0};
+    int flag3 = 0, flag4 = 0;
+    const int num_results = (int)pptr.size();
+    outp.clear();
+    for (int i = 0; i < num_results; i++)
+        for (int j = i + 1; j < num_results; j++) {
+            const int sid = get_chr_id(chr, pptr[i].sb), sid2 = get_chr_id(chr, pptr[j].sb);
+            if (sid == sid2 && labs(pptr[j].qb - pptr[i].qb) > 1000 && labs(pptr[i].qe - pptr[j].qe) > 1000 && pptr[i].sb != pptr[j].sb &&
+                fabs((double)((pptr[i].qb - pptr[j].qb) / (pptr[i].sb - pptr[j].sb) - 1)) < delta) {
+                vote[i]++;
+                vote[j]++;
+                mark[i] = 1;
+                mark[j] = 1;
+            }
+        }
+    for (int k = 0; k < num_results; k++) {
+        int delete_flag = 0;
+        if (mark[k] == 0) outp.push_back(&pptr[k]);
+        if (mark[k] == 1) {
+            int maxi_vote = vote[k], maxi = k;
+            const int sid = get_chr_id(chr, pptr[k].sb);
+            for (int p = k + 1; p < num_results; p++) {
+                if (sid != get_chr_id(chr, pptr[p].sb)) continue;
+                const int lk = pptr[k].qe - pptr[k].qb, lp = pptr[p].qe - pptr[p].qb;
+                if (labs(pptr[p].qb - pptr[k].qb) < 1500) {
+                    mark[p] = 2;
+                    delete_flag = 1;
+                    if (labs(lk - lp) > 3000) {
+                        maxi = lk > lp ? k : p;
+                    } else {
+                        if (maxi_vote > vote[p]) maxi = k;
+                        if (maxi_vote == vote[p]) maxi = lk > lp ? k : p;
+                        if (maxi_vote < vote[p]) {
+                            maxi = p;
+                            maxi_vote = vote[p];
+                        }
+                    }
+                } else {
+                    for (int q = p + 1; q < num_results; q++)
+                        if (sid == get_chr_id(chr, pptr[q].sb)) {
+                            flag3 = 1;
+                            break;
+                        }
+                    if (flag3 == 0) outp.push_back(&pptr[k]);
+                    flag3 = 0;
+                }
+            }
+            if (delete_flag == 1) outp.push_back(&pptr[maxi]);
+            for (int w = k + 1; w < num_results; w++)
+                if (sid == get_chr_id(chr, pptr[w].sb)) {
+                    flag4 = 1;
+                    break;
+                }
+            if (flag4 == 0) outp.push_back(&pptr[k]);
+            flag4 = 0;
+        }
+    }
+}
+
+void write_all(FILE *f, const std::string &buf)
+{
+    if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+        fprintf(stderr, "mecat2ref (aligngraph2_b200): write failed\n");
+        abort();
+    }
+}
+
+// result_combine (mecat2ref.cpp:523-599): thread files -> -o, grouped by read id, first num_output of a group.
+// File-based form: used when the thread files are all there is (AG2_SKIP_MAP); a mapping run writes -o / -p from the
+// records in memory (ResultWriter below), through the same format_* / polish_group functions.
 void result_combine(const Options &o, const std::vector<ChrInfo> &chr, int argc, char **argv)
 {
     fprintf(stderr, "output file name: %s\n", o.output);
@@ -420,6 +541,7 @@ void result_combine(const Options &o, const std::vector<ChrInfo> &chr, int argc,
     if (o.output_format == 2) sam_header(chr, argc, argv, out);
     char *line = nullptr;
     size_t cap = 0;
+    std::string buf;
     for (int i = 1; i <= o.num_cores; ++i) {
         const std::string path = std::string(o.wrk_dir) + "/" + std::to_string(i) + ".r";
         FILE *f = fopen(path.c_str(), "r");
@@ -433,9 +555,13 @@ void result_combine(const Options &o, const std::vector<ChrInfo> &chr, int argc,
             last = t.read_id;
         }
         auto flush = [&]() {
-            std::vector<const TempResult *> p;
-            for (const TempResult &g : group) p.push_back(&g);
-            output_query_results(chr, p, o.num_output, o.output_format, out);
+            std::vector<RecView> v;
+            for (const TempResult &g : group) v.push_back(view_of(g));
+            std::vector<const RecView *> p;
+            for (const RecView &g : v) p.push_back(&g);
+            buf.clear();
+            format_query_results(chr, p, o.num_output, o.output_format, buf);
+            write_all(out, buf);
             group.clear();
         };
         while (ok) {
@@ -462,6 +588,7 @@ void polish_result(const Options &o, const std::vector<ChrInfo> &chr, int argc, 
     if (o.output_format == 2) sam_header(chr, argc, argv, out);
     char *line = nullptr;
     size_t cap = 0;
+    std::string buf;
     for (int ww = 1; ww <= o.num_cores; ww++) {
         const std::string path = std::string(o.wrk_dir) + "/" + std::to_string(ww) + ".r";
         FILE *f = fopen(path.c_str(), "r");
@@ -474,85 +601,178 @@ void polish_result(const Options &o, const std::vector<ChrInfo> &chr, int argc, 
             pptr.push_back(t);
             last_id = t.read_id;
         }
-        int vote[16] = {0}, mark[16] = {0};
-        int flag3 = 0, flag4 = 0;
+        auto emit = [&](bool filtered) {
+            std::vector<RecView> v;
+            for (const TempResult &g : pptr) v.push_back(view_of(g));
+            std::vector<const RecView *> outp;
+            if (filtered) polish_group(v, chr, o.delta, outp);
+            else
+                for (const RecView &g : v) outp.push_back(&g);
+            buf.clear();
+            format_query_results(chr, outp, o.num_output, o.output_format, buf);
+            write_all(out, buf);
+            pptr.clear();
+        };
         while (rok) {
             rok = load_temp_result(t, f, line, cap);
             if (!rok) break;
-            if (t.read_id != last_id) {
-                const int num_results = (int)pptr.size();
-                std::vector<const TempResult *> outp;
-                for (int i = 0; i < num_results; i++)
-                    for (int j = i + 1; j < num_results; j++) {
-                        const int sid = get_chr_id(chr, pptr[i].sb), sid2 = get_chr_id(chr, pptr[j].sb);
-                        if (sid == sid2 && labs(pptr[j].qb - pptr[i].qb) > 1000 && labs(pptr[i].qe - pptr[j].qe) > 1000 &&
-                            pptr[i].sb != pptr[j].sb &&
-                            fabs((double)((pptr[i].qb - pptr[j].qb) / (pptr[i].sb - pptr[j].sb) - 1)) < o.delta) {
-                            vote[i]++;
-                            vote[j]++;
-                            mark[i] = 1;
-                            mark[j] = 1;
-                        }
-                    }
-                for (int k = 0; k < num_results; k++) {
-                    int delete_flag = 0;
-                    if (mark[k] == 0) outp.push_back(&pptr[k]);
-                    if (mark[k] == 1) {
-                        int maxi_vote = vote[k], maxi = k;
-                        const int sid = get_chr_id(chr, pptr[k].sb);
-                        for (int p = k + 1; p < num_results; p++) {
-                            if (sid != get_chr_id(chr, pptr[p].sb)) continue;
-                            const int lk = pptr[k].qe - pptr[k].qb, lp = pptr[p].qe - pptr[p].qb;
-                            if (labs(pptr[p].qb - pptr[k].qb) < 1500) {
-                                mark[p] = 2;
-                                delete_flag = 1;
-                                if (labs(lk - lp) > 3000) {
-                                    maxi = lk > lp ? k : p;
-                                } else {
-                                    if (maxi_vote > vote[p]) maxi = k;
-                                    if (maxi_vote == vote[p]) maxi = lk > lp ? k : p;
-                                    if (maxi_vote < vote[p]) {
-                                        maxi = p;
-                                        maxi_vote = vote[p];
-                                    }
-                                }
-                            } else {
-                                for (int q = p + 1; q < num_results; q++)
-                                    if (sid == get_chr_id(chr, pptr[q].sb)) {
-                                        flag3 = 1;
-                                        break;
-                                    }
-                                if (flag3 == 0) outp.push_back(&pptr[k]);
-                                flag3 = 0;
-                            }
-                        }
-                        if (delete_flag == 1) outp.push_back(&pptr[maxi]);
-                        for (int w = k + 1; w < num_results; w++)
-                            if (sid == get_chr_id(chr, pptr[w].sb)) {
-                                flag4 = 1;
-                                break;
-                            }
-                        if (flag4 == 0) outp.push_back(&pptr[k]);
-                        flag4 = 0;
-                    }
-                }
-                output_query_results(chr, outp, o.num_output, o.output_format, out);
-                pptr.clear();
-                for (int i = 0; i < 16; i++) mark[i] = vote[i] = 0;
-            }
+            if (t.read_id != last_id) emit(true);
             last_id = t.read_id;
             pptr.push_back(t);
         }
-        if (!pptr.empty()) {
-            std::vector<const TempResult *> p;
-            for (const TempResult &g : pptr) p.push_back(&g);
-            output_query_results(chr, p, o.num_output, o.output_format, out);
-        }
+        if (!pptr.empty()) emit(false);
         fclose(f);
     }
     free(line);
     fclose(out);
 }
+
+// The three result files of a mapping run, written from the records in memory: <wrk>/1.r as
+// output_temp_result prints it, -o as result_combine and -p as polish_result would make them from that file -- without
+// writing it, reading it back twice and parsing 2 x 10 kB of text per record.  A batch is cut at read-group boundaries into
+// pieces that worker threads format side by side; the three files are then written by three threads.  polish_result's
+// "last group of the thread file is not filtered" (:854) is kept by holding the last group of every batch back until it is
+// known whether another batch follows.
+class ResultWriter {
+public:
+    ResultWriter(const Options &o, const std::vector<ChrInfo> &chr, int argc, char **argv) : o_(o), chr_(chr)
+    {
+        const std::string wrk = o.wrk_dir;
+        f_r_ = open_or_die((wrk + "/1.r").c_str());
+        same_ = strcmp(o.output, o.refoutput) == 0;   // the reference writes -o, then -p over it
+        fprintf(stderr, "output file name: %s\n", o.output);
+        if (!same_) f_o_ = open_or_die(o.output);
+        fprintf(stderr, "output file name: %s\n", o.refoutput);
+        f_p_ = open_or_die(o.refoutput);
+        if (o.output_format == 2) {
+            if (f_o_) sam_header(chr, argc, argv, f_o_);
+            sam_header(chr, argc, argv, f_p_);
+        }
+        workers_ = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (const char *e = getenv("AG2_WRITER_THREADS")) workers_ = std::max(1, atoi(e));
+    }
+
+    // records of one batch, in thread-file order; the views point into buffers that outlive the call
+    void add_batch(const std::vector<RecView> &recs)
+    {
+        // read groups: [g[k], g[k+1])
+        std::vector<size_t> g;
+        for (size_t i = 0; i < recs.size(); ++i)
+            if (i == 0 || recs[i].read_id != recs[i - 1].read_id) g.push_back(i);
+        g.push_back(recs.size());
+        const size_t ngroups = g.size() - 1;
+        if (ngroups == 0) return;
+        // -p: the carried group of the previous batch is now known not to be the last one of the file
+        std::string carried_p;
+        if (!carry_.empty()) {
+            format_polished(carry_, true, carried_p);
+            carry_.clear();
+            carry_store_.clear();
+        }
+        const size_t per = std::max<size_t>(1, (ngroups + (size_t)workers_ * 4 - 1) / ((size_t)workers_ * 4));
+        const size_t npieces = (ngroups + per - 1) / per;
+        std::vector<std::string> tr(npieces), to(npieces), tp(npieces);
+        std::vector<std::thread> th;
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            std::vector<RecView> grp;
+            std::vector<const RecView *> sel;
+            for (;;) {
+                const size_t pc = next.fetch_add(1);
+                if (pc >= npieces) break;
+                const size_t g0 = pc * per, g1 = std::min(ngroups, g0 + per);
+                size_t bytes = 0;
+                for (size_t i = g[g0]; i < g[g1]; ++i) bytes += 2 * (size_t)recs[i].len + 96;
+                tr[pc].reserve(bytes);
+                if (f_o_) to[pc].reserve(bytes + 64 * (g[g1] - g[g0]));
+                tp[pc].reserve(bytes + 64 * (g[g1] - g[g0]));
+                for (size_t k = g0; k < g1; ++k) {
+                    grp.assign(recs.begin() + (long)g[k], recs.begin() + (long)g[k + 1]);
+                    for (const RecView &r : grp) format_temp(r, tr[pc]);
+                    if (f_o_) {
+                        sel.clear();
+                        for (const RecView &r : grp) sel.push_back(&r);
+                        format_query_results(chr_, sel, o_.num_output, o_.output_format, to[pc]);
+                    }
+                    if (k + 1 < ngroups) {   // the batch's last group waits for the next batch (or the end)
+                        polish_group(grp, chr_, o_.delta, sel);
+                        format_query_results(chr_, sel, o_.num_output, o_.output_format, tp[pc]);
+                    }
+                }
+            }
+        };
+        for (int w = 1; w < workers_; ++w) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+        // hold the last group back: copy it (its buffers go away with the batch)
+        for (size_t i = g[ngroups - 1]; i < g[ngroups]; ++i) {
+            carry_store_.emplace_back(std::string(recs[i].qmap, (size_t)recs[i].len), std::string(recs[i].smap, (size_t)recs[i].len));
+            carry_.push_back(recs[i]);
+        }
+        for (size_t i = 0; i < carry_.size(); ++i) {
+            carry_[i].qmap = carry_store_[i].first.data();
+            carry_[i].smap = carry_store_[i].second.data();
+        }
+        // three files, three writers; the pieces are megabytes each: straight write(2), no stdio copy
+        std::thread wr([&] { for (const std::string &b : tr) write_fd(f_r_, b); });
+        std::thread wo([&] { if (f_o_) for (const std::string &b : to) write_fd(f_o_, b); });
+        write_fd(f_p_, carried_p);
+        for (const std::string &b : tp) write_fd(f_p_, b);
+        wr.join();
+        wo.join();
+    }
+
+    void finish()
+    {
+        if (!carry_.empty()) {   // the last group of the file: written as it is (mecat2ref.cpp:854)
+            std::string p;
+            format_polished(carry_, false, p);
+            write_fd(f_p_, p);
+            carry_.clear();
+        }
+        fclose(f_r_);
+        if (f_o_) fclose(f_o_);
+        fclose(f_p_);
+        f_r_ = f_o_ = f_p_ = nullptr;
+    }
+
+private:
+    static FILE *open_or_die(const char *path)
+    {
+        FILE *f = fopen(path, "w");
+        if (!f) { fprintf(stderr, "failed to open file %s for writing.\n", path); abort(); }
+        setvbuf(f, nullptr, _IOFBF, 1 << 22);
+        return f;
+    }
+    static void write_fd(FILE *f, const std::string &buf)
+    {
+        fflush(f);   // whatever stdio still holds (the SAM header) goes first
+        const int fd = fileno(f);
+        for (size_t done = 0; done < buf.size();) {
+            const ssize_t n = write(fd, buf.data() + done, buf.size() - done);
+            if (n < 0) {
+                fprintf(stderr, "mecat2ref (aligngraph2_b200): write failed\n");
+                abort();
+            }
+            done += (size_t)n;
+        }
+    }
+    void format_polished(const std::vector<RecView> &grp, bool filtered, std::string &out)
+    {
+        std::vector<const RecView *> sel;
+        if (filtered) polish_group(grp, chr_, o_.delta, sel);
+        else
+            for (const RecView &r : grp) sel.push_back(&r);
+        format_query_results(chr_, sel, o_.num_output, o_.output_format, out);
+    }
+    const Options &o_;
+    const std::vector<ChrInfo> &chr_;
+    FILE *f_r_ = nullptr, *f_o_ = nullptr, *f_p_ = nullptr;
+    bool same_ = false;
+    int workers_ = 1;
+    std::vector<RecView> carry_;
+    std::vector<std::pair<std::string, std::string>> carry_store_;
+};
 
 double now_sec()
 {
@@ -609,7 +829,7 @@ template <class F> void on_every_device(std::vector<DeviceShard> &sh, F f)
 }
 
 // the mapping part of meap_ref_impl_large (:1994-2149) on the GPU; returns seconds {read index, ref index, mapping}
-void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
+void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3], ResultWriter &rw)
 {
     const std::vector<int> devs = device_list();
     std::vector<DeviceShard> sh;
@@ -637,10 +857,6 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
     const std::string wrk = o.wrk_dir;
     FILE *fq = fopen((wrk + "/0.fq").c_str(), "r");
     if (!fq) { fprintf(stderr, "failed to open %s/0.fq\n", wrk.c_str()); exit(1); }
-    FILE *out = fopen((wrk + "/1.r").c_str(), "w");
-    if (!out) { fprintf(stderr, "failed to open %s/1.r for writing\n", wrk.c_str()); exit(1); }
-    std::vector<char> obuf(1 << 24);
-    setvbuf(out, obuf.data(), _IOFBF, obuf.size());
     for (int t = 2; t <= o.num_cores; ++t) fclose(fopen((wrk + "/" + std::to_string(t) + ".r").c_str(), "w"));
     for (int t = 1; t <= o.num_cores; ++t) fclose(fopen((wrk + "/ref" + std::to_string(t) + ".r").c_str(), "w"));
 
@@ -679,6 +895,7 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
         }
     };
     // two batches in flight: while the GPUs map one and its records are printed, a second thread parses the next
+    std::thread writer;
     Batch batches[2];
     int cur_i = 0;
     load_fastq(batches[0]);
@@ -737,22 +954,52 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3])
         });
         first_batch = false;
         secs[2] += now_sec() - t0;
-        for (const DeviceShard &d : sh)
-            for (int64_t k = 0; k < d.n_rec; ++k) { // output_temp_result (output.cpp:237-251)
-                const ag2_record &r = d.rec[(size_t)k];
-                fprintf(out, "%d\t%c\t%d\t%d\t%d\t%d\t%ld\t%ld\n", ids[(size_t)(d.lo + r.read)], r.strand ? 'R' : 'F', r.vscore, r.qb, r.qe, r.qs,
-                        (long)r.sb, (long)r.se);
-                fwrite(d.qaln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
-                fputc('\n', out);
-                fwrite(d.saln.data() + r.aln_off, 1, (size_t)r.aln_len, out);
-                fputc('\n', out);
-            }
+        // the batch's records go to the writer (1.r, -o, -p from memory) on its own thread while the next batch is mapped
+        struct BatchResult {
+            std::vector<std::vector<ag2_record>> rec;
+            std::vector<std::vector<char>> q, s;
+            std::vector<int64_t> lo, n_rec;
+            std::vector<int> ids;
+        };
+        auto res = std::make_shared<BatchResult>();
+        for (DeviceShard &d : sh) {
+            res->rec.push_back(std::move(d.rec));
+            res->q.push_back(std::move(d.qaln));
+            res->s.push_back(std::move(d.saln));
+            res->lo.push_back(d.lo);
+            res->n_rec.push_back(d.n_rec);
+            d.rec.clear();
+            d.qaln.clear();
+            d.saln.clear();
+        }
+        res->ids = ids;
+        if (writer.joinable()) writer.join();
+        writer = std::thread([res, &rw] {
+            std::vector<RecView> views;
+            size_t total = 0;
+            for (int64_t n : res->n_rec) total += (size_t)n;
+            views.reserve(total);
+            for (size_t k = 0; k < res->rec.size(); ++k)
+                for (int64_t i = 0; i < res->n_rec[k]; ++i) { // output_temp_result (output.cpp:237-251)
+                    const ag2_record &r = res->rec[k][(size_t)i];
+                    RecView v;
+                    v.read_id = res->ids[(size_t)(res->lo[k] + r.read)];
+                    v.read_dir = r.strand ? 'R' : 'F';
+                    v.vscore = r.vscore, v.qb = r.qb, v.qe = r.qe, v.qs = r.qs;
+                    v.sb = (long)r.sb, v.se = (long)r.se;
+                    v.qmap = res->q[k].data() + r.aln_off;
+                    v.smap = res->s[k].data() + r.aln_off;
+                    v.len = r.aln_len;
+                    views.push_back(v);
+                }
+            rw.add_batch(views);
+        });
         if (!cur.more) break;
         cur_i ^= 1;   // the batch read ahead (join_ahead waits for it before the next round starts)
     }
+    if (writer.joinable()) writer.join();
     free(line);
     fclose(fq);
-    fclose(out);
     for (DeviceShard &d : sh) ag2_ctx_destroy(d.ctx);
 }
 
@@ -785,15 +1032,23 @@ int main(int argc, char **argv)
     }
     printf("first task is sucess\n");
     double secs[3] = {0, 0, 0};
+    bool wrote_results = false;
     {
         std::string ref_seq;
         const double t0 = now_sec();
         load_reference(o.reference, wrk, ref_seq);
         const double t_load = now_sec() - t0;
         stage_done("reference, chrindex.txt");
-        if (!getenv("AG2_SKIP_MAP")) map_on_gpu(o, ref_seq, secs);
+        if (!getenv("AG2_SKIP_MAP")) {
+            // 1.r, -o and -p are written from the records in memory while the mapping goes on
+            const std::vector<ChrInfo> chr0 = read_chrindex(wrk);
+            ResultWriter rw(o, chr0, argc, argv);
+            map_on_gpu(o, ref_seq, secs, rw);
+            rw.finish();
+            wrote_results = true;
+        }
         secs[1] += t_load;
-        stage_done("mapping (read, map, 1.r)");
+        stage_done("mapping (read, map, 1.r, -o, -p)");
     }
     {
         FILE *cfg = fopen("config.txt", "a");
@@ -803,9 +1058,11 @@ int main(int argc, char **argv)
         fclose(cfg);
     }
     const std::vector<ChrInfo> chr = read_chrindex(wrk);
-    // the two passes over the thread files are independent (own output file, no shared state): side by side, unless -o and
-    // -p name the same file, which the reference would write one after the other
-    if (strcmp(o.output, o.refoutput) != 0) {
+    // Without a mapping run (AG2_SKIP_MAP: the thread files are given) -o / -p come from the thread files as in the reference.
+    // The two passes are independent (own output file, no shared state): side by side, unless -o and -p name the same file,
+    // which the reference would write one after the other
+    if (wrote_results) {
+    } else if (strcmp(o.output, o.refoutput) != 0) {
         std::thread combine([&] { result_combine(o, chr, argc, argv); });
         polish_result(o, chr, argc, argv);
         combine.join();

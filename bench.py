@@ -62,6 +62,11 @@ def parse():
     ap.add_argument("--full-steps", type=int, default=5, help="timed steps of the full-path arm (at most --steps)")
     ap.add_argument("--full-cpu-reads-per-core", type=int, default=1000,
                     help="--impl reference: reads per host core of the full-path CPU arm (the reference hands out chunks of 1000 reads)")
+    ap.add_argument("--exec", dest="exec_reads", type=int, default=0,
+                    help="process-boundary measurement instead of the normal run: bin/mecat2ref (this repo) and oracle/_ref/mecat2ref -t <cores> "
+                         "on the same files with this many reads; wall-clock aligned Gbp/s of both, files compared")
+    ap.add_argument("--exec-ref-len", type=int, default=5_000_000)
+    ap.add_argument("--exec-no-reference", action="store_true", help="--exec: skip the reference binary (minutes of CPU)")
     ap.add_argument("--pagraph-cpu", action="store_true", help="also time the reference classes on the A-Bruijn stage input (minutes)")
     ap.add_argument("--pagraph-reads", type=int, default=4000, help="reads of the A-Bruijn build stage line (0 = skip)")
     ap.add_argument("--pagraph-k", type=int, default=14)
@@ -420,6 +425,87 @@ def full_path_reference(args, cores: int):
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+def exec_bench(args):
+    """the reference's real boundary is the process.  Runs the drop-in executable and the unmodified reference
+    binary on the same FASTA / FASTQ files (page-cached, /dev/shm when it has room) with the pipeline's argv and reports
+    wall-clock aligned Gbp/s of the whole process (file conversion, index builds, mapping, -o / -p writing) for both, plus
+    each one's own "The Mapping Time"; the -o / -p files are compared as multisets of records (the reference's -t N order is
+    scheduling-dependent)."""
+    import hashlib
+    import shutil
+    import tempfile
+    import torch
+    from aligngraph2_b200 import build, synth
+    cores = host_cores()
+    n = args.exec_reads
+    d = synth.make_batch_torch(args.seed + 77, args.exec_ref_len, n, args.tlen, device="cuda" if torch.cuda.is_available() else "cpu")
+    ref = d["ref"].cpu().numpy()
+    bases, off = d["bases"].cpu().numpy(), d["offsets"].cpu().numpy()
+    del d
+    need = 12 * int(bases.size)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need else None
+    tmp = tempfile.mkdtemp(prefix="ag2_exec_", dir=base)
+    out = {"reads": n, "read_bases": int(off[-1]), "ref_len": args.exec_ref_len, "host_cores": cores, "dir": "tmpfs" if base else "tmp"}
+    argv = ["-d", "reads.fq", "-r", "ref.fa", "-b", "1", "-w", "./wrk", "-o", "o.txt", "-p", "p.txt", "-l", "0.5", "-u", "2.0", "-z", "200", "-y", "0.9"]
+
+    def digest(path):
+        h, aligned, recs = [], 0, 0
+        with open(path, "rb") as f:
+            lines = f.read().split(b"\n")
+        for k in range(0, len(lines) - 2, 3):
+            t = lines[k].split(b"\t")
+            aligned += int(t[5]) - int(t[4])
+            recs += 1
+            h.append(hashlib.blake2b(lines[k] + b"\n" + lines[k + 1] + b"\n" + lines[k + 2], digest_size=12).digest())
+        h.sort()
+        return hashlib.sha256(b"".join(h)).hexdigest(), aligned, recs
+
+    def times(dirpath):
+        t = {}
+        for ln in open(os.path.join(dirpath, "config.txt")):
+            if "Time" in ln and ":" in ln:
+                k, v = ln.rsplit(":", 1)
+                try:
+                    t[k.strip()] = float(v.split()[0])
+                except ValueError:
+                    pass
+        return t
+    try:
+        runs = [("ours", build.build_host(), "1")]
+        ref_exe = os.path.join(ROOT, "oracle", "_ref", "mecat2ref")
+        if not args.exec_no_reference and os.path.exists(ref_exe):
+            runs.append(("reference", ref_exe, str(cores)))
+        for who, exe, t in runs:
+            dd = os.path.join(tmp, who)
+            os.makedirs(dd)
+            synth.write_fasta(os.path.join(dd, "ref.fa"), "chr1", ref)
+            with open(os.path.join(dd, "reads.fq"), "wb") as f:
+                for i in range(n):
+                    rd = bases[off[i]:off[i + 1]].tobytes()
+                    f.write(b"@r%d\n" % i + rd + b"\n+\n" + b"I" * len(rd) + b"\n")
+            t0 = time.perf_counter()
+            r = subprocess.run([exe, "-t", t] + argv, cwd=dd, env=dict(os.environ, AG2_TRACE="1"), capture_output=True, text=True)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                out[who] = {"error": r.stderr[-400:]}
+                continue
+            p_sha, aligned, recs = digest(os.path.join(dd, "p.txt"))
+            o_sha, _, _ = digest(os.path.join(dd, "o.txt"))
+            tt = times(dd)
+            out[who] = {"threads_flag": int(t), "wall_s": wall, "aligned_bases": aligned, "records": recs, "wall_gbp_per_s": aligned / wall / 1e9,
+                        "config_txt_times_s": tt, "mapping_time_gbp_per_s": aligned / tt["The Mapping Time"] / 1e9 if tt.get("The Mapping Time") else None,
+                        "p_records_sha256": p_sha, "o_records_sha256": o_sha,
+                        "host_trace": [ln for ln in r.stderr.splitlines() if ln.startswith("[mecat2ref host]")]}
+            shutil.rmtree(os.path.join(dd, "wrk"), ignore_errors=True)
+        if "reference" in out and "wall_s" in out.get("reference", {}) and "wall_s" in out.get("ours", {}):
+            out["files_identical_as_record_multisets"] = (out["ours"]["p_records_sha256"] == out["reference"]["p_records_sha256"]
+                                                          and out["ours"]["o_records_sha256"] == out["reference"]["o_records_sha256"])
+            out["wall_speedup"] = out["reference"]["wall_s"] / out["ours"]["wall_s"]
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps({"metric": "exec_wall_gbp_per_s", "unit": UNIT, "exec": out}))
+
+
 def cbar_guard(st) -> float:
     return max(1.0, st["cells"] / max(1, st["aligned"]))
 
@@ -483,6 +569,9 @@ def workload_config(args, sample=None):
 
 def main():
     args = parse()
+    if args.exec_reads > 0:
+        exec_bench(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return
