@@ -691,6 +691,23 @@ void ag2_ctx_destroy(ag2_ctx *ctx)
 
 void *ag2_ctx_stream(ag2_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
+int ag2_host_alloc(size_t bytes, void **ptr)
+{
+    if (!ptr) return AG2_EINVAL;
+    *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? AG2_ENOMEM : AG2_ECUDA;
+    }
+    return AG2_OK;
+}
+
+void ag2_host_free(void *ptr)
+{
+    if (ptr) cudaFreeHost(ptr);
+}
+
 int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len)
 {
     if (!ctx || !ref || ref_len <= 0 || ref_len > 0xfffffff0ll) return fail(ctx, AG2_EINVAL, "ag2_ref_load: bad argument");

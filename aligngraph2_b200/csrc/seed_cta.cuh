@@ -370,7 +370,7 @@ __device__ __forceinline__ int run_lower_bound(const RunView &v, int nruns, int6
 __device__ int seed_cta_build(const RefIndex &ix, const uint32_t *reads2, const uint32_t *irr, int64_t roff, int rlen, int strand, int BC,
                               int64_t zv, int cap, int block_bits, SeedCtaSmem &sm, uint32_t *pool)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int cleave_num = (rlen - kSeedLen) / BC + 1;
     int n_ev = 0;
     bool overflow = false;

@@ -39,6 +39,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -804,12 +805,59 @@ std::vector<int> device_list()
     return devs;
 }
 
+// Page-locked result buffers (ag2_host_alloc), recycled between batches: a fresh std::vector of a gigabyte is a second of
+// page faults and zero-filling, and device copies into pageable memory run at a fraction of the PCIe rate.
+class PinnedPool {
+public:
+    struct Block {
+        char *p = nullptr;
+        size_t cap = 0;
+    };
+    Block take(size_t bytes)
+    {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            size_t best = free_.size();
+            for (size_t i = 0; i < free_.size(); ++i)
+                if (free_[i].cap >= bytes && (best == free_.size() || free_[i].cap < free_[best].cap)) best = i;
+            if (best != free_.size()) {
+                Block b = free_[best];
+                free_.erase(free_.begin() + (long)best);
+                return b;
+            }
+        }
+        Block b;
+        b.cap = bytes + bytes / 8 + 4096;
+        void *q = nullptr;
+        if (ag2_host_alloc(b.cap, &q) != AG2_OK) {
+            fprintf(stderr, "mecat2ref (aligngraph2_b200): cannot allocate %zu bytes of host memory\n", b.cap);
+            fflush(stderr);
+            _exit(1);
+        }
+        b.p = (char *)q;
+        return b;
+    }
+    void give(Block b)
+    {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> g(m_);
+        free_.push_back(b);
+    }
+    ~PinnedPool()
+    {
+        for (Block &b : free_) ag2_host_free(b.p);
+    }
+
+private:
+    std::mutex m_;
+    std::vector<Block> free_;
+};
+
 struct DeviceShard {   // one GPU's context and what it produced for the current batch
     ag2_ctx *ctx = nullptr;
     int64_t lo = 0, hi = 0;   // its contiguous range of the batch's reads
     std::vector<int64_t> offs;
-    std::vector<ag2_record> rec;
-    std::vector<char> qaln, saln;
+    PinnedPool::Block rec, qaln, saln;   // ag2_record[n_rec], the two string pools
     int64_t n_rec = 0;
     int rc = AG2_OK;
     const char *what = "";
@@ -895,6 +943,7 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3], Re
         }
     };
     // two batches in flight: while the GPUs map one and its records are printed, a second thread parses the next
+    PinnedPool pool;
     std::thread writer;
     Batch batches[2];
     int cur_i = 0;
@@ -945,54 +994,56 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3], Re
             int64_t used = 0;
             d.what = "ag2_map_reads";
             if ((d.rc = ag2_map_reads(d.ctx, o.num_candidates, o.num_output, &d.n_rec)) != AG2_OK) return;
-            d.rec.resize((size_t)d.n_rec + 1);
+            d.rec = pool.take(((size_t)d.n_rec + 1) * sizeof(ag2_record));
             d.what = "ag2_map_fetch";
-            if ((d.rc = ag2_map_fetch(d.ctx, d.rec.data(), nullptr, nullptr, 0, &used)) != AG2_OK) return;
-            d.qaln.resize((size_t)used + 1);
-            d.saln.resize((size_t)used + 1);
-            d.rc = ag2_map_fetch(d.ctx, d.rec.data(), d.qaln.data(), d.saln.data(), used, &used);
+            if ((d.rc = ag2_map_fetch(d.ctx, (ag2_record *)d.rec.p, nullptr, nullptr, 0, &used)) != AG2_OK) return;
+            d.qaln = pool.take((size_t)used + 1);
+            d.saln = pool.take((size_t)used + 1);
+            d.rc = ag2_map_fetch(d.ctx, (ag2_record *)d.rec.p, d.qaln.p, d.saln.p, used, &used);
         });
         first_batch = false;
         secs[2] += now_sec() - t0;
         // the batch's records go to the writer (1.r, -o, -p from memory) on its own thread while the next batch is mapped
         struct BatchResult {
-            std::vector<std::vector<ag2_record>> rec;
-            std::vector<std::vector<char>> q, s;
+            std::vector<PinnedPool::Block> rec, q, s;
             std::vector<int64_t> lo, n_rec;
             std::vector<int> ids;
         };
         auto res = std::make_shared<BatchResult>();
         for (DeviceShard &d : sh) {
-            res->rec.push_back(std::move(d.rec));
-            res->q.push_back(std::move(d.qaln));
-            res->s.push_back(std::move(d.saln));
+            res->rec.push_back(d.rec);
+            res->q.push_back(d.qaln);
+            res->s.push_back(d.saln);
             res->lo.push_back(d.lo);
             res->n_rec.push_back(d.n_rec);
-            d.rec.clear();
-            d.qaln.clear();
-            d.saln.clear();
+            d.rec = d.qaln = d.saln = PinnedPool::Block();
         }
         res->ids = ids;
         if (writer.joinable()) writer.join();
-        writer = std::thread([res, &rw] {
+        writer = std::thread([res, &rw, &pool] {
             std::vector<RecView> views;
             size_t total = 0;
             for (int64_t n : res->n_rec) total += (size_t)n;
             views.reserve(total);
             for (size_t k = 0; k < res->rec.size(); ++k)
                 for (int64_t i = 0; i < res->n_rec[k]; ++i) { // output_temp_result (output.cpp:237-251)
-                    const ag2_record &r = res->rec[k][(size_t)i];
+                    const ag2_record &r = ((const ag2_record *)res->rec[k].p)[(size_t)i];
                     RecView v;
                     v.read_id = res->ids[(size_t)(res->lo[k] + r.read)];
                     v.read_dir = r.strand ? 'R' : 'F';
                     v.vscore = r.vscore, v.qb = r.qb, v.qe = r.qe, v.qs = r.qs;
                     v.sb = (long)r.sb, v.se = (long)r.se;
-                    v.qmap = res->q[k].data() + r.aln_off;
-                    v.smap = res->s[k].data() + r.aln_off;
+                    v.qmap = res->q[k].p + r.aln_off;
+                    v.smap = res->s[k].p + r.aln_off;
                     v.len = r.aln_len;
                     views.push_back(v);
                 }
             rw.add_batch(views);
+            for (size_t k = 0; k < res->rec.size(); ++k) {   // the buffers go back for the batch after next
+                pool.give(res->rec[k]);
+                pool.give(res->q[k]);
+                pool.give(res->s[k]);
+            }
         });
         if (!cur.more) break;
         cur_i ^= 1;   // the batch read ahead (join_ahead waits for it before the next round starts)

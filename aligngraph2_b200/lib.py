@@ -38,7 +38,7 @@ class MapStats(C.Structure):
 
 
 EXPORTS = [
-    "ag2_device_count", "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load", "ag2_reads_load_async", "ag2_reads_wait",
+    "ag2_device_count", "ag2_host_alloc", "ag2_host_free", "ag2_ctx_create", "ag2_ctx_destroy", "ag2_last_error", "ag2_version", "ag2_ref_load", "ag2_reads_load", "ag2_reads_load_async", "ag2_reads_wait",
     "ag2_xdrop_extend_batch", "ag2_xdrop_extend_batch_packed", "ag2_extend_fetch_packed", "ag2_expand_alignments", "ag2_extend_upload", "ag2_extend_run", "ag2_extend_fetch", "ag2_extend_get_stats",
     "ag2_ctx_stream", "ag2_index_build", "ag2_index_fetch", "ag2_seed_candidates",
     "ag2_extend_upload_from_seeds", "ag2_map_reads", "ag2_map_fetch", "ag2_map_fetch_packed", "ag2_map_get_stats",
@@ -64,6 +64,9 @@ def load() -> C.CDLL:
     L = C.CDLL(SO)
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
     L.ag2_device_count.argtypes = [C.POINTER(i32)]
+    L.ag2_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.ag2_host_free.argtypes = [vp]
+    L.ag2_host_free.restype = None
     L.ag2_ctx_create.argtypes = [i32, C.POINTER(vp)]
     L.ag2_ctx_destroy.argtypes = [vp]
     L.ag2_ctx_destroy.restype = None

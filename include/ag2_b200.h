@@ -81,6 +81,12 @@ void ag2_ctx_destroy(ag2_ctx *ctx);
 const char *ag2_last_error(const ag2_ctx *ctx);
 const char *ag2_version(void);
 
+/* Page-locked host memory for the buffers of the calls below (records, alignment strings, read bases): device copies from
+ * and to such memory run at full PCIe speed and do not stall on page faults of fresh allocations.  Plain malloc'ed
+ * buffers work everywhere too. */
+int ag2_host_alloc(size_t bytes, void **ptr);
+void ag2_host_free(void *ptr);
+
 /* Reference: ASCII bases, already concatenated over chromosomes and upper-cased the way
  * creat_ref_index does (impl_large.cpp:432-437).  Packed 2 bits/base on the device. */
 int ag2_ref_load(ag2_ctx *ctx, const char *ref, int64_t ref_len);

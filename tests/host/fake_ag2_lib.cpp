@@ -34,6 +34,14 @@ std::mutex g_oracle;   // the oracle is single-threaded test code; the host call
 
 extern "C" {
 
+int ag2_host_alloc(size_t bytes, void **ptr)
+{
+    *ptr = malloc(bytes ? bytes : 1);
+    return *ptr ? AG2_OK : AG2_ENOMEM;
+}
+void ag2_host_free(void *ptr) { free(ptr); }
+
+
 int ag2_device_count(int *count)
 {
     const char *e = getenv("FAKE_AG2_DEVICES");
