@@ -1038,11 +1038,18 @@ int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
         pg->stats.launches += 2;
     }
     PG_TRY(exclusive_sum(pg, seg_cnt.p, seg_off.p, nv + 1));
+    Dev<uint32_t> big_list, big_n;
+    PG_CUDA(big_n.alloc(1));
+    PG_CUDA(cudaMemsetAsync(big_n.p, 0, 4, pg->stream));
+    PG_CUDA(cudaEventRecord(pg->ev[0], pg->stream));          // sorted: the clustering starts
     if (nt) {
-        const int blocks = (int)std::min<int64_t>((nv + kJoinWarps - 1) / kJoinWarps, 148 * 8);
-        pg_join_kernel<<<blocks, kJoinWarps * 32, 0, pg->stream>>>(seg_off.p, nv, items_sorted.p, eps, rep_scratch.p, cnt_scratch.p,
-                                                                 o_ctg.p, o_ref.p, o_cnt.p, nrep.p);
-        ++pg->stats.launches;
+        // a vertex with more than kSmallJoin items has at least kSmallJoin + 1 of the nt items
+        PG_CUDA(big_list.alloc(nt / (kSmallJoin + 1) + 1));
+        pg_join_small_kernel<<<grid_for(nv), 256, 0, pg->stream>>>(seg_off.p, nv, items_sorted.p, eps, o_ctg.p, o_ref.p, o_cnt.p, nrep.p,
+                                                                   big_list.p, big_n.p);
+        pg_join_kernel<<<148 * 8, kJoinWarps * 32, 0, pg->stream>>>(seg_off.p, nv, items_sorted.p, eps, rep_scratch.p, cnt_scratch.p,
+                                                                    o_ctg.p, o_ref.p, o_cnt.p, nrep.p, big_list.p, big_n.p);
+        pg->stats.launches += 2;
     }
     pg_widen_kernel<<<grid_for(nv + 1), 256, 0, pg->stream>>>(nrep.p, nv + 1, nrep64.p);
     PG_TRY(exclusive_sum(pg, nrep64.p, pg->g_pos_off.p, nv + 1));
@@ -1053,11 +1060,12 @@ int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
     PG_CUDA(pg->g_ref.alloc((int64_t)npos));
     PG_CUDA(pg->g_cnt.alloc((int64_t)npos));
     if (npos) {
-        pg_compact_kernel<<<grid_for(nv * 32), 256, 0, pg->stream>>>(seg_off.p, pg->g_pos_off.p, nv, o_ctg.p, o_ref.p, o_cnt.p,
-                                                                      pg->g_ctg.p, pg->g_ref.p, pg->g_cnt.p);
+        pg_compact_kernel<<<grid_for(nt), 256, 0, pg->stream>>>(key_sorted.p, nt, seg_off.p, nrep.p, pg->g_pos_off.p, o_ctg.p, o_ref.p, o_cnt.p,
+                                                                 pg->g_ctg.p, pg->g_ref.p, pg->g_cnt.p);
         ++pg->stats.launches;
     }
     pg->g_npos = (int64_t)npos;
+    PG_CUDA(cudaEventRecord(pg->ev[1], pg->stream));          // positions done: the edges start
 
     // ---- edges: sort by (from, to, step), unique
     Dev<unsigned long long> ft, ft2, e_cnt64;
@@ -1103,6 +1111,12 @@ int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
     float ms = 0;
     cudaEventElapsedTime(&ms, pg->ev[2], pg->ev[3]);
     pg->stats.join_ms = ms;
+    cudaEventElapsedTime(&ms, pg->ev[2], pg->ev[0]);
+    pg->stats.join_sort_ms = ms;
+    cudaEventElapsedTime(&ms, pg->ev[0], pg->ev[1]);
+    pg->stats.join_cluster_ms = ms;
+    cudaEventElapsedTime(&ms, pg->ev[1], pg->ev[3]);
+    pg->stats.join_edges_ms = ms;
     pg->stats.positions = pg->g_npos;
     pg->stats.edges = pg->g_nedge;
     pg->have_graph = true;

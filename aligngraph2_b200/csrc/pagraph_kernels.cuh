@@ -400,8 +400,9 @@ __global__ void __launch_bounds__(kJoinWarps * 32)
 pg_join_kernel(const uint32_t* __restrict__ seg_off, int64_t n_vertices, const unsigned long long* __restrict__ items /* ctg | ref<<32 */,
                uint32_t eps, unsigned long long* __restrict__ rep_scratch, uint32_t* __restrict__ cnt_scratch,
                uint32_t* __restrict__ out_ctg, uint32_t* __restrict__ out_ref, uint16_t* __restrict__ out_cnt,
-               uint32_t* __restrict__ nrep)
+               uint32_t* __restrict__ nrep, const uint32_t* __restrict__ list, const uint32_t* __restrict__ n_list)
 {
+    if (list) n_vertices = *n_list;   // the vertices pg_join_small_kernel left for a warp each
     __shared__ unsigned long long s_rep[kJoinWarps][kRepSmem];
     __shared__ uint32_t s_cnt[kJoinWarps][kRepSmem];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -409,7 +410,8 @@ pg_join_kernel(const uint32_t* __restrict__ seg_off, int64_t n_vertices, const u
     const int64_t n_warps = (int64_t)gridDim.x * kJoinWarps;
     unsigned long long* rep = s_rep[wib];
     uint32_t* cnt = s_cnt[wib];
-    for (int64_t v = warp; v < n_vertices; v += n_warps) {
+    for (int64_t w = warp; w < n_vertices; w += n_warps) {
+        const int64_t v = list ? (int64_t)list[w] : w;
         const uint32_t b = seg_off[v], e = seg_off[v + 1];
         if (b == e) {
             if (lane == 0) nrep[v] = 0;
@@ -464,23 +466,80 @@ pg_join_kernel(const uint32_t* __restrict__ seg_off, int64_t n_vertices, const u
     }
 }
 
-// compaction of the per-vertex results: one warp per vertex
-__global__ void pg_compact_kernel(const uint32_t* __restrict__ seg_off, const unsigned long long* __restrict__ pos_off, int64_t n_vertices,
+// The same clustering for the many vertices that hold only a few items (at k = 14 on noisy reads: 100 M vertices, two
+// items each on average): one THREAD per vertex, representatives in registers; a vertex with more than kSmallJoin items
+// goes to `list` for pg_join_kernel (one warp each).
+constexpr int kSmallJoin = 8;
+__global__ void __launch_bounds__(256)
+pg_join_small_kernel(const uint32_t* __restrict__ seg_off, int64_t n_vertices, const unsigned long long* __restrict__ items, uint32_t eps,
+                     uint32_t* __restrict__ out_ctg, uint32_t* __restrict__ out_ref, uint16_t* __restrict__ out_cnt, uint32_t* __restrict__ nrep,
+                     uint32_t* __restrict__ list, uint32_t* __restrict__ n_list)
+{
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_vertices; v += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = seg_off[v], e = seg_off[v + 1];
+        const uint32_t n = e - b;
+        if (n == 0) {
+            nrep[v] = 0;
+            continue;
+        }
+        if (n > (uint32_t)kSmallJoin) {
+            list[atomicAdd(n_list, 1u)] = (uint32_t)v;
+            continue;
+        }
+        unsigned long long rep[kSmallJoin];
+        uint32_t cnt[kSmallJoin];
+        uint32_t p = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const unsigned long long it = __ldg(items + b + i);
+            const uint32_t ic = (uint32_t)it, ir = (uint32_t)(it >> 32);
+            int hit = -1;
+#pragma unroll
+            for (int j = kSmallJoin - 1; j >= 0; --j)      // downwards: the lowest matching j stays
+                if ((uint32_t)j < p && coord_similar(ic, (uint32_t)rep[j], eps) && coord_similar(ir, (uint32_t)(rep[j] >> 32), eps)) hit = j;
+#pragma unroll
+            for (int j = 0; j < kSmallJoin; ++j) {
+                if (j == hit) cnt[j] = (cnt[j] + 1u) & 0xffffu;
+                if (hit < 0 && (uint32_t)j == p) {
+                    rep[j] = it;
+                    cnt[j] = 1u;
+                }
+            }
+            if (hit < 0) ++p;
+        }
+#pragma unroll
+        for (int j = 0; j < kSmallJoin; ++j) {
+            if ((uint32_t)j >= p) continue;
+            const unsigned long long key = ((rep[j] & 0xffffffffull) << 32) | (rep[j] >> 32);   // (ctg, ref) lexicographic
+            uint32_t rank = 0;
+#pragma unroll
+            for (int q = 0; q < kSmallJoin; ++q) {
+                const unsigned long long ok = ((rep[q] & 0xffffffffull) << 32) | (rep[q] >> 32);
+                rank += ((uint32_t)q < p && ok < key) ? 1u : 0u;
+            }
+            out_ctg[b + rank] = (uint32_t)rep[j];
+            out_ref[b + rank] = (uint32_t)(rep[j] >> 32);
+            out_cnt[b + rank] = (uint16_t)cnt[j];
+        }
+        nrep[v] = p;
+    }
+}
+
+// compaction of the per-vertex results, one thread per slot of the sorted stream: slot i of vertex v = key[i] survives if
+// it is one of the first nrep[v] of its segment
+__global__ void pg_compact_kernel(const uint32_t* __restrict__ key, int64_t n_items, const uint32_t* __restrict__ seg_off,
+                                  const uint32_t* __restrict__ nrep, const unsigned long long* __restrict__ pos_off,
                                   const uint32_t* __restrict__ in_ctg, const uint32_t* __restrict__ in_ref,
                                   const uint16_t* __restrict__ in_cnt, uint32_t* __restrict__ ctg, uint32_t* __restrict__ ref,
                                   uint16_t* __restrict__ cnt)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t v = warp; v < n_vertices; v += n_warps) {
-        const unsigned long long o = pos_off[v], n = pos_off[v + 1] - o;
-        const uint32_t b = seg_off[v];
-        for (unsigned long long j = lane; j < n; j += 32) {
-            ctg[o + j] = in_ctg[b + j];
-            ref[o + j] = in_ref[b + j];
-            cnt[o + j] = in_cnt[b + j];
-        }
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_items; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = key[i];
+        const uint32_t r = (uint32_t)i - seg_off[v];
+        if (r >= nrep[v]) continue;
+        const unsigned long long o = pos_off[v] + r;
+        ctg[o] = in_ctg[i];
+        ref[o] = in_ref[i];
+        cnt[o] = in_cnt[i];
     }
 }
 

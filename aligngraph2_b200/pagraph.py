@@ -24,7 +24,8 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("n_vertices", C.c_int64), ("lanes", C.c_int64 * 2), ("columns", C.c_int64 * 2), ("samples", C.c_int64 * 2),
                 ("tuples", C.c_int64 * 2), ("edges_raw", C.c_int64 * 2), ("positions", C.c_int64), ("edges", C.c_int64),
-                ("launches", C.c_int64), ("extract_ms", C.c_double), ("join_ms", C.c_double)]
+                ("launches", C.c_int64), ("extract_ms", C.c_double), ("join_ms", C.c_double),
+                ("join_sort_ms", C.c_double), ("join_cluster_ms", C.c_double), ("join_edges_ms", C.c_double)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if hasattr(getattr(self, n), "__len__") else getattr(self, n)) for n, _ in self._fields_}
@@ -321,6 +322,15 @@ def build_distributed(job: Job, block: int, params: Params, group=None) -> Stats
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     job.load_block(block, rank, world)
+    return extract_exchange_join(job, params, group)
+
+
+def extract_exchange_join(job: Job, params: Params, group=None) -> Stats:
+    """build_distributed without the file loading: the block's reads of this rank are loaded already."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
     job.extract(params)
     if world == 1:
         return job.join(params)

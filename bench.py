@@ -67,6 +67,7 @@ def parse():
                          "on the same files with this many reads; wall-clock aligned Gbp/s of both, files compared")
     ap.add_argument("--exec-ref-len", type=int, default=5_000_000)
     ap.add_argument("--exec-no-reference", action="store_true", help="--exec: skip the reference binary (minutes of CPU)")
+    ap.add_argument("--only-pagraph", action="store_true", help="run only the A-Bruijn build stage (configs[3] at --pagraph-reads reads) and print its object")
     ap.add_argument("--pagraph-cpu", action="store_true", help="also time the reference classes on the A-Bruijn stage input (minutes)")
     ap.add_argument("--pagraph-reads", type=int, default=4000, help="reads of the A-Bruijn build stage line (0 = skip)")
     ap.add_argument("--pagraph-k", type=int, default=14)
@@ -212,8 +213,12 @@ def pagraph_stage(args, local: int):
     d = tempfile.mkdtemp(prefix="ag2_pg_")
     try:
         n = args.pagraph_reads
+        t_gen = time.perf_counter()
         info = synth_pg.make_input_set(d, args.seed, max(400_000, n * 40), n, tlen=args.tlen, n_ctg=8)
+        t_gen = time.perf_counter() - t_gen
+        t_km = time.perf_counter()
         words = synth_pg.solid_words_from_reads(d, args.pagraph_k, 0.2, local)
+        t_km = time.perf_counter() - t_km
         j = lambda x: os.path.join(d, x)
         job = pagraph.Job(j("solid.bin"), j("ctg.fasta"), j("ref.fasta"), d, j("c2r.ref"), device=local)
         p = pagraph.default_params(10, 2)
@@ -237,11 +242,14 @@ def pagraph_stage(args, local: int):
                            f"k={args.pagraph_k}, epsilon=10, -v 2", "read_bases": info["read_bases"], "columns": info["columns"],
                "vertices": sd["n_vertices"], "solid_kmers": int(len(words) - 1), "tuples": tuples, "edges_raw": edges_raw,
                "positions": sd["positions"], "edges": sd["edges"], "build_ms": build_ms, "extract_ms": sd["extract_ms"],
-               "join_ms": sd["join_ms"], "launches": sd["launches"], "e2e_ms": e2e_ms,
+               "join_ms": sd["join_ms"], "join_sort_ms": sd["join_sort_ms"], "join_cluster_ms": sd["join_cluster_ms"],
+               "join_edges_ms": sd["join_edges_ms"], "launches": sd["launches"], "e2e_ms": e2e_ms,
                "read_gbp_per_s": info["read_bases"] / (build_ms * 1e-3) / 1e9,
                "e2e_read_gbp_per_s": info["read_bases"] / (e2e_ms * 1e-3) / 1e9,
                "algorithmic_GBps": alg_bytes / (build_ms * 1e-3) / 1e9,
-               "d2h_bytes": int(g.ctg.nbytes + g.ref.nbytes + g.count.nbytes + g.edge_to.nbytes + g.edge_step.nbytes + 2 * g.pos_off.nbytes)}
+               "d2h_bytes": int(g.ctg.nbytes + g.ref.nbytes + g.count.nbytes + g.edge_to.nbytes + g.edge_step.nbytes + 2 * g.pos_off.nbytes),
+               "input_generation_s": t_gen, "kmer_counter_s_incl_file_parse": t_km,
+               "algorithmic_frac_of_hbm_peak": alg_bytes / (build_ms * 1e-3) / 1e9 / peaks()[0]}
         job.close()
         # the CPU beside it: the unmodified reference classes when built here, else the port; one core (-t 1 is the only
         # deterministic setting of the reference)
@@ -532,6 +540,65 @@ def exec_bench(args):
     print(json.dumps({"metric": "exec_wall_gbp_per_s", "unit": UNIT, "exec": out}))
 
 
+def pagraph_stage_distributed(args):
+    """BASELINE configs[3] over the GPUs of one box under torchrun: rank 0 writes the synthetic input set, every rank opens it,
+    takes its contiguous share of the reads, and a step = extract + owner-partitioned NCCL all-to-all of the vertex tuples
+    and edges + join of the rank's vertex range (aligngraph2_b200/pagraph.py).  STRONG scaling: the read set is fixed."""
+    import shutil
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from aligngraph2_b200 import pagraph, synth_pg
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.pagraph_reads
+    box = [None]
+    if rank == 0:
+        box[0] = tempfile.mkdtemp(prefix="ag2_pgd_")
+        info = synth_pg.make_input_set(box[0], args.seed, max(400_000, n * 40), n, tlen=args.tlen, n_ctg=8)
+        synth_pg.solid_words_from_reads(box[0], args.pagraph_k, 0.2, local)
+    dist.broadcast_object_list(box, src=0)
+    d = box[0]
+    try:
+        j = lambda x: os.path.join(d, x)
+        job = pagraph.Job(j("solid.bin"), j("ctg.fasta"), j("ref.fasta"), d, j("c2r.ref"), device=local)
+        p = pagraph.default_params(10, 2)
+        job.load_block(0, rank, world)
+        for _ in range(2):
+            st = pagraph.extract_exchange_join(job, p)
+        torch.cuda.synchronize()
+        dist.barrier()
+        reps, t0 = 3, time.perf_counter()
+        for _ in range(reps):
+            st = pagraph.extract_exchange_join(job, p)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / reps], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sd = st.as_dict()
+        tot = torch.tensor([float(sum(sd["tuples"])), float(sum(sd["edges_raw"])), float(sd["positions"]), float(sd["edges"])], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        job.close()
+        if rank != 0:
+            return None
+        tuples, edges_raw, positions, edges = (float(x) for x in tot.tolist())
+        build_ms = float(ms.item())
+        alg_bytes = 80.0 * tuples + 100.0 * edges_raw
+        return {"workload": f"{n} synthetic pre-aligned CLR reads ({args.tlen} bp templates) vs 8 contigs + 5%-diverged reference, k={args.pagraph_k}, "
+                            f"epsilon=10, -v 2; reads sharded over {world} GPUs, owner-partitioned NCCL all-to-all", "scaling": "strong",
+                "read_bases": info["read_bases"], "vertices": sd["n_vertices"], "tuples_received_all_ranks": tuples, "edges_raw_received_all_ranks": edges_raw,
+                "positions": positions, "edges": edges, "build_ms": build_ms, "read_gbp_per_s": info["read_bases"] / (build_ms * 1e-3) / 1e9,
+                "algorithmic_GBps": alg_bytes / (build_ms * 1e-3) / 1e9, "algorithmic_frac_of_hbm_peak_per_gpu": alg_bytes / (build_ms * 1e-3) / 1e9 / peaks()[0] / world,
+                "rank0_join_ms": sd["join_ms"], "rank0_extract_ms": sd["extract_ms"]}
+    finally:
+        dist.barrier()
+        if rank == 0:
+            shutil.rmtree(d, ignore_errors=True)
+        dist.destroy_process_group()
+
+
 def cbar_guard(st) -> float:
     return max(1.0, st["cells"] / max(1, st["aligned"]))
 
@@ -596,6 +663,14 @@ def main():
     args = parse()
     if args.exec_reads > 0:
         exec_bench(args)
+        return
+    if args.only_pagraph:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        t0 = time.perf_counter()
+        out = pagraph_stage(args, int(os.environ.get("LOCAL_RANK", "0"))) if world == 1 else pagraph_stage_distributed(args)
+        if out is not None:
+            out["stage_wall_s"] = time.perf_counter() - t0
+            print(json.dumps({"metric": "pagraph_build", "n_gpus": world, "pagraph": out}))
         return
     if args.impl == "reference":
         run_reference(args)

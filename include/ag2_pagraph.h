@@ -68,6 +68,7 @@ typedef struct ag2_pg_stats {
     int64_t edges;               /* edges left after mergeEdge */
     int64_t launches;            /* kernel launches of the last build */
     double extract_ms, join_ms;  /* CUDA-event times of the two stages of the last build */
+    double join_sort_ms, join_cluster_ms, join_edges_ms;  /* join_ms split: tuple sort by vertex; first-fit clustering + (ctg, ref) order + compaction; edge sort / unique */
 } ag2_pg_stats;
 
 int ag2_pg_create(int device, ag2_pg **pg);
