@@ -38,7 +38,7 @@ def test_exports_every_declared_pagraph_symbol(lib):
         assert hasattr(lib, n), f"{n} declared in include/ag2_pagraph.h but not exported"
     from aligngraph2_b200.pagraph import EXPORTS, ALN_DTYPE, Params, Stats
     assert sorted(EXPORTS) == names
-    assert ALN_DTYPE.itemsize == 72 and C.sizeof(Params) == 48 and C.sizeof(Stats) == 128
+    assert ALN_DTYPE.itemsize == 72 and C.sizeof(Params) == 48 and C.sizeof(Stats) == 152
 
 
 def test_pagraph_refuses_without_gpu(lib, tmp_path):
@@ -58,6 +58,8 @@ def test_struct_layouts_match_header(lib):
     assert CANDIDATE_DTYPE.itemsize == 24
     assert RECORD_DTYPE.itemsize == 56
     assert C.sizeof(ExtendStats) == 80
+    from aligngraph2_b200.lib import MapStats
+    assert C.sizeof(MapStats) == 7 * 8 + 9 * 8      # ag2_map_stats: 7 doubles, 9 int64
 
 
 def test_version_and_no_cpu_fallback(lib):
