@@ -31,7 +31,6 @@ namespace {
 
 constexpr int kWideK = 23;        // 736 columns: covers every possible block (N <= 718)
 constexpr int kWideWarps = 2;
-constexpr int kNarrowK = 4;       // small batches: 128 columns, rows ~5 x shorter; falls back to kWideK
 constexpr int kMaxStreamChunks = 256;
 
 // ---------------------------------------------------------------------------------------------
@@ -301,7 +300,10 @@ __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
         t = __shfl_sync(kFull, t, 0);
         if ((int64_t)t >= g.n_chains) break;
         const int64_t chain = g.queue ? (int64_t)g.queue[t] : (int64_t)t;
-        const bool done = run_chain<K>(g, chain, sm, tb, lane, ctr);
+        // most bands that left the pair kernel's 96-column window still fit 128 columns: rows ~5 x shorter than with K = 23
+        bool done = false;
+        if (K > kNarrowK && g.try_narrow) done = run_chain<kNarrowK>(g, chain, sm, tb, lane, ctr);
+        if (!done) done = run_chain<K>(g, chain, sm, tb, lane, ctr);
         if (!done) {
             ctr.wide += 1;
             if (lane == 0 && g.wide_count) g.wide_queue[atomicAdd(g.wide_count, 1u)] = (int32_t)chain;
@@ -366,7 +368,9 @@ __global__ void __launch_bounds__(WARPS * 32) xdrop_stream_kernel(ChainArgs g, c
         chain = __shfl_sync(kFull, chain, 0);
         if (chain < 0) break;
         __threadfence();
-        const bool ok = run_chain<K>(g, chain, sm, tb, lane, ctr);
+        bool ok = false;
+        if (K > kNarrowK && g.try_narrow) ok = run_chain<kNarrowK>(g, chain, sm, tb, lane, ctr);
+        if (!ok) ok = run_chain<K>(g, chain, sm, tb, lane, ctr);
         if (!ok) ctr.wide += 1;
     }
     if (lane == 0) {
@@ -1150,6 +1154,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             cw.queue = (const int32_t *)ctx->lane_queue.p;
             cw.next = &sc->next_wide;
             cw.counters = &sc->ctr;
+            cw.try_narrow = 1;
             CK(cudaStreamSynchronize(st));
             if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
             CK(cudaGetLastError());
@@ -1209,6 +1214,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
                 w.wide_queue = nullptr;
                 w.wide_count = nullptr;
                 w.counters = &sc->ctr;
+                w.try_narrow = 1;
                 xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
                 CK(cudaGetLastError());
                 ++launches;
@@ -1453,6 +1459,7 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     cw.queue = (const int32_t *)ctx->lane_queue.p;
     cw.next = &sc->next_wide;
     cw.counters = &sc->ctr;
+    cw.try_narrow = 1;
     CK(cudaStreamSynchronize(st));
     if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
     CK(cudaGetLastError());

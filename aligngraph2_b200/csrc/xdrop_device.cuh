@@ -454,7 +454,10 @@ struct ChainArgs {
     int32_t *wide_queue;    // chains that outgrew K (written when wide_count != nullptr)
     unsigned int *wide_count;
     ChainCounters *counters;
+    int try_narrow;          // run the direction with kNarrowK columns per lane first (the kernel's K only if its band leaves that window)
 };
+
+constexpr int kNarrowK = 4;  // 128 columns: rows ~5 x shorter than with 23 columns per lane (736, any band)
 
 // One extension direction, start to finish (align_ex, MC/xdrop_gapalign.cpp:263-357).
 template <int K>
