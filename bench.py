@@ -551,7 +551,8 @@ def pagraph_stage_distributed(args):
     from aligngraph2_b200 import pagraph, synth_pg
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    quiet = StdoutToStderr()
+    quiet.enter()
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.pagraph_reads
     box = [None]
@@ -597,6 +598,27 @@ def pagraph_stage_distributed(args):
         if rank == 0:
             shutil.rmtree(d, ignore_errors=True)
         dist.destroy_process_group()
+        quiet.leave()
+
+
+class StdoutToStderr:
+    """Under torchrun NCCL prints its version banner on file descriptor 1; the contract is ONE JSON line on stdout.  Everything
+    written to fd 1 between enter() and leave() goes to stderr instead."""
+
+    def __init__(self):
+        self.saved = None
+
+    def enter(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def leave(self):
+        if self.saved is not None:
+            sys.stdout.flush()
+            os.dup2(self.saved, 1)
+            os.close(self.saved)
+            self.saved = None
 
 
 def cbar_guard(st) -> float:
@@ -687,8 +709,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: aligngraph2_b200 has no CPU path")
     torch.cuda.set_device(local)
+    quiet = StdoutToStderr()
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's own log lines (its version banner) off stdout: one JSON line there
+        quiet.enter()                                              # NCCL's version banner goes to fd 1: keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -919,7 +942,9 @@ def main():
                 "dtype": DTYPE, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": e2e, "gpu_launches": int(st["launches"]) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "full_path": full, "stages": stages,
                 "stats": {k: st[k] for k in ("cells", "rows", "blocks", "aligned", "columns", "lane_chains", "wide_chains", "interior")}}
+        quiet.leave()
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
