@@ -37,6 +37,9 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <cstdarg>
 #include <memory>
 #include <mutex>
@@ -130,7 +133,8 @@ int parse_options(int argc, char **argv, Options &o)
 }
 
 // chang_fastqfile / change_ref_fq (mecat2ref.cpp:272-395): FASTA -> ids 0.., FASTQ (4 lines) -> ids 1..
-int convert_to_fq(const char *in_path, const std::string &out_path)
+// `sink` (may be empty) sees every read as it is written: (id, sequence, length).
+int convert_to_fq(const char *in_path, const std::string &out_path, const std::function<void(int, const char *, size_t)> &sink = nullptr)
 {
     FILE *fp = fopen(in_path, "r");
     if (!fp) { fprintf(stderr, "failed to open file %s for reading.\n", in_path); exit(1); }
@@ -146,7 +150,10 @@ int convert_to_fq(const char *in_path, const std::string &out_path)
             if (ch == '>') {
                 while ((ch = getc_unlocked(fp)) != EOF && ch != '\n') {}
                 if (ch == '\n') ungetc(ch, fp);
-                if (kk > 0) fprintf(ot, "%d\t%d\t%s\n", kk - 1, (int)one.size(), one.c_str());
+                if (kk > 0) {
+                    fprintf(ot, "%d\t%d\t%s\n", kk - 1, (int)one.size(), one.c_str());
+                    if (sink) sink(kk - 1, one.data(), one.size());
+                }
                 one.clear();
                 kk++;
             } else if (ch != '\n' && ch != '\r') {
@@ -154,6 +161,7 @@ int convert_to_fq(const char *in_path, const std::string &out_path)
             }
         }
         fprintf(ot, "%d\t%d\t%s\n", kk - 1, (int)one.size(), one.c_str());
+        if (sink) sink(kk - 1, one.data(), one.size());
     } else {
         fseek(fp, 0L, SEEK_SET);
         // The reference reads a record with fscanf("%[^\n]s") / fscanf("%s\n") pairs (mecat2ref.cpp:317): the name and '+'
@@ -222,14 +230,17 @@ int convert_to_fq(const char *in_path, const std::string &out_path)
             fprintf(ot, "%d\t%d\t", ++kk, (int)slen);
             fwrite(l2, 1, slen, ot);
             fputc('\n', ot);
+            if (sink) sink(kk, l2, slen);
         }
         free(l1);
         free(l2);
         free(l3);
         free(l4);
         std::string seq, qual;
-        while (scan_line() != EOF && scan_token(seq) != EOF && scan_line() != EOF && scan_token(qual) != EOF)
+        while (scan_line() != EOF && scan_token(seq) != EOF && scan_line() != EOF && scan_token(qual) != EOF) {
             fprintf(ot, "%d\t%d\t%s\n", ++kk, (int)seq.size(), seq.c_str());
+            if (sink) sink(kk, seq.data(), seq.size());
+        }
     }
     fclose(fp);
     fclose(ot);
@@ -805,6 +816,86 @@ std::vector<int> device_list()
     return devs;
 }
 
+// load_fastq's batches (mecat2ref_impl_large.cpp:1965-1991: up to SVM reads / MAXSTR characters, plus the record that ended
+// the loop) straight from the conversion of the reads file: chang_fastqfile's pass over the FASTA / FASTQ input runs on
+// its own thread, writes <wrk>/0.fq as ever, and hands every batch to the mapping as soon as it is complete -- the reference
+// (and round 1) finish the conversion first and then parse 0.fq again.
+struct ReadBatch {
+    std::string bases;
+    std::vector<int64_t> offs;
+    std::vector<int> ids;
+};
+
+class ReadFeeder {
+public:
+    ReadFeeder(const char *in_path, const std::string &out_path)
+    {
+        th_ = std::thread([this, in_path, out_path] {
+            auto cur = std::make_unique<ReadBatch>();
+            cur->offs.assign(1, 0);
+            long sum = 0;
+            auto push = [&](std::unique_ptr<ReadBatch> b) {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return q_.size() < 2; });
+                q_.push_back(std::move(b));
+                cv_.notify_all();
+            };
+            const int n = convert_to_fq(in_path, out_path, [&](int id, const char *seq, size_t len) {
+                const bool within = (int)cur->ids.size() < kSVM && sum < kMAXSTR;
+                cur->bases.append(seq, len);
+                cur->offs.push_back((int64_t)cur->bases.size());
+                cur->ids.push_back(id);
+                sum += (long)len + 1;
+                if (!within) {
+                    push(std::move(cur));
+                    cur = std::make_unique<ReadBatch>();
+                    cur->offs.assign(1, 0);
+                    sum = 0;
+                }
+            });
+            if (!cur->ids.empty()) push(std::move(cur));
+            std::lock_guard<std::mutex> g(m_);
+            count_ = n;
+            done_ = true;
+            cv_.notify_all();
+        });
+    }
+    // next batch, or null at the end of the file
+    std::unique_ptr<ReadBatch> next()
+    {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return !q_.empty() || done_; });
+        if (q_.empty()) return nullptr;
+        std::unique_ptr<ReadBatch> b = std::move(q_.front());
+        q_.erase(q_.begin());
+        cv_.notify_all();
+        return b;
+    }
+    // number of reads; waits for the conversion to end (batches nobody took are dropped)
+    int finish()
+    {
+        {
+            std::unique_lock<std::mutex> g(m_);
+            while (!done_) {
+                q_.clear();
+                cv_.notify_all();
+                cv_.wait_for(g, std::chrono::milliseconds(20));
+            }
+        }
+        if (th_.joinable()) th_.join();
+        return count_;
+    }
+    ~ReadFeeder() { finish(); }
+
+private:
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::vector<std::unique_ptr<ReadBatch>> q_;
+    bool done_ = false;
+    int count_ = 0;
+};
+
 // Page-locked result buffers (ag2_host_alloc), recycled between batches: a fresh std::vector of a gigabyte is a second of
 // page faults and zero-filling, and device copies into pageable memory run at a fraction of the PCIe rate.
 class PinnedPool {
@@ -877,7 +968,7 @@ template <class F> void on_every_device(std::vector<DeviceShard> &sh, F f)
 }
 
 // the mapping part of meap_ref_impl_large (:1994-2149) on the GPU; returns seconds {read index, ref index, mapping}
-void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3], ResultWriter &rw)
+void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3], ResultWriter &rw, ReadFeeder &feeder)
 {
     const std::vector<int> devs = device_list();
     std::vector<DeviceShard> sh;
@@ -893,7 +984,8 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3], Re
     }
     if (sh.empty()) {
         fprintf(stderr, "mecat2ref (aligngraph2_b200): no usable CUDA device; there is no CPU path\n");
-        exit(1);
+        fflush(stderr);
+        _exit(1);   // the conversion thread is still writing 0.fq: no stdio teardown under it
     }
     const size_t ndev = sh.size();
     double t0 = now_sec();
@@ -903,62 +995,19 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3], Re
     });
     secs[1] = now_sec() - t0;
     const std::string wrk = o.wrk_dir;
-    FILE *fq = fopen((wrk + "/0.fq").c_str(), "r");
-    if (!fq) { fprintf(stderr, "failed to open %s/0.fq\n", wrk.c_str()); exit(1); }
     for (int t = 2; t <= o.num_cores; ++t) fclose(fopen((wrk + "/" + std::to_string(t) + ".r").c_str(), "w"));
     for (int t = 1; t <= o.num_cores; ++t) fclose(fopen((wrk + "/ref" + std::to_string(t) + ".r").c_str(), "w"));
 
-    char *line = nullptr;
-    size_t cap = 0;
-    // load_fastq (:1965-1991): up to SVM reads / MAXSTR characters, plus the record that ended the loop
-    struct Batch {
-        std::string bases;
-        std::vector<int64_t> offs;
-        std::vector<int> ids;
-        bool more = false;
-    };
-    auto load_fastq = [&](Batch &b) {
-        b.bases.clear();
-        b.offs.assign(1, 0);
-        b.ids.clear();
-        b.more = false;
-        long sum = 0;
-        for (;;) {
-            const ssize_t n = getline(&line, &cap, fq);
-            if (n < 0) break;
-            int readno = 0, readlen = 0;
-            int consumed = 0;
-            if (sscanf(line, "%d\t%d\t%n", &readno, &readlen, &consumed) < 2) continue;
-            size_t len = (size_t)n - (size_t)consumed;
-            while (len && (line[consumed + len - 1] == '\n' || line[consumed + len - 1] == '\r')) --len;
-            const bool within = (int)b.ids.size() < kSVM && sum < kMAXSTR;
-            b.bases.append(line + consumed, len);
-            b.offs.push_back((int64_t)b.bases.size());
-            b.ids.push_back(readno);
-            sum += (long)len + 1;
-            if (!within) {
-                b.more = true;
-                break;
-            }
-        }
-    };
-    // two batches in flight: while the GPUs map one and its records are printed, a second thread parses the next
+    // the batches come from the conversion thread (ReadFeeder); while the GPUs map one and the writer prints the one before,
+    // the feeder is already parsing the next
     PinnedPool pool;
     std::thread writer;
-    Batch batches[2];
-    int cur_i = 0;
-    load_fastq(batches[0]);
     bool first_batch = true;
     secs[0] = secs[2] = 0;
     for (;;) {
-        Batch &cur = batches[cur_i];
-        if (cur.ids.empty()) break;
-        std::thread ahead;
-        if (cur.more) ahead = std::thread([&load_fastq, &batches, cur_i] { load_fastq(batches[cur_i ^ 1]); });
-        struct JoinAhead {   // on every way out of this round, the exits of die_ag2 aside
-            std::thread &t;
-            ~JoinAhead() { if (t.joinable()) t.join(); }
-        } join_ahead{ahead};
+        std::unique_ptr<ReadBatch> cur_p = feeder.next();
+        if (!cur_p) break;
+        const ReadBatch &cur = *cur_p;
         const std::string &bases = cur.bases;
         const std::vector<int64_t> &offs = cur.offs;
         const std::vector<int> &ids = cur.ids;
@@ -1045,12 +1094,8 @@ void map_on_gpu(const Options &o, const std::string &ref_seq, double secs[3], Re
                 pool.give(res->s[k]);
             }
         });
-        if (!cur.more) break;
-        cur_i ^= 1;   // the batch read ahead (join_ahead waits for it before the next round starts)
     }
     if (writer.joinable()) writer.join();
-    free(line);
-    fclose(fq);
     for (DeviceShard &d : sh) ag2_ctx_destroy(d.ctx);
 }
 
@@ -1072,15 +1117,21 @@ int main(int argc, char **argv)
         if (trace) fprintf(stderr, "[mecat2ref host] %-28s %8.3f s\n", what, now_sec() - t_stage);
         t_stage = now_sec();
     };
-    const int readcount = convert_to_fq(o.reads, wrk + "/0.fq");
+    // chang_fastqfile on its own thread: <wrk>/0.fq is written as ever while the batches already go to the GPUs
+    const bool skip_map = getenv("AG2_SKIP_MAP") != nullptr;
+    std::unique_ptr<ReadFeeder> feeder;
+    int readcount = 0;
+    if (skip_map) readcount = convert_to_fq(o.reads, wrk + "/0.fq");
+    else feeder = std::make_unique<ReadFeeder>(o.reads, wrk + "/0.fq");
     const int refcount = convert_to_fq(o.reference, wrk + "/ref.fq");
-    stage_done("inputs -> 0.fq, ref.fq");
-    {
+    stage_done("reference -> ref.fq (reads -> 0.fq on its own thread)");
+    auto write_config = [&]() {
         FILE *cfg = fopen("config.txt", "w");
-        if (!cfg) { fprintf(stderr, "failed to open config.txt for writing\n"); return 1; }
+        if (!cfg) { fprintf(stderr, "failed to open config.txt for writing\n"); exit(1); }
         fprintf(cfg, "%s\n%s\n%s\n%s\n%s\n%d\t%d\n%d\n", o.wrk_dir, o.reference, o.reads, o.output, o.refoutput, o.num_cores, readcount, refcount);
         fclose(cfg);
-    }
+    };
+    if (skip_map) write_config();
     printf("first task is sucess\n");
     double secs[3] = {0, 0, 0};
     bool wrote_results = false;
@@ -1094,9 +1145,11 @@ int main(int argc, char **argv)
             // 1.r, -o and -p are written from the records in memory while the mapping goes on
             const std::vector<ChrInfo> chr0 = read_chrindex(wrk);
             ResultWriter rw(o, chr0, argc, argv);
-            map_on_gpu(o, ref_seq, secs, rw);
+            map_on_gpu(o, ref_seq, secs, rw, *feeder);
             rw.finish();
             wrote_results = true;
+            readcount = feeder->finish();
+            write_config();   // (the reference writes it before the mapping; nothing reads it in between)
         }
         secs[1] += t_load;
         stage_done("mapping (read, map, 1.r, -o, -p)");
