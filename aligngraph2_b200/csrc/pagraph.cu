@@ -11,6 +11,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -21,32 +22,125 @@ using namespace ag2pg;
 
 namespace {
 
-template <typename T>
+// Device allocations of a handle are recycled: a build allocates and frees ~25 arrays of up to several GB, and cudaMalloc /
+// cudaFree of that much is slower than the kernels that use it (40 k reads: ~160 of 284 ms per build).  A block goes back to
+// the pool of the handle whose entry point is running (PoolScope) and is handed out again for a request it fits within
+// 25 %; blocks of a handle are only ever used on that handle's stream, so stream order keeps reuse safe.
+struct DevPool {
+    struct Block {
+        void* p;
+        size_t bytes;
+        int device;
+    };
+    std::vector<Block> free_;
+    size_t cached = 0;
+    static constexpr size_t kCap = (size_t)64 << 30;   // bytes kept at most
+    void* take(size_t bytes, int device, size_t* got)
+    {
+        size_t best = free_.size();
+        for (size_t i = 0; i < free_.size(); ++i)
+            if (free_[i].device == device && free_[i].bytes >= bytes && free_[i].bytes <= bytes + bytes / 4 + ((size_t)1 << 20) &&
+                (best == free_.size() || free_[i].bytes < free_[best].bytes))
+                best = i;
+        if (best == free_.size()) return nullptr;
+        void* p = free_[best].p;
+        *got = free_[best].bytes;
+        cached -= free_[best].bytes;
+        free_.erase(free_.begin() + (long)best);
+        return p;
+    }
+    bool give(void* p, size_t bytes, int device)
+    {
+        if (cached + bytes > kCap) return false;
+        free_.push_back({p, bytes, device});
+        cached += bytes;
+        return true;
+    }
+    void flush()
+    {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (Block& b : free_) {
+            cudaSetDevice(b.device);
+            cudaFree(b.p);
+        }
+        cudaSetDevice(cur);
+        free_.clear();
+        cached = 0;
+    }
+};
+thread_local DevPool* tl_pool = nullptr;
+struct PoolScope {
+    DevPool* prev;
+    explicit PoolScope(DevPool* p) : prev(tl_pool) { tl_pool = p; }
+    ~PoolScope() { tl_pool = prev; }
+};
+
+template <class T>
 struct Dev {
     T* p = nullptr;
     int64_t n = 0;
+    size_t bytes = 0;   // of the underlying block
+    int device = -1;
     Dev() = default;
     Dev(const Dev&) = delete;
     Dev& operator=(const Dev&) = delete;
     ~Dev() { release(); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && !(tl_pool && device >= 0 && tl_pool->give(p, bytes, device))) cudaFree(p);
         p = nullptr;
         n = 0;
+        bytes = 0;
     }
     cudaError_t alloc(int64_t count)
     {
         release();
         if (count <= 0) count = 1;
-        cudaError_t e = cudaMalloc((void**)&p, (size_t)count * sizeof(T));
-        if (e == cudaSuccess) n = count;
+        const size_t want = (((size_t)count * sizeof(T)) + 511) & ~(size_t)511;
+        cudaGetDevice(&device);
+        if (tl_pool) {
+            size_t got = 0;
+            if (void* q = tl_pool->take(want, device, &got)) {
+                p = (T*)q;
+                n = count;
+                bytes = got;
+                return cudaSuccess;
+            }
+        }
+        cudaError_t e = cudaMalloc((void**)&p, want);
+        if (e != cudaSuccess && tl_pool && tl_pool->cached) {   // out of memory with blocks parked in the pool: give them up
+            cudaGetLastError();
+            tl_pool->flush();
+            e = cudaMalloc((void**)&p, want);
+        }
+        if (e == cudaSuccess) {
+            n = count;
+            bytes = want;
+        } else {
+            p = nullptr;
+        }
         return e;
     }
     void swap(Dev& o)
     {
         std::swap(p, o.p);
         std::swap(n, o.n);
+        std::swap(bytes, o.bytes);
+        std::swap(device, o.device);
+    }
+};
+
+// AG2_PG_TRACE=1: host wall clock between the marks of a build, on stderr
+struct Lap {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    bool on = getenv("AG2_PG_TRACE") != nullptr;
+    void mark(const char* what)
+    {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ag2_pg trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
     }
 };
 
@@ -110,6 +204,7 @@ struct ag2_pg {
 
     Dev<unsigned char> cub_tmp;
     ag2_pg_stats stats{};
+    DevPool pool;   // recycled device blocks of this handle (see DevPool)
 };
 
 namespace {
@@ -494,6 +589,7 @@ void ag2_pg_destroy(ag2_pg* pg)
     for (auto& e : pg->ev)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(pg->stream);
+    pg->pool.flush();
     delete pg;
 }
 
@@ -515,6 +611,7 @@ void* ag2_pg_stream(ag2_pg* pg) { return pg ? (void*)pg->stream : nullptr; }
 
 int ag2_pg_set_kmers(ag2_pg* pg, const uint64_t* words, int64_t n_words, int64_t* n_vertices)
 {
+    PoolScope pool_scope(pg ? &pg->pool : nullptr);
     if (!pg || !words || n_words < 1) return fail(pg, AG2_EINVAL, "ag2_pg_set_kmers: bad arguments");
     PG_CUDA(cudaSetDevice(pg->device));
     const uint64_t k = words[0];
@@ -575,6 +672,7 @@ int ag2_pg_fetch_codes(ag2_pg* pg, uint64_t* out, int64_t cap)
 
 int ag2_pg_set_targets(ag2_pg* pg, const int64_t* ctg_len, int64_t n_ctg, const int64_t* ref_len, int64_t n_ref)
 {
+    PoolScope pool_scope(pg ? &pg->pool : nullptr);
     if (!pg || n_ctg < 0 || n_ref < 0 || (n_ctg && !ctg_len) || (n_ref && !ref_len)) return fail(pg, AG2_EINVAL, "ag2_pg_set_targets: bad arguments");
     PG_CUDA(cudaSetDevice(pg->device));
     pg->ctg_len.assign(ctg_len, ctg_len + n_ctg);
@@ -599,6 +697,7 @@ int ag2_pg_set_targets(ag2_pg* pg, const int64_t* ctg_len, int64_t n_ctg, const 
 
 int ag2_pg_set_reads(ag2_pg* pg, const char* bases, const int64_t* offs, int64_t n_reads, int64_t first_read)
 {
+    PoolScope pool_scope(pg ? &pg->pool : nullptr);
     if (!pg || n_reads < 0 || first_read < 0 || !offs || (n_reads && !bases && offs[n_reads] > 0)) return fail(pg, AG2_EINVAL, "ag2_pg_set_reads: bad arguments");
     PG_CUDA(cudaSetDevice(pg->device));
     pg->n_reads = n_reads;
@@ -637,6 +736,7 @@ int ag2_pg_set_reads(ag2_pg* pg, const char* bases, const int64_t* offs, int64_t
 
 int ag2_pg_set_alignments(ag2_pg* pg, int which, const ag2_pg_aln* alns, int64_t n, const char* text, int64_t text_len)
 {
+    PoolScope pool_scope(pg ? &pg->pool : nullptr);
     if (!pg || which < 0 || which > 2 || n < 0 || (n && !alns) || text_len < 0 || (text_len && !text))
         return fail(pg, AG2_EINVAL, "ag2_pg_set_alignments: bad arguments");
     PG_CUDA(cudaSetDevice(pg->device));
@@ -677,6 +777,7 @@ int ag2_pg_set_filters(ag2_pg* pg, const uint8_t* ref_flag, const uint8_t* ctg_f
 
 int ag2_pg_extract(ag2_pg* pg, const ag2_pg_params* params)
 {
+    PoolScope pool_scope(pg ? &pg->pool : nullptr);
     if (!pg || !params) return fail(pg, AG2_EINVAL, "ag2_pg_extract: bad arguments");
     PG_TRY(check_ready(pg));
     if (params->outer_sample < 1) return fail(pg, AG2_EINVAL, "ag2_pg_extract: outer_sample must be >= 1");
@@ -686,14 +787,18 @@ int ag2_pg_extract(ag2_pg* pg, const ag2_pg_params* params)
     pg->stats = ag2_pg_stats{};
     pg->stats.n_vertices = nv;
     pg->have_graph = pg->have_streams = false;
+    Lap lap;
     PG_TRY(build_ctg_table(pg));
+    lap.mark("extract: ctg table");
 
     PhasePlan plan[2];
     plan_phase0(pg, P, plan[0]);
     plan_phase1(pg, P, plan[1]);
+    lap.mark("extract: plans (host)");
     PG_CUDA(cudaEventRecord(pg->ev[0], pg->stream));
     PhaseDev dev[2];
     for (int ph = 0; ph < 2; ++ph) PG_TRY(run_walk_and_count(pg, ph, P, plan[ph], dev[ph]));
+    lap.mark("extract: walk + count");
     const unsigned long long nt = dev[0].total.tuples + dev[1].total.tuples, ne = dev[0].total.edges + dev[1].total.edges;
     if (nt >= 0xffffffffull || ne >= 0xffffffffull) return fail(pg, AG2_ECAP, "ag2_pg_extract: %llu tuples / %llu edges exceed the 32-bit stream index", nt, ne);
     PG_CUDA(pg->t_vertex.alloc((int64_t)nt));
@@ -702,6 +807,7 @@ int ag2_pg_extract(ag2_pg* pg, const ag2_pg_params* params)
     PG_CUDA(pg->e_from.alloc((int64_t)ne));
     PG_CUDA(pg->e_to.alloc((int64_t)ne));
     PG_CUDA(pg->e_step.alloc((int64_t)ne));
+    lap.mark("extract: stream allocation");
     for (int ph = 0; ph < 2; ++ph) {
         const int64_t n_lanes = (int64_t)plan[ph].lanes.size();
         pg->stats.lanes[ph] = n_lanes;
@@ -728,6 +834,7 @@ int ag2_pg_extract(ag2_pg* pg, const ag2_pg_params* params)
     float ms = 0;
     cudaEventElapsedTime(&ms, pg->ev[0], pg->ev[1]);
     pg->stats.extract_ms = ms;
+    lap.mark("extract: emit kernels");
     pg->n_tuples = (int64_t)nt;
     pg->n_edges = (int64_t)ne;
     pg->have_streams = true;
@@ -736,6 +843,7 @@ int ag2_pg_extract(ag2_pg* pg, const ag2_pg_params* params)
 
 int ag2_pg_partition(ag2_pg* pg, int n_owners, int64_t* counts)
 {
+    PoolScope pool_scope(pg ? &pg->pool : nullptr);
     if (!pg || n_owners < 1 || !counts) return fail(pg, AG2_EINVAL, "ag2_pg_partition: bad arguments");
     if (!pg->have_streams) return fail(pg, AG2_ESTATE, "ag2_pg_partition: no streams (call ag2_pg_extract)");
     PG_CUDA(cudaSetDevice(pg->device));
@@ -771,6 +879,8 @@ int ag2_pg_partition(ag2_pg* pg, int n_owners, int64_t* counts)
             pg->e_to.swap(b);
             std::swap(*(uint32_t**)&pg->e_step.p, c.p);
             std::swap(pg->e_step.n, c.n);
+            std::swap(pg->e_step.bytes, c.bytes);
+            std::swap(pg->e_step.device, c.device);
         }
         pg->stats.launches += 2;
     }
@@ -795,6 +905,7 @@ int ag2_pg_stream_dev(ag2_pg* pg, int64_t* n_tuples, void** tuple_dev3, int64_t*
 
 int ag2_pg_import_dev(ag2_pg* pg, int64_t n_tuples, void* const* tuple_dev3, int64_t n_edges, void* const* edge_dev3)
 {
+    PoolScope pool_scope(pg ? &pg->pool : nullptr);
     if (!pg || n_tuples < 0 || n_edges < 0 || (n_tuples && !tuple_dev3) || (n_edges && !edge_dev3)) return fail(pg, AG2_EINVAL, "ag2_pg_import_dev: bad arguments");
     if (n_tuples >= 0xffffffffll || n_edges >= 0xffffffffll) return fail(pg, AG2_ECAP, "ag2_pg_import_dev: streams exceed the 32-bit index");
     PG_CUDA(cudaSetDevice(pg->device));
@@ -1003,6 +1114,7 @@ int ag2_pg_group_gather(ag2_pg* const* pgs, int n)
 
 int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
 {
+    PoolScope pool_scope(pg ? &pg->pool : nullptr);
     if (!pg || !params) return fail(pg, AG2_EINVAL, "ag2_pg_join: bad arguments");
     if (!pg->have_streams) return fail(pg, AG2_ESTATE, "ag2_pg_join: no streams (call ag2_pg_extract)");
     if (params->epsilon < 0) return fail(pg, AG2_EINVAL, "ag2_pg_join: epsilon < 0");
@@ -1010,6 +1122,7 @@ int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
     const int64_t nv = pg->n_vertices, nt = pg->n_tuples, ne = pg->n_edges;
     const uint32_t eps = (uint32_t)std::min<int64_t>(params->epsilon, 0xffffffffll);
     const int vbits = bits_for((uint64_t)std::max<int64_t>(nv, 1));
+    Lap lap;
     PG_CUDA(cudaEventRecord(pg->ev[2], pg->stream));
 
     // ---- positions: stable sort by vertex, per-vertex first-fit clustering, (ctg, ref) order, compaction
@@ -1031,6 +1144,7 @@ int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
     PG_CUDA(o_ctg.alloc(nt));
     PG_CUDA(o_ref.alloc(nt));
     PG_CUDA(o_cnt.alloc(nt));
+    lap.mark("join: position allocations");
     if (nt) {
         pg_hist_kernel<<<grid_for(nt), 256, 0, pg->stream>>>(pg->t_vertex.p, nt, seg_cnt.p);
         pg_pack_pairs_kernel<<<grid_for(nt), 256, 0, pg->stream>>>(pg->t_ctg.p, pg->t_ref.p, nt, items.p);
@@ -1065,6 +1179,7 @@ int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
         ++pg->stats.launches;
     }
     pg->g_npos = (int64_t)npos;
+    lap.mark("join: positions (kernels)");
     PG_CUDA(cudaEventRecord(pg->ev[1], pg->stream));          // positions done: the edges start
 
     // ---- edges: sort by (from, to, step), unique
@@ -1080,6 +1195,7 @@ int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
     PG_CUDA(e_cnt64.alloc(nv + 1));
     PG_CUDA(pg->g_edge_off.alloc(nv + 1));
     PG_CUDA(cudaMemsetAsync(per_vertex.p, 0, (size_t)(nv + 1) * 4, pg->stream));
+    lap.mark("join: edge allocations");
     unsigned long long nedge = 0;
     if (ne) {
         pg_pack_pairs_kernel<<<grid_for(ne), 256, 0, pg->stream>>>(pg->e_to.p, pg->e_from.p, ne, ft.p);   // to | from << 32
@@ -1117,6 +1233,7 @@ int ag2_pg_join(ag2_pg* pg, const ag2_pg_params* params)
     pg->stats.join_cluster_ms = ms;
     cudaEventElapsedTime(&ms, pg->ev[1], pg->ev[3]);
     pg->stats.join_edges_ms = ms;
+    lap.mark("join: edges (kernels)");
     pg->stats.positions = pg->g_npos;
     pg->stats.edges = pg->g_nedge;
     pg->have_graph = true;
