@@ -372,6 +372,7 @@ __device__ int seed_cta_build(const RefIndex &ix, const uint32_t *reads2, const 
 {
     const int tid = threadIdx.x;
     const int cleave_num = (rlen - kSeedLen) / BC + 1;
+    if (cleave_num > 0x7fff) return -1;   // the seed number has 15 bits here (reads beyond the reference's RM = 100 000 characters): thread path
     int n_ev = 0;
     bool overflow = false;
     uint64_t *ev = sm.ev;
