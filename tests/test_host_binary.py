@@ -232,3 +232,49 @@ def test_fastq_token_semantics_match_reference(binary, tmp_path):
         outs[who] = (d / "wrk" / "0.fq").read_bytes()
     assert outs["ours"] == outs["ref"]
     assert outs["ref"].count(b"\n") == 7
+
+
+@pytest.mark.parametrize("fmt", ["1", "2"])
+def test_m4_and_sam_formats_match_reference(binary, tmp_path, fmt):
+    """`-m 1` (m4) and `-m 2` (SAM) of result_combine / polish_result (output.cpp:45-186): the reference binary maps the stress
+    fixture and writes -o / -p in that format; the drop-in executable makes the same files from the reference's thread file
+    (AG2_SKIP_MAP: no GPU needed -- the GPU run goes through the same formatters, see the test below).  SAM's @PG line
+    carries argv[0], which differs by construction."""
+    from oracle import binding
+    if not os.path.exists(binding.REF_BIN):
+        pytest.skip("oracle/_ref/mecat2ref not built on this box")
+    args = ARGS + ["-m", fmt]
+    a, b = tmp_path / "ref", tmp_path / "ours"
+    for d in (a, b):
+        d.mkdir()
+        _inputs(d)
+    subprocess.run([binding.REF_BIN, "-t", "1"] + args, cwd=a, check=True, capture_output=True)
+    (b / "wrk").mkdir()
+    (b / "wrk" / "1.r").write_bytes((a / "wrk" / "1.r").read_bytes())
+    r = subprocess.run([binary] + args, cwd=b, env=dict(os.environ, AG2_SKIP_MAP="1"), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    norm = lambda blob: b"\n".join(ln for ln in blob.split(b"\n") if not ln.startswith(b"@PG"))
+    for name in ("o.txt", "p.txt"):
+        want, got = (a / name).read_bytes(), (b / name).read_bytes()
+        assert len(want) > 1000
+        assert norm(got) == norm(want), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["1", "2"])
+def test_m4_and_sam_formats_whole_program(binary, tmp_path, fmt):
+    """The same formats from a mapping run (records formatted from memory by the ResultWriter)."""
+    from oracle import binding
+    if not os.path.exists(binding.REF_BIN):
+        pytest.skip("oracle/_ref/mecat2ref not built on this box")
+    args = ARGS + ["-m", fmt]
+    a, b = tmp_path / "ref", tmp_path / "gpu"
+    for d in (a, b):
+        d.mkdir()
+        _inputs(d)
+    subprocess.run([binding.REF_BIN, "-t", "1"] + args, cwd=a, check=True, capture_output=True)
+    r = subprocess.run([binary] + args, cwd=b, capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    norm = lambda blob: b"\n".join(ln for ln in blob.split(b"\n") if not ln.startswith(b"@PG"))
+    for name in ("o.txt", "p.txt"):
+        assert norm((b / name).read_bytes()) == norm((a / name).read_bytes()), name
