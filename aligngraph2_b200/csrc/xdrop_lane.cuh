@@ -533,6 +533,35 @@ __device__ void lane_kernel_body(const LaneArgs &g, LaneSmem &sm, int tid, uint8
     atomicAdd(&g.counters->wide, wide);
 }
 
+// dst[i] = src[i] (forward) or src[-i] (reverse) for i < n, by the 32 lanes of a warp: 4 bytes per lane and step through
+// ALIGNED destination words (two aligned source words, a funnel shift, and a byte reversal when the order flips); the up to
+// 3 + 3 bytes around them singly.  Sources lie inside the workspace strings, which are allocated with slack on both sides of
+// what the shifted word loads touch.
+__device__ __forceinline__ void warp_copy_bytes(char *dst, const char *src, int n, bool reverse, int lane)
+{
+#ifdef AG2_EMU
+    for (int i = lane; i < n; i += 32) dst[i] = reverse ? src[-i] : src[i];
+#else
+    int head = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+    if (head > n) head = n;
+    if (lane < head) dst[lane] = reverse ? src[-lane] : src[lane];
+    const int nw = (n - head) >> 2;
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst + head);
+    for (int w = lane; w < nw; w += 32) {
+        const char *first = reverse ? src - (head + 4 * w) - 3 : src + head + 4 * w;   // lowest address of the 4 source bytes
+        const uintptr_t a = reinterpret_cast<uintptr_t>(first) & ~(uintptr_t)3;
+        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(first) & 3) * 8;
+        const uint32_t lo = *reinterpret_cast<const uint32_t *>(a);
+        const uint32_t hi = sh ? *reinterpret_cast<const uint32_t *>(a + 4) : 0u;
+        uint32_t x = __funnelshift_r(lo, hi, sh);
+        if (reverse) x = __byte_perm(x, 0, 0x0123);
+        d[w] = x;
+    }
+    const int done = head + 4 * nw;
+    if (lane < n - done) dst[done + lane] = reverse ? src[-(done + lane)] : src[done + lane];
+#endif
+}
+
 // Dense strings of one record from the two directions' workspace areas.  Executed by one warp.
 //   left, lane path : blocks last -> first, each in walk order, minus the very first column (:401-402)
 //   right, lane path: blocks first -> last, each in reversed walk order
@@ -545,10 +574,8 @@ __device__ void assemble_record(const ExtGeom &ge, const ChainResult &l, const C
     if (l.ncols > 1) {
         if (l.mode == 1) {
             const int64_t src = ge.slot + ge.capL - l.ncols + 1;
-            for (int i = lane; i < l.ncols - 1; i += 32) {
-                out_q[i] = ws_q[src + i];
-                out_t[i] = ws_t[src + i];
-            }
+            warp_copy_bytes(out_q, ws_q + src, l.ncols - 1, false, lane);
+            warp_copy_bytes(out_t, ws_t + src, l.ncols - 1, false, lane);
             o = l.ncols - 1;
         } else {
             int64_t end = ge.slot; // one past the last block's segment
@@ -564,10 +591,8 @@ __device__ void assemble_record(const ExtGeom &ge, const ChainResult &l, const C
                     ++lo;
                     drop = false;
                 }
-                for (int i = lo + lane; i < n; i += 32) {
-                    out_q[o + i - lo] = ws_q[seg + i];
-                    out_t[o + i - lo] = ws_t[seg + i];
-                }
+                warp_copy_bytes(out_q + o, ws_q + seg + lo, n - lo, false, lane);
+                warp_copy_bytes(out_t + o, ws_t + seg + lo, n - lo, false, lane);
                 o += n - lo;
             }
         }
@@ -575,20 +600,16 @@ __device__ void assemble_record(const ExtGeom &ge, const ChainResult &l, const C
     // ---- right ----
     if (r.mode == 1) {
         const int64_t src = ge.slot + ge.capL;
-        for (int i = lane; i < r.ncols; i += 32) {
-            out_q[o + i] = ws_q[src + i];
-            out_t[o + i] = ws_t[src + i];
-        }
+        warp_copy_bytes(out_q + o, ws_q + src, r.ncols, false, lane);
+        warp_copy_bytes(out_t + o, ws_t + src, r.ncols, false, lane);
     } else {
         int64_t seg = ge.slot + ge.capL;
         for (int k = 0; k < r.nblocks; ++k) {
             const uint32_t w = meta[ge.meta + ge.nmetaL + k];
             const int n = (int)(w & 0xffffu), skip = (int)(w >> 16);
             const int e = n - skip;
-            for (int i = lane; i < e; i += 32) {
-                out_q[o + i] = ws_q[seg + n - 1 - i];
-                out_t[o + i] = ws_t[seg + n - 1 - i];
-            }
+            warp_copy_bytes(out_q + o, ws_q + seg + n - 1, e, true, lane);
+            warp_copy_bytes(out_t + o, ws_t + seg + n - 1, e, true, lane);
             o += e;
             seg += n;
         }
