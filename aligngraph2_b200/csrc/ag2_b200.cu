@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kLaneThreads) xdrop_lane_kernel(LaneArgs g)
 
 // Pair path (xdrop_pair.cuh): two directions per thread in packed 16-bit arithmetic, 64 directions in lock step
 // per warp.  The dominant kernel; the lane kernel above restarts the directions it hands over.
-__global__ void __launch_bounds__(kPairThreads, 7) xdrop_pair_kernel(LaneArgs g)
+__global__ void __launch_bounds__(kPairThreads, 8) xdrop_pair_kernel(LaneArgs g)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PairSmem &sm = *reinterpret_cast<PairSmem *>(smem_raw);
@@ -1933,7 +1933,8 @@ static size_t seed_limit(ag2_ctx *ctx)
 struct SeedCtl {
     unsigned next1, ovf1, next2, ovf2;            // seeding: CTA launch 1, its overflow, CTA launch 2, its overflow
     unsigned plan_n, pnext1, povf1, pnext2, povf2; // planning: listed items, then as above
-    unsigned pad[7];
+    unsigned snext[3], sovf[3];                   // seeding with three CTA launches (seed_stage)
+    unsigned pad[1];
 };
 
 constexpr int kSeedCapMax = 13824;   // index hits per strand that fit the 227 KB of shared memory of one CTA
@@ -1954,6 +1955,26 @@ static int seed_cap(const ag2_ctx *ctx, int pass, int tier)
     const double ev = (mean_len / bc + 1.0) * (density + 0.2);
     const int cap = ((int)(ev * 1.25) + 128 + 127) & ~127;
     return std::max(256, std::min(kSeedCapMax, cap));
+}
+
+// A tighter table for the FIRST launch (6 % + 32 over the expected number of events) where that fits one more CTA on an SM
+// and still leaves the SM ~4 KB of L1: the kernel is latency-bound (3 -> 4 CTAs per SM at 250 Mb: 75 -> 65 ms per 250 k
+// reads; with no L1 left it was 82 ms), and the few reads the smaller table turns away go to the next launch.  0 = none.
+static int seed_cap_tight(const ag2_ctx *ctx, const void *kernel, int pass, int cap)
+{
+    if (getenv("AG2_SEED_CAP")) return 0;
+    const double mean_len = ctx->n_reads ? (double)ctx->read_bases / (double)ctx->n_reads : 10000.0;
+    const double bc = pass == 0 ? std::min(20.0, 5.0 + mean_len / 1000.0) : 5.0;
+    const double ev = (mean_len / bc + 1.0) * ((double)ctx->ix_npos / (double)kNCodes + 0.2);
+    const int floor_cap = std::max(256, ((int)(ev * 1.06) + 32 + 63) & ~63);
+    int occ0 = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, kernel, kSeedCtaThreads, seed_cta_smem_bytes(cap)) != cudaSuccess) return 0;
+    for (int c = cap - 64; c >= floor_cap; c -= 64) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kSeedCtaThreads, seed_cta_smem_bytes(c) + 1024) != cudaSuccess) break;
+        if (occ > occ0) return c;
+    }
+    return 0;
 }
 
 static int seed_cta_config(ag2_ctx *ctx, const void *kernel, int cap, size_t *smem_out, int *grid_out)
@@ -2016,8 +2037,16 @@ static int seed_stage(ag2_ctx *ctx, int pass, int maxc, const int32_t *d_reads, 
     RESERVE(ctx->seed_ovf2, (size_t)n * 4);
     SeedCtl *ctl = (SeedCtl *)ctx->seed_ctl.p;
     CK(cudaMemsetAsync(ctl, 0, sizeof(SeedCtl), st));
-    const int caps[2] = {seed_cap(ctx, pass, 0), seed_cap(ctx, pass, 1)};
-    for (int tier = 0; tier < 2; ++tier) {
+    CK(cudaFuncSetAttribute((const void *)seed_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)seed_cta_smem_bytes(kSeedCapMax)));
+    int caps[3], n_tiers = 0;
+    {
+        const int standard = seed_cap(ctx, pass, 0), tight = seed_cap_tight(ctx, (const void *)seed_cta_kernel, pass, standard);
+        if (tight > 0) caps[n_tiers++] = tight;
+        caps[n_tiers++] = standard;
+        caps[n_tiers++] = seed_cap(ctx, pass, 1);
+    }
+    DevBuf *lists[2] = {&ctx->seed_ovf1, &ctx->seed_ovf2};   // launch t reads the list launch t - 1 wrote, and writes the other one
+    for (int tier = 0; tier < n_tiers; ++tier) {
         size_t smem = 0;
         int grid = 0;
         int rc = seed_cta_config(ctx, (const void *)seed_cta_kernel, caps[tier], &smem, &grid);
@@ -2031,17 +2060,17 @@ static int seed_stage(ag2_ctx *ctx, int pass, int maxc, const int32_t *d_reads, 
         a.read_off = sq.read_off;
         a.read_len = sq.read_len;
         a.reads = d_reads;
-        a.work = tier == 0 ? nullptr : (const int32_t *)ctx->seed_ovf1.p;
-        a.n_work_dev = tier == 0 ? nullptr : &ctl->ovf1;
+        a.work = tier == 0 ? nullptr : (const int32_t *)lists[(tier - 1) & 1]->p;
+        a.n_work_dev = tier == 0 ? nullptr : &ctl->sovf[tier - 1];
         a.n_work = (unsigned)n;
         a.pass = pass;
         a.maxc = maxc;
         a.cap = caps[tier];
-        a.next = tier == 0 ? &ctl->next1 : &ctl->next2;
+        a.next = &ctl->snext[tier];
         a.cands = (SeedCand *)ctx->seed_cands.p;
         a.ncand = (int32_t *)ctx->seed_ncand.p;
-        a.ovf = (int32_t *)(tier == 0 ? ctx->seed_ovf1.p : ctx->seed_ovf2.p);
-        a.ovf_count = tier == 0 ? &ctl->ovf1 : &ctl->ovf2;
+        a.ovf = (int32_t *)lists[tier & 1]->p;
+        a.ovf_count = &ctl->sovf[tier];
         a.heavy_pool = (uint32_t *)ctx->seed_pool.p;
         seed_cta_kernel<<<grid, kSeedCtaThreads, smem, st>>>(a);
         CK(cudaGetLastError());
@@ -2049,16 +2078,18 @@ static int seed_stage(ag2_ctx *ctx, int pass, int maxc, const int32_t *d_reads, 
     SeedCtl h;
     CK(cudaMemcpyAsync(&h, ctl, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    ctx->seed_overflow[0] = h.ovf1;
-    ctx->seed_overflow[1] = h.ovf2;
-    if (h.ovf2 > 0) {   // one thread per read, table in global memory
+    ctx->seed_overflow[0] = h.sovf[0];
+    ctx->seed_overflow[1] = h.sovf[n_tiers - 1];
+    const int32_t *left_list = (const int32_t *)lists[(n_tiers - 1) & 1]->p;
+    const unsigned n_left = h.sovf[n_tiers - 1];
+    if (n_left > 0) {   // one thread per read, table in global memory
         std::vector<std::pair<int64_t, int64_t>> chunks;
-        int rc = thread_path_scratch(ctx, ix, pass, d_reads, (const int32_t *)ctx->seed_ovf2.p, h.ovf2, chunks);
+        int rc = thread_path_scratch(ctx, ix, pass, d_reads, left_list, n_left, chunks);
         if (rc != AG2_OK) return rc;
         for (auto &c : chunks) {
             const int64_t cn = c.second - c.first;
             seed_map_sub_kernel<<<grid_for(cn, 128, ctx->sm_count), 128, 0, st>>>(
-                ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads, (const int32_t *)ctx->seed_ovf2.p, c.first, cn, pass, maxc,
+                ix, sq.reads2, sq.reads_irr, sq.read_off, sq.read_len, d_reads, left_list, c.first, cn, pass, maxc,
                 (const int64_t *)ctx->seed_prefix.p, (uint8_t *)ctx->seed_scratch.p, (SeedCand *)ctx->seed_cands.p, (int32_t *)ctx->seed_ncand.p);
         }
         CK(cudaGetLastError());

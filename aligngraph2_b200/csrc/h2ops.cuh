@@ -126,6 +126,7 @@ inline h2 h2_fma(h2 a, h2 b, h2 c) // exact only: every product and sum in play 
 }
 inline h2 h2_mul(h2 a, h2 b) { return h2_fma(a, b, 0u); }
 inline uint32_t h2_opaque(uint32_t x) { return x; }
+inline uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | c; }
 inline uint32_t vadd2(uint32_t a, uint32_t b) { return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16); }
 inline h2 h2_from_ints(int lo, int hi) { return h2emu::enc(lo) | (h2emu::enc(hi) << 16); }
 inline int h2_lo_int(h2 a) { return h2emu::dec(a); }
@@ -155,6 +156,14 @@ __device__ __forceinline__ uint32_t h2_opaque(uint32_t x)
 {
     asm volatile("" : "+r"(x));
     return x;
+}
+// (a & b) | c as ONE LOP3, whatever the compiler knows about b and c (two constants would otherwise be split into two
+// instructions with an immediate each)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
 }
 __device__ __forceinline__ uint32_t vadd2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 __device__ __forceinline__ h2 h2_from_ints(int lo, int hi) { return h2_bits(__halves2half2(__int2half_rn(lo), __int2half_rn(hi))); }

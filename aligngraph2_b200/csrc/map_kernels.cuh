@@ -14,7 +14,7 @@ constexpr int kOutCap = 3 * kMaxAlns; // output_results writes at most 3 records
 __device__ __forceinline__ int64_t item_read(const int32_t *reads, int64_t k) { return reads ? reads[k] : k; }
 
 // ---- seeding + candidate scoring: one CTA per read (seed_cta.cuh) ----
-__global__ void __launch_bounds__(kSeedCtaThreads) seed_cta_kernel(SeedCtaArgs a)
+__global__ void AG2_SEED_BOUNDS seed_cta_kernel(SeedCtaArgs a)
 {
     extern __shared__ __align__(16) uint8_t seed_smem[];
     seed_cta_body(a, seed_smem);

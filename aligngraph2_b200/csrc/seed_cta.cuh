@@ -34,8 +34,15 @@ namespace ag2 {
 
 #ifdef AG2_EMU
 constexpr int kSeedCtaThreads = 32;
+#elif defined(AG2_SEED_THREADS)
+constexpr int kSeedCtaThreads = AG2_SEED_THREADS;       // experiments/runs: occupancy sweeps
 #else
 constexpr int kSeedCtaThreads = 256;
+#endif
+#ifdef AG2_SEED_MIN_CTAS
+#define AG2_SEED_BOUNDS __launch_bounds__(kSeedCtaThreads, AG2_SEED_MIN_CTAS)
+#else
+#define AG2_SEED_BOUNDS __launch_bounds__(kSeedCtaThreads)   // a stated minimum of 1 CTA let ptxas take 118 registers: 2 CTAs per SM
 #endif
 constexpr int kSeedCtaWarps = kSeedCtaThreads / 32;
 constexpr int kSeedDigitBits = 9;                       // radix of the sort: 512 bins per warp -- two passes up to 262 144 blocks (250 Mb)

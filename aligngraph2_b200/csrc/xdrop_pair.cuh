@@ -37,7 +37,6 @@ constexpr int kPairThreads = 64;                   // threads per CTA (128 direc
 constexpr int kPairSlots = 96;                     // window width in columns (band + lead of CLR reads: 89 at most in 6500 sampled blocks)
 constexpr int kPairGroups = kPairSlots / 8;
 constexpr int kPairQuads = (kPairGroups + 3) / 4;  // a traceback row = kPairQuads pieces of 16 bytes (4 groups = 32 columns each)
-constexpr int kPairMainGroups = 8;                 // the walk fetches the first 8 groups of a row (64 columns); the rest on demand
 constexpr int kPairQuadStride = 2 * kPairThreads * 16; // the CTA's 128 directions side by side: a warp stores 512 contiguous bytes
 constexpr int kPairRowStride = kPairQuads * kPairQuadStride;
 constexpr size_t kPairTbCta = (size_t)(kMaxBlk + 2) * kPairRowStride; // traceback of one CTA
@@ -55,8 +54,9 @@ constexpr int kPairMinN = 32;                      // shortest target block this
 struct PairSmem {
     uint32_t v[kPairSlots / 4][kPairThreads][4];   // slot j of both directions: v[j >> 2][tid][j & 3]
     uint32_t tg[kPairGroups][kPairThreads];        // 8 target codes of group g (2 bits each), per half
-    uint32_t ph[kPairGroups][kPairThreads];        // forced-mismatch bits (even bit positions), per half
 };
+// 27 KB: eight CTAs (16 warps) per SM.  The forced-mismatch bits of the columns from N - 1 on are not stored: they are
+// needed in the last rows of a block only, and computed there (pair_dp).
 
 // Views into the CTA's scratch for one direction (hh = 0 / 1: low / high half of thread tid).  Traceback: piece q of row a
 // is the 16 bytes at tb + (a * kPairQuads + q) * kPairQuadStride -- the directions of a warp are adjacent, so the lock-step DP
@@ -104,6 +104,15 @@ __device__ __forceinline__ void pair_lds4(const uint32_t *p, uint32_t (&d)[4])
                  : "r"((unsigned)__cvta_generic_to_shared(p)));
 #endif
 }
+__device__ __forceinline__ void pair_sts4(uint32_t *p, const uint32_t (&d)[4])
+{
+#ifdef AG2_EMU
+    p[0] = d[0]; p[1] = d[1]; p[2] = d[2]; p[3] = d[3];
+#else
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3])
+                 : "memory");
+#endif
+}
 __device__ __forceinline__ uint32_t pair_lds1(const uint32_t *p)
 {
 #ifdef AG2_EMU
@@ -130,23 +139,24 @@ struct PairCarry {
     uint32_t one; // binary16 1.0 in both halves, held in a register
 };
 
-// One DP cell of both directions.  K = slot within the group.  IN = the group is interior for every running direction of
-// the warp (all 8 slots and the one after them are standard cells, the leading run is over): the boundary masks drop out.
+// One DP cell of both directions.  K = slot within the group.  END = some running direction of the warp has its band end in
+// the group (a slot of the group, or the one after it, is not a standard cell): the boundary masks are needed.  LEAD = some
+// running direction is still in its run of leading pruned cells.  Neither: the group is interior.
 // Instruction budget (the kernel is bound by the ALU pipe, where HSET2 / HMNMX2 / LOP3 issue, at one warp instruction per
 // two cycles; HADD2 / HFMA2 / IMAD issue on the FMA pipe): selects keyed on a compare are done as g * (a - b) + b with the
 // compare's 1.0 / 0.0 form wherever the operands stay exact, and the traceback nibble is summed, not assembled.
 // Nibble: bit 0 "gap in A beats the rest", bit 1 "gap in B beats the diagonal" (the walk gives bit 0 priority), bit 2 kExtA,
 // bit 3 kExtB; slot k of a group sits at bits 16 * (k / 4) + 4 * (3 - k % 4) of the group's word.
-template <int K, bool IN>
-__device__ __forceinline__ void pair_slot(uint32_t &v, PairCarry &c, const h2 nDg, const h2 Jg, const uint32_t mmw, uint32_t &acc)
+template <int K, bool END, bool LEAD>
+__device__ __forceinline__ void pair_slot(uint32_t &v, PairCarry &c, const h2 nDg, const uint32_t mmw, uint32_t &acc, h2 &npend)
 {
-    const h2 Jc = h2_add(Jg, H2C(K));
-    const h2 mt = ((mmw << (15 - 2 * K)) & kH2Sign) | c.one;   // +1 match, -1 mismatch
+    constexpr bool IN = !END && !LEAD;
+    const h2 mt = and_or(mmw << (15 - 2 * K), kH2Sign, c.one); // +1 match, -1 mismatch
     const h2 nd = h2_add(v, mt);                           // h(a-1, b) + match: the next slot's diagonal
     h2 e = h2_add(h2_abs(v), H2C(-1));                     // e(a-1, b)
     h2 dg = c.diag;                                        // h(a-1, b-1) + match
     uint32_t Ms = 0xffffffffu;
-    if (!IN) {
+    if (END) {
         Ms = c.Ms;                                         // this slot is a standard cell (column < nD)
         const uint32_t Me = h2_gt(nDg, H2C(K + 1));        // the next one is: this slot's vertical gap is valid
         c.Ms = Me;
@@ -156,24 +166,31 @@ __device__ __forceinline__ void pair_slot(uint32_t &v, PairCarry &c, const h2 nD
     const h2 m1 = h2_max(dg, e);
     const h2 sc = h2_max(m1, c.hgap);                      // (:95-107)
     uint32_t Ml = h2_ge(sc, c.thr);                        // not pruned (:109)
-    if (!IN) Ml &= Ms | c.Mlp;                             // extension cells need a live left neighbour
+    if (END) Ml &= Ms | c.Mlp;                             // extension cells need a live left neighbour
     const h2 gl = Ml & c.one;                              // 1.0 where live
-    const h2 gls = IN ? gl : (Ml & Ms & c.one);            // 1.0 where a live standard cell
+    const h2 gls = END ? (Ml & Ms & c.one) : gl;           // 1.0 where a live standard cell
     // traceback nibble (+1024 to read it off the mantissa)
     const h2 P1 = h2_ltf(dg, e), P2 = h2_ltf(m1, c.hgap);
     const h2 PA = h2_eqf(e, sc), PB = h2_eqf(c.hgap, sc);  // kExtA (:121-126), kExtB (:129-133): unpruned cells only
     const h2 fl = h2_mul(h2_fma(PB, H2C(2), PA), gls);
-    const h2 nib = h2_fma(fl, H2C(4), h2_fma(P1, H2C(2), h2_add(P2, H2C(1024))));
-    acc = acc * 16u + (nib & 0x000f000fu);
+    if ((K & 1) == 0) {                                    // even slot: its nibble waits, 16-fold, for the odd one's
+        npend = h2_fma(fl, H2C(64), h2_fma(P1, H2C(32), h2_mul(P2, H2C(16))));
+    } else {
+        const h2 nib = h2_fma(fl, H2C(4), h2_fma(P1, H2C(2), h2_add(P2, H2C(1024))));
+        acc = acc * 256u + (h2_add(nib, npend) & 0x00ff00ffu);
+    }
     // running best (:114-118) and band bookkeeping
     const h2 gnew = h2_gtf(sc, c.best);
     c.best = h2_max(c.best, sc);
     c.thr = h2_add(c.best, H2C(-kXdrop));
-    c.be = h2_fma(gnew, h2_sub(Jc, c.be), c.be);
-    c.lastj = h2_sel(Ml, Jc, c.lastj);
-    c.hgap = h2_fma(gl, h2_sub(h2_add(sc, H2C(-1)), c.hgap), c.hgap); // not decayed across pruned cells
+    c.be = h2_fma(gnew, h2_sub(H2C(K), c.be), c.be);       // be, lastj: relative to the group's first column
+    c.lastj = h2_sel(Ml, H2C(K), c.lastj);
+    // horizontal gap: not decayed across pruned cells.  A select (ALU pipe) in interior groups, g * (a - b) + b (FMA pipe)
+    // in the others, whose masks already fill the ALU pipe
+    if (IN) c.hgap = h2_sel(Ml, h2_add(sc, H2C(-1)), c.hgap);
+    else c.hgap = h2_fma(gl, h2_sub(h2_add(sc, H2C(-1)), c.hgap), c.hgap);
     uint32_t dead = v | kH2Sign;                           // pruned inside the band: h = MIN, e kept
-    if (!IN) {
+    if (LEAD) {
         c.Mlead &= ~Ml;                                    // still in the run of leading pruned cells (:110)
         c.cnt = vadd2(c.cnt, c.Mlead);
         dead &= ~c.Mlead;                                  // left the band
@@ -183,19 +200,32 @@ __device__ __forceinline__ void pair_slot(uint32_t &v, PairCarry &c, const h2 nD
     c.Mlp = Ml;
 }
 
-template <bool IN>
-__device__ __forceinline__ void pair_group(uint32_t (&va)[4], uint32_t (&vb)[4], PairCarry &c, const h2 nDg, const h2 Jg, const uint32_t mmw,
-                                           uint32_t &acc0, uint32_t &acc1)
+// One group of 8 slots: va = slots 0-3, vb = slots 4-7, computed in place.  Where the stores and loads of the window stand
+// matters: a store's source registers cannot be overwritten until the store has left the memory queue, and a register move
+// into them right behind it stalls the warp for that long (with the next group's operands prefetched into a second set of
+// registers and moved over at the end of the loop that was 5 % of the kernel, twice).  So there is no second set: each half
+// is stored as soon as it is computed, and the same registers are then loaded with the NEXT group's half (row `vnext`) --
+// memory-queue operations are processed in order -- half a group before anything computes on them again.
+template <bool END, bool LEAD>
+__device__ __forceinline__ void pair_group(uint32_t (&va)[4], uint32_t (&vb)[4], uint32_t *vrow, const uint32_t *vnext, PairCarry &c,
+                                           const h2 nDg, const uint32_t mmw, uint32_t &acc0, uint32_t &acc1)
 {
-    pair_slot<0, IN>(va[0], c, nDg, Jg, mmw, acc0);
-    pair_slot<1, IN>(va[1], c, nDg, Jg, mmw, acc0);
-    pair_slot<2, IN>(va[2], c, nDg, Jg, mmw, acc0);
-    pair_slot<3, IN>(va[3], c, nDg, Jg, mmw, acc0);
-    pair_slot<4, IN>(vb[0], c, nDg, Jg, mmw, acc1);
-    pair_slot<5, IN>(vb[1], c, nDg, Jg, mmw, acc1);
-    pair_slot<6, IN>(vb[2], c, nDg, Jg, mmw, acc1);
-    pair_slot<7, IN>(vb[3], c, nDg, Jg, mmw, acc1);
-    if (IN) c.Ms = 0xffffffffu;
+    h2 npend = 0;
+    pair_slot<0, END, LEAD>(va[0], c, nDg, mmw, acc0, npend);
+    pair_slot<1, END, LEAD>(va[1], c, nDg, mmw, acc0, npend);
+    pair_slot<2, END, LEAD>(va[2], c, nDg, mmw, acc0, npend);
+    pair_slot<3, END, LEAD>(va[3], c, nDg, mmw, acc0, npend);
+    pair_sts4(vrow, va);
+    pair_lds4(vnext, va);
+    pair_slot<4, END, LEAD>(vb[0], c, nDg, mmw, acc1, npend);
+    pair_slot<5, END, LEAD>(vb[1], c, nDg, mmw, acc1, npend);
+    pair_slot<6, END, LEAD>(vb[2], c, nDg, mmw, acc1, npend);
+    pair_slot<7, END, LEAD>(vb[3], c, nDg, mmw, acc1, npend);
+    pair_sts4(vrow + 4 * kPairThreads, vb);
+    pair_lds4(vnext + 4 * kPairThreads, vb);
+    if (!END) c.Ms = 0xffffffffu;
+    c.be = h2_add(c.be, H2C(-8));                          // relative to the next group
+    c.lastj = h2_add(c.lastj, H2C(-8));
 }
 
 #ifdef AG2_EMU_STATS
@@ -229,7 +259,6 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
         }
         for (int g = 0; g < kPairGroups; ++g) {
             sm.tg[g][tid] = pair_tg16(s0.tcodes, 8 * g) | (pair_tg16(s1.tcodes, 8 * g) << 16);
-            sm.ph[g][tid] = pair_ph16(8 * g, N0 - 1) | (pair_ph16(8 * g, N1 - 1) << 16);
         }
     }
     const int rows_max = __reduce_max_sync(kFull, max(M0, M1));
@@ -269,16 +298,10 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
                     s1.log[nsh1++] = (uint16_t)a;
                 }
                 for (int g = 0; g < kPairGroups; ++g) {
-                    uint32_t tn, pn;
-                    if (g + 1 < kPairGroups) {
-                        tn = sm.tg[g + 1][tid];
-                        pn = sm.ph[g + 1][tid];
-                    } else {
-                        tn = pair_tg16(s0.tcodes, base0 + 8 * g) | (pair_tg16(s1.tcodes, base1 + 8 * g) << 16);
-                        pn = pair_ph16(base0 + 8 * g, N0 - 1) | (pair_ph16(base1 + 8 * g, N1 - 1) << 16);
-                    }
+                    uint32_t tn;
+                    if (g + 1 < kPairGroups) tn = sm.tg[g + 1][tid];
+                    else tn = pair_tg16(s0.tcodes, base0 + 8 * g) | (pair_tg16(s1.tcodes, base1 + 8 * g) << 16);
                     sm.tg[g][tid] = h2_sel(Msh, tn, sm.tg[g][tid]);
-                    sm.ph[g][tid] = h2_sel(Msh, pn, sm.ph[g][tid]);
                 }
                 const h2 m8 = Msh & H2C(-8);
                 frelh = h2_add(frelh, m8);
@@ -334,33 +357,40 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
         int g = 0;
         bool more = g_std > 0;
         // operands of the next group are fetched from shared memory while the current one computes
-        uint32_t va[4], vb[4], tgw, phw;
+        uint32_t va[4], vb[4], tgw;
+        // forced mismatches from column N - 1 on: only when that column is inside the window of some direction of the warp
+        const bool lim_in = __any_sync(kFull, (h2_lt(nrelm1, H2C(kPairSlots)) & run) != 0);
+        int lim0 = 0, lim1 = 0;
+        if (lim_in) {
+            lim0 = N0 - 1 - base0;
+            lim1 = N1 - 1 - base1;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             va[i] = sm.v[0][tid][i];
             vb[i] = sm.v[1][tid][i];
         }
         tgw = sm.tg[0][tid];
-        phw = sm.ph[0][tid];
         while (more) {
             const int gn = min(g + 1, kPairGroups - 1);
-            uint32_t na[4], nb[4];
-            pair_lds4(&sm.v[2 * gn][tid][0], na);
-            pair_lds4(&sm.v[2 * gn + 1][tid][0], nb);
-            const uint32_t ntg = pair_lds1(&sm.tg[gn][tid]), nph = pair_lds1(&sm.ph[gn][tid]);
+            const uint32_t ntg = pair_lds1(&sm.tg[gn][tid]);
             const uint32_t x = tgw ^ acrep;
-            const uint32_t mmw = x | (x >> 1) | phw; // bit 2k of each half: slot k mismatches
+            uint32_t mmw = x | (x >> 1); // bit 2k of each half: slot k mismatches
+            if (lim_in) mmw |= pair_ph16(8 * g, lim0) | (pair_ph16(8 * g, lim1) << 16);
             uint32_t acc0 = 0, acc1 = 0;
-            // interior group: no running direction of the warp has a band edge or its leading run in these 8 slots
-            const uint32_t inner = (h2_ge(nDg, H2C(9)) & ~c.Mlead) | ~run;
-            const bool all_in = __all_sync(kFull, inner == 0xffffffffu);
-            PES(if (tid == 0) { g_pes.groups++; g_pes.groups_in += all_in; if (g < g_std) g_pes.gstd_groups++; else g_pes.tail_groups++; })
-            if (all_in) pair_group<true>(va, vb, c, nDg, Jg, mmw, acc0, acc1);
-            else pair_group<false>(va, vb, c, nDg, Jg, mmw, acc0, acc1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                sm.v[2 * g][tid][i] = va[i];
-                sm.v[2 * g + 1][tid][i] = vb[i];
+            // which masks the group needs: has a running direction of the warp its band end in these 8 slots or the one after
+            // them; is one still in its leading run.  (Two votes and two branches: a four-way switch on one reduced value
+            // became an indexed jump through a table, 6 % of the kernel waiting for the table load.)
+            const bool noend = __all_sync(kFull, (h2_ge(nDg, H2C(9)) | ~run) == 0xffffffffu);
+            const bool nolead = __all_sync(kFull, (~c.Mlead | ~run) == 0xffffffffu);
+            PES(if (tid == 0) { g_pes.groups++; g_pes.groups_in += noend && nolead; if (g < g_std) g_pes.gstd_groups++; else g_pes.tail_groups++; })
+            uint32_t *vrow = &sm.v[2 * g][tid][0];
+            const uint32_t *vnext = &sm.v[2 * gn][tid][0];
+            if (nolead) {
+                if (noend) pair_group<false, false>(va, vb, vrow, vnext, c, nDg, mmw, acc0, acc1);
+                else pair_group<true, false>(va, vb, vrow, vnext, c, nDg, mmw, acc0, acc1);
+            } else {
+                pair_group<true, true>(va, vb, vrow, vnext, c, nDg, mmw, acc0, acc1);
             }
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -376,13 +406,7 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             }
             Jg = h2_add(Jg, H2C(8));
             nDg = h2_add(nDg, H2C(-8));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                va[i] = na[i];
-                vb[i] = nb[i];
-            }
             tgw = ntg;
-            phw = nph;
             if (g < g_std) continue;
             more = __any_sync(kFull, ((c.Ms | c.Mlp) & run) != 0);
             if (g >= kPairGroups) break;
@@ -399,6 +423,8 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             pair_store16(row1 + (size_t)(g >> 2) * kPairQuadStride, t1);
         }
         if (more) bail |= (c.Ms | c.Mlp) & run; // the window is too narrow for this direction
+        c.be = h2_add(c.be, Jg);                // back to window columns
+        c.lastj = h2_add(c.lastj, Jg);
         PES({ const int l0 = h2_lo_int(c.lastj), l1 = h2_hi_int(c.lastj);
               if (run & 0xffffu) g_pes.dir_groups_need += (max(l0, 0) + 2 + 7) >> 3;
               if (run >> 16) g_pes.dir_groups_need += (max(l1, 0) + 2 + 7) >> 3; })
@@ -432,6 +458,20 @@ __device__ __forceinline__ void pair_copy16_async(uint32_t *smem_dst, const uint
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 #endif
 }
+__device__ __forceinline__ void pair_copy_commit()
+{
+#ifndef AG2_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+// waits until all but the thread's N most recent groups of copies have landed
+template <int N>
+__device__ __forceinline__ void pair_copy_wait_but()
+{
+#ifndef AG2_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
 __device__ __forceinline__ void pair_copy_wait()
 {
 #ifndef AG2_EMU
@@ -439,15 +479,42 @@ __device__ __forceinline__ void pair_copy_wait()
 #endif
 }
 
-constexpr int kPairWalkRows = (kPairSlots / 4) / (kPairMainGroups / 4); // traceback rows per batch: what the band window holds
-static_assert(kPairMainGroups % 4 == 0 && kPairGroups <= 4 * kPairQuads && kPairWalkRows >= 4, "walk batches");
+constexpr int kPairWalkRows = (kPairSlots / 4) / kPairQuads;             // traceback rows in flight: what the band window holds
+constexpr int kPairMoveStep = kPairShiftMask + 1;                        // the window base can move at multiples of this row
+static_assert(kPairGroups == 4 * kPairQuads && kPairWalkRows >= 4 && kPairWalkRows <= 16, "walk ring");
+static_assert((kPairMoveStep & (kPairMoveStep - 1)) == 0, "move rows are tested with a mask");
+static_assert(kPairGroups >= 12 && (kMaxBlk + 2) / kPairMoveStep < 8 * 32, "sm.tg holds the walk's code words and move bits");
+static_assert(kPairLogBytes <= kPairWalkRows * kPairQuads * 16 + 64, "the move log is staged in the row ring");
+
+// 4-byte global -> shared copy (LDGSTS)
+__device__ __forceinline__ void pair_copy4_async(uint32_t *smem_dst, const uint32_t *gmem_src)
+{
+#ifdef AG2_EMU
+    *smem_dst = *gmem_src;
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#endif
+}
 
 // Traceback (:170-210) over the pair layout: row a holds the nibbles of columns base(a) .. base(a) + kPairSlots - 1, base(a) =
-// 8 x (number of logged window moves at rows <= a).  Otherwise lane_walk.  The rows live in HBM (the scratch of all resident
-// directions is far larger than L2) and a step depends on the previous one, so the walk fetches kPairWalkRows whole rows at a
-// time with asynchronous copies into the thread's band window, which is idle during the walk.  Called by the whole warp
-// (`active` = this lane has a direction to walk): the fetches are issued by all lanes together, then every lane steps through
-// its own batch -- a lane-private fetch loop would serialise the warp.
+// 8 x (number of logged window moves at rows <= a).  Otherwise lane_walk.
+//
+// Everything the walk reads lives in HBM (the scratch of all resident directions is far larger than L2), a step depends on
+// the previous one, and the 32 lanes of the warp are at different places of their blocks.  Two things follow.
+// (1) A load into a register anywhere in the step -- however far ahead of its use for the lane that issues it -- stalls the
+// WARP at the next step, when another lane touches that register (the scoreboard is per warp): the first form of this walk,
+// which read the code words and the move log one word ahead, ran at one memory latency per step.  So the step loads nothing
+// into registers from global memory: all of it arrives in shared memory through asynchronous copies, whose completion is
+// counted per thread.
+//   * rows: the thread's band window, idle during the walk, is a ring of kPairWalkRows whole rows; when the walk leaves a
+//     row, the row kPairWalkRows below it is requested into the slot that has become free;
+//   * code words of the block (16 positions each): two-word rings in sm.tg[0..3]; entering a word requests the one below;
+//   * window moves: a bit per kPairMoveStep rows in sm.tg[4..11], built once from the log.
+// Every step commits one group of copies (possibly empty) and starts by waiting for all but the kPairWalkRows - 1 youngest:
+// the row the walk stands on was requested at least that many steps ago, a code word at least 16.
+// (2) A branch on the lane's own state (kind of step, word boundary, trimming) makes the warp run every side of it at nearly
+// every step.  The step is straight-line code: selects, and side effects under the lane's `walking`.
+// Called by the whole warp (`active` = this lane has a direction to walk).
 __device__ int pair_walk(PairSmem &sm, int tid, uint8_t *cta_scratch, int hh, bool active, int nshift, int ae, int be, char *wq, char *wt,
                          int cap, int &qcnt, int &tcnt, int &acnt, bool &trim_ok, int &first_op, int &op_after_trim)
 {
@@ -457,92 +524,104 @@ __device__ int pair_walk(PairSmem &sm, int tid, uint8_t *cta_scratch, int hh, bo
     bool scanning = true;
     first_op = -1;
     op_after_trim = -1;
-    // The block's codes and the window-move log are read one word AHEAD of the walk (it only moves towards the origin):
-    // the lanes of a warp cross word boundaries at different steps, and a load consumed right away would stall all of
-    // them for a memory latency at almost every step.
-    int qi = min(max(a - 1, 0) >> 4, kSeqWords - 1), ti = min(max(b - 1, 0) >> 4, kSeqWords - 1);
-    uint32_t qwv = 0, twv = 0, qwn = 0, twn = 0;
-    int ns = nshift;
-    int ns_row = 0, ns_next = 0; // rows of the last two window moves at or below the walk
-    if (active) {
-        qwv = ps.qcodes[qi];
-        twv = ps.tcodes[ti];
-        qwn = qi > 0 ? ps.qcodes[qi - 1] : 0u;
-        twn = ti > 0 ? ps.tcodes[ti - 1] : 0u;
-        ns_row = ns > 0 ? (int)ps.log[ns - 1] : 0;
-        ns_next = ns > 1 ? (int)ps.log[ns - 2] : 0;
-    }
     bool walking = active && (a > 0 || b > 0) && n < cap;
-    for (;;) {
-        if (!__any_sync(kFull, walking)) break;
-        int a_lo = a;
-        if (walking && a > 0) { // fetch rows a_lo .. a
-            a_lo = max(1, a - (kPairWalkRows - 1));
-            const uint8_t *src = ps.tb + (size_t)a_lo * kPairRowStride;
-            const int nchunks = (a - a_lo + 1) * (kPairMainGroups / 4);
-            for (int c = 0; c < nchunks; c += kPairMainGroups / 4) {
-#pragma unroll
-                for (int q = 0; q < kPairMainGroups / 4; ++q) pair_copy16_async(&sm.v[c + q][tid][0], src + (size_t)q * kPairQuadStride);
-                src += kPairRowStride;
+    // ---- the window moves as a bit set; ns = moves at rows <= a
+    int ns = 0;
+    {
+        const int nchunk = walking ? (nshift + 7) >> 3 : 0;
+        for (int c = 0; c < nchunk; ++c) pair_copy16_async(&sm.v[c][tid][0], reinterpret_cast<const uint8_t *>(ps.log) + 16 * c);
+        for (int w = 4; w < 12; ++w) sm.tg[w][tid] = 0;
+        pair_copy_wait();
+        if (walking) {
+            for (int i = 0; i < nshift; ++i) {
+                const uint32_t pr = sm.v[i >> 3][tid][(i >> 1) & 3];
+                const int row = (int)((pr >> (16 * (i & 1))) & 0xffffu);
+                const int bit = row / kPairMoveStep;
+                sm.tg[4 + (bit >> 5)][tid] |= 1u << (bit & 31);
+                ns += row <= a;
             }
         }
-        pair_copy_wait();
-        while (walking && (a == 0 || a >= a_lo)) {
-            int cell = kOpGapA; // row 0 is all SCRIPT_GAP_IN_A (:61)
-            if (a > 0) {
-                while (ns_row > a) {
-                    --ns;
-                    ns_row = ns_next;
-                    ns_next = ns > 1 ? (int)ps.log[ns - 2] : 0;
-                }
-                const int slot = b - 8 * ns, w = slot >> 3;
-                uint32_t word;
-                if (w < kPairMainGroups) {
-                    const int f = (a - a_lo) * kPairMainGroups + w;
-                    word = sm.v[f >> 2][tid][f & 3];
-                } else { // far right of the window: not part of the fetched rows
-                    word = *reinterpret_cast<const uint32_t *>(ps.tb + (size_t)a * kPairRowStride + (size_t)(w >> 2) * kPairQuadStride + 4 * (w & 3));
-                }
-                cell = (int)((word >> (16 * ((slot >> 2) & 1) + 4 * (3 - (slot & 3)))) & 15u);
+    }
+    // ---- code words: position p of the block is in word p >> 4; ring slot = word & 1
+    int qi = min(max(a - 1, 0) >> 4, kSeqWords - 1), ti = min(max(b - 1, 0) >> 4, kSeqWords - 1);
+    if (walking) {
+        pair_copy4_async(&sm.tg[qi & 1][tid], ps.qcodes + qi);
+        if (qi > 0) pair_copy4_async(&sm.tg[(qi - 1) & 1][tid], ps.qcodes + qi - 1);
+        pair_copy4_async(&sm.tg[2 + (ti & 1)][tid], ps.tcodes + ti);
+        if (ti > 0) pair_copy4_async(&sm.tg[2 + ((ti - 1) & 1)][tid], ps.tcodes + ti - 1);
+    }
+    // ---- the row ring: row r in slot r % kPairWalkRows
+    int slot_a = a % kPairWalkRows;                 // slot of row a
+    int fetch = a;                                  // next row to request
+    const uint8_t *fsrc = ps.tb + (size_t)fetch * kPairRowStride;
+    {
+        int fs = slot_a;
+        for (int i = 0; i < kPairWalkRows; ++i) {
+            if (walking && fetch >= 1) {
+#pragma unroll
+                for (int qd = 0; qd < kPairQuads; ++qd) pair_copy16_async(&sm.v[fs * kPairQuads + qd][tid][0], fsrc + (size_t)qd * kPairQuadStride);
             }
-            int nxt = (cell & 1) ? kOpGapA : (cell & 2); // kOpGapB == 2, kOpSub == 0
-            if (cur == kOpGapA && (cell & kExtA)) nxt = kOpGapA;
-            if (cur == kOpGapB && (cell & kExtB)) nxt = kOpGapB;
-            cur = nxt;
-            if (cur != kOpGapA) --a;
-            if (cur != kOpGapB) --b;
-            int qc = 4, tc = 4;
-            if (cur != kOpGapA) {
-                if ((a >> 4) != qi) { // a moved into the word below: take the prefetched one, fetch the next
-                    qi = a >> 4;
-                    qwv = qwn;
-                    qwn = qi > 0 ? ps.qcodes[qi - 1] : 0u;
-                }
-                qc = (int)((qwv >> (2 * (a & 15))) & 3u);
-            }
-            if (cur != kOpGapB) {
-                if ((b >> 4) != ti) {
-                    ti = b >> 4;
-                    twv = twn;
-                    twn = ti > 0 ? ps.tcodes[ti - 1] : 0u;
-                }
-                tc = (int)((twv >> (2 * (b & 15))) & 3u);
-            }
-            if (n == 0) first_op = cur;
-            if (!scanning && op_after_trim < 0) op_after_trim = cur;
-            if (scanning) { // trim_mismatch_end scans from the END of the block's alignment = walk start
-                ++ac;
-                if (cur != kOpGapA) ++q;
-                if (cur != kOpGapB) ++t;
-                m = (qc == tc) ? m + 1 : 0;
-                if (m == kTailMatch) scanning = false;
-            }
+            pair_copy_commit();
+            --fetch;
+            fsrc -= kPairRowStride;
+            fs = fs ? fs - 1 : kPairWalkRows - 1;
+        }
+    }
+    while (__any_sync(kFull, walking)) {
+        pair_copy_wait_but<kPairWalkRows - 1>();
+        // the cell: row a (ring slot slot_a), window slot b - 8 ns
+        const int slot = b - 8 * ns;
+        const int f = slot_a * kPairGroups + min(max(slot >> 3, 0), kPairGroups - 1);
+        const uint32_t word = sm.v[f >> 2][tid][f & 3];
+        int cell = (int)((word >> (16 * ((slot >> 2) & 1) + 4 * (3 - (slot & 3)))) & 15u);
+        cell = a > 0 ? cell : kOpGapA;              // row 0 is all SCRIPT_GAP_IN_A (:61)
+        int nxt = (cell & 1) ? kOpGapA : (cell & 2); // kOpGapB == 2, kOpSub == 0
+        nxt = (cur == kOpGapA && (cell & kExtA)) ? kOpGapA : nxt;
+        nxt = (cur == kOpGapB && (cell & kExtB)) ? kOpGapB : nxt;
+        cur = walking ? nxt : cur;
+        const bool da = walking && cur != kOpGapA, db = walking && cur != kOpGapB;
+        // a window move logged at the row being left no longer counts
+        const int mbit = a / kPairMoveStep;
+        const uint32_t mword = sm.tg[4 + ((mbit >> 5) & 7)][tid];
+        ns -= (da && (a & (kPairMoveStep - 1)) == 0) ? (int)((mword >> (mbit & 31)) & 1u) : 0;
+        // the slot of the row being left takes the row kPairWalkRows below it
+        if (da && fetch >= 1) {
+#pragma unroll
+            for (int qd = 0; qd < kPairQuads; ++qd) pair_copy16_async(&sm.v[slot_a * kPairQuads + qd][tid][0], fsrc + (size_t)qd * kPairQuadStride);
+        }
+        a -= da;
+        fetch -= da;
+        fsrc -= da ? kPairRowStride : 0;
+        slot_a = da ? (slot_a ? slot_a - 1 : kPairWalkRows - 1) : slot_a;
+        b -= db;
+        // codes of the step; a position in the word below: that word is in the ring, the one below it is requested
+        const int qn = da ? a >> 4 : qi, tn = db ? b >> 4 : ti;
+        if (qn != qi && qn > 0) pair_copy4_async(&sm.tg[(qn - 1) & 1][tid], ps.qcodes + qn - 1);
+        if (tn != ti && tn > 0) pair_copy4_async(&sm.tg[2 + ((tn - 1) & 1)][tid], ps.tcodes + tn - 1);
+        qi = qn;
+        ti = tn;
+        pair_copy_commit();
+        const uint32_t qwv = sm.tg[qi & 1][tid], twv = sm.tg[2 + (ti & 1)][tid];
+        const int qc = da ? (int)((qwv >> (2 * (a & 15))) & 3u) : 4;
+        const int tc = db ? (int)((twv >> (2 * (b & 15))) & 3u) : 4;
+        first_op = (walking && n == 0) ? cur : first_op;
+        op_after_trim = (walking && !scanning && op_after_trim < 0) ? cur : op_after_trim;
+        {   // trim_mismatch_end scans from the END of the block's alignment = walk start
+            const bool sc = walking && scanning;
+            ac += sc;
+            q += sc && da;
+            t += sc && db;
+            m = sc ? ((qc == tc) ? m + 1 : 0) : m;
+            scanning = scanning && !(sc && m == kTailMatch);
+        }
+        if (walking) {
             wq[n] = code_char(qc);
             wt[n] = code_char(tc);
-            ++n;
-            walking = (a > 0 || b > 0) && n < cap;
         }
+        n += walking;
+        walking = walking && (a > 0 || b > 0) && n < cap;
     }
+    pair_copy_wait(); // nothing may land in the window once the next block's DP owns it
     qcnt = q;
     tcnt = t;
     acnt = ac;
@@ -570,15 +649,34 @@ __device__ void pair_prepare(const LaneArgs &g, const LaneChain &s, const PairSc
     }
     const int qw = (blk.qblk + 15) >> 4, tw = (blk.tblk + 16) >> 4;
     const int qdir = s.c.strand == 0 ? s.inc : -s.inc;
-    for (int w = 0; w < qw; ++w) {
-        const int p = s.q0 + s.inc * (s.qidx + 16 * w);
-        const int64_t fp = s.c.strand == 0 ? p : (int64_t)s.rlen - 1 - p;
-        uint32_t v = fetch16(g.seqs.reads2, s.roff, s.rlen, fp, qdir);
-        if (s.c.strand != 0) v ^= ~spread_bits16(fetch16_bits(g.seqs.reads_irr, s.roff, fp, qdir));
-        ps.qcodes[w] = v;
+    // four words at a time: their loads are in flight together, and leave as one 16-byte store (the arrays are padded to 48 words)
+    static_assert(kPairSeqBytes >= 4 * ((kSeqWords + 3) / 4 * 4), "code arrays hold whole groups of four words");
+    for (int w0 = 0; w0 < qw; w0 += 4) {
+        uint32_t v4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int w = w0 + i;
+            uint32_t v = 0;
+            if (w < qw) {
+                const int p = s.q0 + s.inc * (s.qidx + 16 * w);
+                const int64_t fp = s.c.strand == 0 ? p : (int64_t)s.rlen - 1 - p;
+                v = fetch16(g.seqs.reads2, s.roff, s.rlen, fp, qdir);
+                if (s.c.strand != 0) v ^= ~spread_bits16(fetch16_bits(g.seqs.reads_irr, s.roff, fp, qdir));
+            }
+            v4[i] = v;
+        }
+        pair_store16(reinterpret_cast<uint8_t *>(ps.qcodes + w0), v4);
     }
-    for (int w = 0; w < tw && w < kSeqWords; ++w)
-        ps.tcodes[w] = fetch16(g.seqs.ref2, 0, g.seqs.ref_len, s.t0 + (int64_t)s.inc * (s.tidx + 16 * w), s.inc);
+    const int twc = min(tw, kSeqWords);
+    for (int w0 = 0; w0 < twc; w0 += 4) {
+        uint32_t v4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int w = w0 + i;
+            v4[i] = w < twc ? fetch16(g.seqs.ref2, 0, g.seqs.ref_len, s.t0 + (int64_t)s.inc * (s.tidx + 16 * w), s.inc) : 0u;
+        }
+        pair_store16(reinterpret_cast<uint8_t *>(ps.tcodes + w0), v4);
+    }
 }
 
 __device__ __forceinline__ unsigned pair_vol_u32(const unsigned int *p) { return *reinterpret_cast<const volatile unsigned int *>(p); }

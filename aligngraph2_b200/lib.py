@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(PKG, "libag2_b200.so")
+SO = os.environ.get("AG2_B200_LIB") or os.path.join(PKG, "libag2_b200.so")   # the override is for kernel-variant experiments
 
 AG2_OK = 0
 ERRORS = {-1: "AG2_ENODEV", -2: "AG2_ECUDA", -3: "AG2_EINVAL", -4: "AG2_ENOMEM", -5: "AG2_ESTATE", -6: "AG2_ECAP"}

@@ -174,6 +174,13 @@ inline int __reduce_add_sync(unsigned, int v)
     for (int l = 0; l < 32; ++l) r += (int)(int64_t)buf[l];
     return r;
 }
+inline unsigned __reduce_and_sync(unsigned, unsigned v)
+{
+    const uint64_t *buf = warp_emu::exchange(v);
+    unsigned r = 0xffffffffu;
+    for (int l = 0; l < 32; ++l) r &= (unsigned)buf[l];
+    return r;
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { warp_emu::exchange(0); }
 inline void __syncthreads() { warp_emu::exchange(0); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
