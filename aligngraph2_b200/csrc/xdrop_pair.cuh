@@ -275,6 +275,10 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
     c.one = h2_opaque(H2C(1));
     unsigned cells0 = 0, cells1 = 0, rows2 = 0;
     uint32_t aw0 = 0, aw1 = 0, an0 = s0.qcodes[0], an1 = s1.qcodes[0], bail = 0;
+    // target codes just right of the window, held a word ahead: tl = word (base + kPairSlots) >> 4.  A window move takes the
+    // new last group from it (a load consumed on the spot stalled the warp for a memory latency at every fourth check)
+    static_assert((kPairSlots >> 4) < kSeqWords, "look-ahead word");
+    uint32_t tl0 = s0.tcodes[kPairSlots >> 4], tl1 = s1.tcodes[kPairSlots >> 4];
 
     for (int a = 1; a <= rows_max; ++a) {
         if ((a & kPairShiftMask) == 0) {
@@ -300,8 +304,17 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
                 for (int g = 0; g < kPairGroups; ++g) {
                     uint32_t tn;
                     if (g + 1 < kPairGroups) tn = sm.tg[g + 1][tid];
-                    else tn = pair_tg16(s0.tcodes, base0 + 8 * g) | (pair_tg16(s1.tcodes, base1 + 8 * g) << 16);
+                    else   // positions base + 8 g ..: the half of the look-ahead word they are in (only a moved direction's half is kept)
+                        tn = ((tl0 >> (16 * (((base0 + 8 * g) >> 3) & 1))) & 0xffffu) | ((tl1 >> (16 * (((base1 + 8 * g) >> 3) & 1))) << 16);
                     sm.tg[g][tid] = h2_sel(Msh, tn, sm.tg[g][tid]);
+                }
+                if ((Msh & 0xffffu) && ((base0 + kPairSlots) & 15) == 0) {
+                    const int w = (base0 + kPairSlots) >> 4;
+                    tl0 = w < kSeqWords ? s0.tcodes[w] : 0u;
+                }
+                if ((Msh >> 16) && ((base1 + kPairSlots) & 15) == 0) {
+                    const int w = (base1 + kPairSlots) >> 4;
+                    tl1 = w < kSeqWords ? s1.tcodes[w] : 0u;
                 }
                 const h2 m8 = Msh & H2C(-8);
                 frelh = h2_add(frelh, m8);
