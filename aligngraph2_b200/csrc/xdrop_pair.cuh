@@ -647,6 +647,68 @@ struct PairBlk {
     bool last_block;
 };
 
+// fetch16 / fetch16_bits (xdrop_lane.cuh) in two halves, without a branch: `issue` computes the address and starts the loads,
+// `finish` shifts, reverses and clips.  Staging a block issues four words' loads before it finishes the first (with the
+// branchy form every load was consumed on the spot: one memory latency per word, 7 % of the kernel's warp time).
+struct PairFetch {
+    uint32_t lo, hi;
+    int sh, drop;      // drop: codes / bits to drop at the front (backward), or to shift in (bits, forward, p0 < 0)
+    bool rev, valid;
+};
+__device__ __forceinline__ uint32_t pair_ld_ro(const uint32_t *p)
+{
+#ifdef AG2_EMU
+    return *p;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ void pair_fetch16_issue(PairFetch &f, const uint32_t *seq, int64_t off, int64_t len, int64_t p0, int dir, bool want)
+{
+    const bool fwd = dir > 0;
+    const int64_t s0 = fwd ? p0 : p0 - 15;
+    f.rev = !fwd;
+    f.drop = (!fwd && s0 < 0) ? (int)(-s0) : 0;
+    f.valid = want && (fwd ? (p0 < len && p0 >= 0) : (p0 >= 0));
+    const int64_t pos = f.valid ? off + (s0 < 0 ? 0 : s0) : off;
+    f.sh = 2 * (int)(pos & 15);
+    const uint32_t *p = seq + (pos >> 4);
+    f.lo = f.valid ? pair_ld_ro(p) : 0u;
+    f.hi = (f.valid && f.sh) ? pair_ld_ro(p + 1) : 0u;
+}
+__device__ __forceinline__ uint32_t pair_fetch16_finish(const PairFetch &f)
+{
+    const uint32_t w = f.sh ? (f.lo >> f.sh) | (f.hi << (32 - f.sh)) : f.lo;
+    const uint32_t r = rev16(w) >> (2 * f.drop);
+    return f.valid ? (f.rev ? r : w) : 0u;
+}
+__device__ __forceinline__ void pair_fetch16_bits_issue(PairFetch &f, const uint32_t *bits, int64_t off, int64_t p0, int dir, bool want)
+{
+    const bool fwd = dir > 0;
+    const int64_t s0 = fwd ? p0 : p0 - 15;
+    f.rev = !fwd;
+    f.drop = s0 < 0 ? (int)(-s0) : 0;
+    f.valid = want && (fwd ? p0 > -16 : p0 >= 0);
+    const int64_t pos = f.valid ? off + (s0 < 0 ? 0 : s0) : off;
+    f.sh = (int)(pos & 31);
+    const uint32_t *p = bits + (pos >> 5);
+    f.lo = f.valid ? pair_ld_ro(p) : 0u;
+    f.hi = (f.valid && f.sh > 16) ? pair_ld_ro(p + 1) : 0u;
+}
+__device__ __forceinline__ uint32_t pair_fetch16_bits_finish(const PairFetch &f)
+{
+    uint32_t x = f.lo >> f.sh;
+    if (f.sh > 16) x |= f.hi << (32 - f.sh);
+    x &= 0xffffu;                                          // bit j = position s + j
+    uint32_t r = x;                                        // reverse the 16 bits
+    r = ((r >> 1) & 0x5555u) | ((r & 0x5555u) << 1);
+    r = ((r >> 2) & 0x3333u) | ((r & 0x3333u) << 2);
+    r = ((r >> 4) & 0x0f0fu) | ((r & 0x0f0fu) << 4);
+    r = ((r >> 8) & 0x00ffu) | ((r & 0x00ffu) << 8);
+    const uint32_t fw = (x << f.drop) & 0xffffu, bw = r >> f.drop;
+    return f.valid ? (f.rev ? bw : fw) : 0u;
+}
+
 // retrieve_next_aln_block (MC/gapalign.cpp:9-45) + staging of the block's codes in extension order
 __device__ void pair_prepare(const LaneArgs &g, const LaneChain &s, const PairScratch &ps, PairBlk &blk)
 {
@@ -662,32 +724,38 @@ __device__ void pair_prepare(const LaneArgs &g, const LaneChain &s, const PairSc
     }
     const int qw = (blk.qblk + 15) >> 4, tw = (blk.tblk + 16) >> 4;
     const int qdir = s.c.strand == 0 ? s.inc : -s.inc;
+    const bool rc = s.c.strand != 0;
     // four words at a time: their loads are in flight together, and leave as one 16-byte store (the arrays are padded to 48 words)
     static_assert(kPairSeqBytes >= 4 * ((kSeqWords + 3) / 4 * 4), "code arrays hold whole groups of four words");
     for (int w0 = 0; w0 < qw; w0 += 4) {
-        uint32_t v4[4];
+        PairFetch fc[4], fb[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int w = w0 + i;
-            uint32_t v = 0;
-            if (w < qw) {
-                const int p = s.q0 + s.inc * (s.qidx + 16 * w);
-                const int64_t fp = s.c.strand == 0 ? p : (int64_t)s.rlen - 1 - p;
-                v = fetch16(g.seqs.reads2, s.roff, s.rlen, fp, qdir);
-                if (s.c.strand != 0) v ^= ~spread_bits16(fetch16_bits(g.seqs.reads_irr, s.roff, fp, qdir));
-            }
-            v4[i] = v;
+            const int p = s.q0 + s.inc * (s.qidx + 16 * w);
+            const int64_t fp = rc ? (int64_t)s.rlen - 1 - p : p;
+            pair_fetch16_issue(fc[i], g.seqs.reads2, s.roff, s.rlen, fp, qdir, w < qw);
+            pair_fetch16_bits_issue(fb[i], g.seqs.reads_irr, s.roff, fp, qdir, rc && w < qw);
+        }
+        uint32_t v4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t v = pair_fetch16_finish(fc[i]);
+            if (rc) v ^= ~spread_bits16(pair_fetch16_bits_finish(fb[i]));
+            v4[i] = w0 + i < qw ? v : 0u;
         }
         pair_store16(reinterpret_cast<uint8_t *>(ps.qcodes + w0), v4);
     }
     const int twc = min(tw, kSeqWords);
     for (int w0 = 0; w0 < twc; w0 += 4) {
-        uint32_t v4[4];
+        PairFetch fc[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int w = w0 + i;
-            v4[i] = w < twc ? fetch16(g.seqs.ref2, 0, g.seqs.ref_len, s.t0 + (int64_t)s.inc * (s.tidx + 16 * w), s.inc) : 0u;
+            pair_fetch16_issue(fc[i], g.seqs.ref2, 0, g.seqs.ref_len, s.t0 + (int64_t)s.inc * (s.tidx + 16 * (w0 + i)), s.inc, w0 + i < twc);
         }
+        uint32_t v4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v4[i] = pair_fetch16_finish(fc[i]);
         pair_store16(reinterpret_cast<uint8_t *>(ps.tcodes + w0), v4);
     }
 }

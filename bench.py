@@ -31,10 +31,11 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of xdrop_pair_kernel from the ncu --set full capture
-# profiles/kernel_r01h_pair.md (150k reads: 78.28 + 87.24 GB for 1 578 478 191 aligned bases); DRAM bytes per
-# aligned base do not depend on the batch size, so the per-launch figure is that ratio x this launch's bases
-TRAFFIC_BYTES_PER_ALIGNED_BASE = (78.276094e9 + 87.243725e9) / 1578478191
-TRAFFIC_NOTE = "ncu dram bytes per aligned base (profiles/kernel_r01h_pair.md, 150k-read launch) x aligned bases of this launch"
+# profiles/kernel_r02ah_pair.md (150k reads: 110.46 + 88.80 GB for 1 578 478 191 aligned bases; the walk now fetches whole
+# traceback rows ahead of itself, r01h/r02k: 78.3 + 87.2 GB); DRAM bytes per aligned base do not depend on the batch size,
+# so the per-launch figure is that ratio x this launch's bases
+TRAFFIC_BYTES_PER_ALIGNED_BASE = (110.457820e9 + 88.801872e9) / 1578478191
+TRAFFIC_NOTE = "ncu dram bytes per aligned base (profiles/kernel_r02ah_pair.md, 150k-read launch) x aligned bases of this launch"
 METRIC = "aligned_gbp_per_s"
 UNIT = "Gbp/s"
 DTYPE = "f16"          # the DP scores are exact integers held as binary16, two extension directions per 32-bit register (xdrop_pair.cuh)
@@ -908,8 +909,9 @@ def main():
     traffic_bytes = TRAFFIC_BYTES_PER_ALIGNED_BASE * st["aligned"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "achieved_is": "ALGORITHMIC bytes (SURVEY 8d: 3 B per DP cell + 3.6 B per aligned base) / kernel time -- not DRAM utilisation",
-                "limiter": "instruction issue (ALU pipe ~70 %, issue slots ~72 % busy, DRAM ~16 %: profiles/kernel_r01h_pair.md); the score band "
-                           "never leaves the SM, what reaches DRAM is the 4-bit traceback",
+                "limiter": "instruction issue and latency at 16 warps per SM (ALU pipe 68 %, issue slots 67 % busy, DRAM 20 %: "
+                           "profiles/kernel_r02ah_pair.md, stall attribution in profiles/pair_issue_r02.md); the score band never leaves the SM, "
+                           "what reaches DRAM is the 4-bit traceback",
                 "dram_gbs_measured": traffic_bytes / kern_s / 1e9,
                 "traffic": TRAFFIC_BYTES_PER_ALIGNED_BASE * st["aligned"], "traffic_note": TRAFFIC_NOTE,
                 "kernel": "xdrop_pair_kernel", "kernel_ms_per_launch": kernel_ms / args.steps,
