@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--reads", "48", "--steps", "1",
-                        "--warmup", "1", "--cpu-sample-per-core", "6"], capture_output=True, text=True, timeout=600)
+                        "--warmup", "1", "--cpu-sample-per-core", "6", "--full-reads", "0"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
