@@ -911,6 +911,13 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
 {
     cudaStream_t st = ctx->stream;
     int launches = 0;
+    // AG2_TRACE: host clock at the points where this function waits for the stream anyway (no extra synchronisation)
+    static const bool trace = getenv("AG2_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace) fprintf(stderr, "[ag2 trace] extend_batch %-28s %8.3f ms\n", what,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     if (!h_cand) { // without the host's copy of the candidates nothing says which reads a chunk needs: wait for all of them
         int rb = reads_barrier(ctx);
         if (rb != AG2_OK) return rb;
@@ -993,6 +1000,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     CK(cudaMemcpyAsync(ctx->h_prefix.data(), ctx->prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ctx->h_meta_prefix.data(), ctx->meta_prefix.p, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    lap("setup, scans, prefixes home");
     const std::vector<int64_t> &pf = ctx->h_prefix, &mf = ctx->h_meta_prefix;
 
     // candidates are processed in chunks whose workspace strings fit ws_limit
@@ -1156,6 +1164,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             cw.counters = &sc->ctr;
             cw.try_narrow = 1;
             CK(cudaStreamSynchronize(st));
+            lap("chunk inputs in place");
             if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
             CK(cudaGetLastError());
             CK(cudaEventRecord(ctx->side_done, ctx->side_stream));
@@ -1169,6 +1178,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             CK(cudaMemcpyAsync(&n_handed, &sc->lane_count, sizeof n_handed, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(&taken, &sc->next_wide, sizeof taken, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+            lap("pair kernel + consumer done");
             launches += 3;
             ctx->stats_lane_chains += n_handed;
             // [first, n_handed) was published after the consumer's last ticket: few -> wide kernel, many -> lane kernel
@@ -1230,6 +1240,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
         int64_t chunk_total = 0;
         CK(cudaMemcpyAsync(&chunk_total, (int64_t *)ctx->dense_off.p + lo + cn, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        lap("post-pass, finalize, scan");
         assemble_kernel<<<grid_for(cn * 32, 256, ctx->sm_count), 256, 0, st>>>(
             d_rec, (const ExtGeom *)ctx->geom.p, (const ChainResult *)ctx->res.p, (const uint32_t *)ctx->meta.p,
             (const int64_t *)ctx->dense_off.p, dense_base, lo, cn, (const char *)ctx->ws_q.p, (const char *)ctx->ws_t.p,
@@ -1246,6 +1257,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     }
     CK(cudaStreamSynchronize(st));
     if (sink) CK(cudaStreamSynchronize(ctx->copy_stream));
+    lap("assemble (and copies home)");
     *dense_base_out = dense_base;
 
     Scalars hs;
