@@ -523,7 +523,7 @@ __device__ __forceinline__ void pair_copy4_async(uint32_t *smem_dst, const uint3
 //     row, the row kPairWalkRows below it is requested into the slot that has become free;
 //   * code words of the block (16 positions each): two-word rings in sm.tg[0..3]; entering a word requests the one below;
 //   * window moves: a bit per kPairMoveStep rows in sm.tg[4..11], built once from the log.
-// Every step commits one group of copies (possibly empty) and starts by waiting for all but the kPairWalkRows - 1 youngest:
+// Every step commits one group of copies (possibly empty) and starts by waiting for all but the kPairWalkRows - 2 youngest:
 // the row the walk stands on was requested at least that many steps ago, a code word at least 16.
 // (2) A branch on the lane's own state (kind of step, word boundary, trimming) makes the warp run every side of it at nearly
 // every step.  The step is straight-line code: selects, and side effects under the lane's `walking`.
@@ -580,12 +580,22 @@ __device__ int pair_walk(PairSmem &sm, int tid, uint8_t *cta_scratch, int hh, bo
             fs = fs ? fs - 1 : kPairWalkRows - 1;
         }
     }
+    // The refill of a slot is issued one step late, behind the next step's read of its cell: the copies sit in the same
+    // memory queue as that read and would hold it up, and their address registers would be rewritten right behind them.
+    bool refill = false;
+    int refill_slot = 0;
+    const uint8_t *refill_src = fsrc;
     while (__any_sync(kFull, walking)) {
-        pair_copy_wait_but<kPairWalkRows - 1>();
+        pair_copy_wait_but<kPairWalkRows - 2>();
         // the cell: row a (ring slot slot_a), window slot b - 8 ns
         const int slot = b - 8 * ns;
         const int f = slot_a * kPairGroups + min(max(slot >> 3, 0), kPairGroups - 1);
         const uint32_t word = sm.v[f >> 2][tid][f & 3];
+        if (refill) {
+#pragma unroll
+            for (int qd = 0; qd < kPairQuads; ++qd)
+                pair_copy16_async(&sm.v[refill_slot * kPairQuads + qd][tid][0], refill_src + (size_t)qd * kPairQuadStride);
+        }
         int cell = (int)((word >> (16 * ((slot >> 2) & 1) + 4 * (3 - (slot & 3)))) & 15u);
         cell = a > 0 ? cell : kOpGapA;              // row 0 is all SCRIPT_GAP_IN_A (:61)
         int nxt = (cell & 1) ? kOpGapA : (cell & 2); // kOpGapB == 2, kOpSub == 0
@@ -597,11 +607,10 @@ __device__ int pair_walk(PairSmem &sm, int tid, uint8_t *cta_scratch, int hh, bo
         const int mbit = a / kPairMoveStep;
         const uint32_t mword = sm.tg[4 + ((mbit >> 5) & 7)][tid];
         ns -= (da && (a & (kPairMoveStep - 1)) == 0) ? (int)((mword >> (mbit & 31)) & 1u) : 0;
-        // the slot of the row being left takes the row kPairWalkRows below it
-        if (da && fetch >= 1) {
-#pragma unroll
-            for (int qd = 0; qd < kPairQuads; ++qd) pair_copy16_async(&sm.v[slot_a * kPairQuads + qd][tid][0], fsrc + (size_t)qd * kPairQuadStride);
-        }
+        // the slot of the row being left takes the row kPairWalkRows below it (at the next step)
+        refill = da && fetch >= 1;
+        refill_slot = slot_a;
+        refill_src = fsrc;
         a -= da;
         fetch -= da;
         fsrc -= da ? kPairRowStride : 0;
