@@ -285,6 +285,30 @@ __global__ void pack_ops_kernel(const char *__restrict__ q, const char *__restri
     }
 }
 
+// Entry t of the hand-over queue: continued from the block the pair kernel stopped at (run_chain_resumed: 128 columns per
+// lane first, the kernel's K from the block that does not fit them).  false = not possible (no state, or a reservation of
+// the pair / lane format is exceeded): the caller restarts the direction on the plain form.
+template <int K>
+__device__ bool continue_handed_over(const ChainArgs &g, int64_t chain, unsigned long long t, WarpSmem &sm, uint8_t *tb, int lane,
+                                     ChainCounters &ctr)
+{
+    if (!g.resume) return false;
+    LaneChain s;
+    lane_start_chain(g, chain, s);
+    if (!s.ge.valid) return false;
+    lane_resume(s, g.resume[t]);
+    ChainCounters lc = {0, 0, 0, 0, 0};
+    int rc = 2;
+    if (K > kNarrowK && g.try_narrow) rc = run_chain_resumed<kNarrowK>(g, s, sm, tb, lane, lc);
+    if (rc == 2) rc = run_chain_resumed<K>(g, s, sm, tb, lane, lc);
+    if (rc != 0) return false;
+    ctr.cells += lc.cells + s.cells;      // s.cells / rows / blocks: what the pair kernel did before it handed over
+    ctr.rows += lc.rows + s.rows;
+    ctr.blocks += lc.blocks + s.blocks;
+    ctr.interior += lc.interior;
+    return true;
+}
+
 // Wide path (any band a block can have): the int32 row kernel with K columns per lane.
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
@@ -301,8 +325,8 @@ __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)
         if ((int64_t)t >= g.n_chains) break;
         const int64_t chain = g.queue ? (int64_t)g.queue[t] : (int64_t)t;
         // most bands that left the pair kernel's 96-column window still fit 128 columns: rows ~5 x shorter than with K = 23
-        bool done = false;
-        if (K > kNarrowK && g.try_narrow) done = run_chain<kNarrowK>(g, chain, sm, tb, lane, ctr);
+        bool done = continue_handed_over<K>(g, chain, t, sm, tb, lane, ctr);
+        if (!done && K > kNarrowK && g.try_narrow) done = run_chain<kNarrowK>(g, chain, sm, tb, lane, ctr);
         if (!done) done = run_chain<K>(g, chain, sm, tb, lane, ctr);
         if (!done) {
             ctr.wide += 1;
@@ -352,8 +376,9 @@ __global__ void __launch_bounds__(WARPS * 32) xdrop_stream_kernel(ChainArgs g, c
     go = __shfl_sync(kFull, go, 0);
     while (go) {
         int chain = -1;
+        unsigned long long t = 0;
         if (lane == 0 && *done < n_producers) {
-            const unsigned long long t = atomicAdd(g.next, 1ull);
+            t = atomicAdd(g.next, 1ull);
             for (;;) {
                 chain = queue[t];
                 if (chain >= 0) break;
@@ -366,10 +391,11 @@ __global__ void __launch_bounds__(WARPS * 32) xdrop_stream_kernel(ChainArgs g, c
             }
         }
         chain = __shfl_sync(kFull, chain, 0);
+        t = __shfl_sync(kFull, t, 0);
         if (chain < 0) break;
         __threadfence();
-        bool ok = false;
-        if (K > kNarrowK && g.try_narrow) ok = run_chain<kNarrowK>(g, chain, sm, tb, lane, ctr);
+        bool ok = continue_handed_over<K>(g, chain, t, sm, tb, lane, ctr);
+        if (!ok && K > kNarrowK && g.try_narrow) ok = run_chain<kNarrowK>(g, chain, sm, tb, lane, ctr);
         if (!ok) ok = run_chain<K>(g, chain, sm, tb, lane, ctr);
         if (!ok) ctr.wide += 1;
     }
@@ -1163,6 +1189,8 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
             cw.next = &sc->next_wide;
             cw.counters = &sc->ctr;
             cw.try_narrow = 1;
+            cw.resume = (const LaneResume *)ctx->lane_resume.p;   // hand-overs are continued at the block they stopped at
+            cw.meta = a.meta;
             CK(cudaStreamSynchronize(st));
             lap("chunk inputs in place");
             if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
@@ -1225,6 +1253,10 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
                 w.wide_count = nullptr;
                 w.counters = &sc->ctr;
                 w.try_narrow = 1;
+                if (!lane_path) {   // straight from the hand-over queue: the states are there
+                    w.resume = (const LaneResume *)ctx->lane_resume.p + first;
+                    w.meta = a.meta;
+                }
                 xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
                 CK(cudaGetLastError());
                 ++launches;
@@ -1472,6 +1504,8 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     cw.next = &sc->next_wide;
     cw.counters = &sc->ctr;
     cw.try_narrow = 1;
+    cw.resume = (const LaneResume *)ctx->lane_resume.p;
+    cw.meta = pa.meta;
     CK(cudaStreamSynchronize(st));
     if (stream_grid > 0) xdrop_stream_kernel<kWideK, kWideWarps><<<stream_grid, kWideWarps * 32, 0, ctx->side_stream>>>(cw, &sc->pair_done, (unsigned)pair_grid);
     CK(cudaGetLastError());
@@ -1531,6 +1565,7 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
             w.n_chains = n_wide;
             w.queue = post_queue;
             w.next = &sc->next_post;
+            w.resume = lane_path ? nullptr : (const LaneResume *)ctx->lane_resume.p + first;   // parallel to `queue`
             xdrop_chains_kernel<kWideK, kWideWarps><<<wide_grid, kWideWarps * 32, 0, st>>>(w);
             CK(cudaGetLastError());
             ++launches;

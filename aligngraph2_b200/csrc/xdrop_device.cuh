@@ -439,6 +439,8 @@ __device__ __forceinline__ bool wait_for_read(const StreamSignal &s, int64_t rea
     return true;
 }
 
+struct LaneResume;   // xdrop_lane.cuh: state of a direction at a block boundary
+
 struct ChainArgs {
     StreamSignal sig;
     PackedSeqs seqs;
@@ -455,6 +457,10 @@ struct ChainArgs {
     unsigned int *wide_count;
     ChainCounters *counters;
     int try_narrow;          // run the direction with kNarrowK columns per lane first (the kernel's K only if its band leaves that window)
+    // hand-overs of the pair kernel: entry t of `queue` comes with the state at the block it stopped at and is CONTINUED
+    // from there in the pair / lane format (xdrop_lane.cuh: run_chain_resumed); null = every direction starts at its origin
+    const LaneResume *resume;
+    uint32_t *meta;          // block metadata words of that format
 };
 
 constexpr int kNarrowK = 4;  // 128 columns: rows ~5 x shorter than with 23 columns per lane (736, any band)

@@ -344,7 +344,8 @@ struct LaneChain { // registers of the chain a lane is running
     unsigned long long cells, rows, blocks;
 };
 
-__device__ __forceinline__ void lane_start_chain(const LaneArgs &g, int64_t chain, LaneChain &s)
+template <typename Args>   // LaneArgs or ChainArgs
+__device__ __forceinline__ void lane_start_chain(const Args &g, int64_t chain, LaneChain &s)
 {
     s.chain = chain;
     const int64_t ci = chain >> 1;
@@ -433,6 +434,117 @@ __device__ __forceinline__ int lane_block_tail(const LaneArgs &g, LaneChain &s, 
     return 0;
 }
 
+
+// A direction on the row-parallel kernel (one WARP per direction, xdrop_device.cuh) but in THIS path's format -- per block a
+// segment of the workspace in walk order and a metadata word -- from the block boundary held in `s` (all lanes hold the same
+// `s`).  It is how a direction the pair kernel hands over late is finished: continued at the block it stopped at, not
+// restarted (a restart of a 10 kb direction is ~17 ms on one warp, and the launch waited for it).
+// Returns 0 = the direction is complete (result written), 2 = this block's band does not fit K columns per lane (`s` is at
+// that block's boundary: a wider K continues from it), 3 = a reservation of the format is exceeded (restart on the plain form).
+template <int K>
+__device__ int run_chain_resumed(const ChainArgs &g, LaneChain &s, WarpSmem &sm, uint8_t *tb, int lane, ChainCounters &lc)
+{
+    for (int iter = 0; iter < (1 << 14); ++iter) { // the bound only guards against a hang
+        // retrieve_next_aln_block (MC/gapalign.cpp:9-45)
+        const int qleft = s.qsize - s.qidx, tleft = s.tsize - s.tidx;
+        int qblk, tblk;
+        bool last_block;
+        if (qleft < kBlk + kBlkSlack || tleft < kBlk + kBlkSlack) {
+            qblk = min(qleft, stretch_0p2(tleft));
+            tblk = min(tleft, stretch_0p2(qleft));
+            last_block = true;
+        } else {
+            qblk = kBlk;
+            tblk = kBlk;
+            last_block = false;
+        }
+        // stage the block: one code per byte, extension order (as run_chain)
+        __syncwarp();
+        for (int i = lane; i < qblk; i += 32) {
+            const int p = s.q0 + s.inc * (s.qidx + i);
+            int code;
+            if (s.c.strand == 0) {
+                code = get2(g.seqs.reads2, s.roff + p);
+            } else {
+                const int64_t fp = s.roff + (s.rlen - 1 - p);
+                code = get2(g.seqs.reads2, fp);
+                if (!get1(g.seqs.reads_irr, fp)) code ^= 3;
+            }
+            sm.A[i] = (uint8_t)code;
+        }
+        for (int i = lane; i < tblk; i += 32) sm.B[i] = (uint8_t)get2(g.seqs.ref2, s.t0 + (int64_t)s.inc * (s.tidx + i));
+        __syncwarp();
+        int ae = 0, be = 0;
+        ChainCounters bc = {0, 0, 0, 0, 0};
+        if (qblk > 0 && tblk > 0) {
+            if (dp_block<K>(sm.A, qblk, sm.B, tblk, tb, lane, ae, be, bc)) return 2;
+        }
+        lc.cells += bc.cells;
+        lc.rows += bc.rows;
+        lc.blocks += bc.blocks;
+        lc.interior += bc.interior;
+        __syncwarp();
+        const int cap = (int)min((int64_t)(2 * kMaxBlk), s.seg_end - s.seg);
+        if (ae + be > cap || s.meta + s.nblocks >= s.meta_end) return 3;
+        int nops = 0, qcnt = 0, tcnt = 0, acnt = 0, trim_m = 0, trim_w = -1;
+        if (lane == 0) nops = walk_block<K>(tb, ae, be, sm, qcnt, tcnt, acnt, trim_m, trim_w);
+        nops = __shfl_sync(kFull, nops, 0);
+        qcnt = __shfl_sync(kFull, qcnt, 0);
+        tcnt = __shfl_sync(kFull, tcnt, 0);
+        acnt = __shfl_sync(kFull, acnt, 0);
+        trim_m = __shfl_sync(kFull, trim_m, 0);
+        trim_w = __shfl_sync(kFull, trim_w, 0);
+        __syncwarp();
+        // the segment: walk step i (from the block's end cell towards its origin) at seg + i
+        int qi = 0, ti = 0;
+        for (int base = 0; base < nops; base += 32) {
+            const int i = base + lane;
+            const bool on = i < nops;
+            const int op = on ? sm.ops[i] : kOpGapA;
+            const unsigned qm = __ballot_sync(kFull, on && op != kOpGapA);
+            const unsigned tm = __ballot_sync(kFull, on && op != kOpGapB);
+            const unsigned lt = (1u << lane) - 1u;
+            if (on) {
+                g.ws_q[s.seg + i] = op != kOpGapA ? code_char(sm.A[ae - 1 - (qi + __popc(qm & lt))]) : '-';
+                g.ws_t[s.seg + i] = op != kOpGapB ? code_char(sm.B[be - 1 - (ti + __popc(tm & lt))]) : '-';
+            }
+            qi += __popc(qm);
+            ti += __popc(tm);
+        }
+        // lane_block_tail, by all lanes alike; lane 0 writes the metadata word
+        const bool full_map = (qblk - ae <= kFullMapSlack) || (tblk - be <= kFullMapSlack); // (:334-335)
+        const bool stop = !full_map || last_block;
+        const bool trim_ok = trim_m == kTailMatch && (nops - 2 - trim_w) > 0;
+        int skip = 0;
+        if (!stop) {
+            if (!trim_ok) { // (:349) the block's columns are dropped and the direction ends
+                if (lane == 0) g.meta[s.meta + s.nblocks] = (uint32_t)nops | ((uint32_t)nops << 16);
+                ++s.nblocks;
+                break;
+            }
+            skip = acnt;
+        }
+        if (lane == 0) g.meta[s.meta + s.nblocks] = (uint32_t)nops | ((uint32_t)skip << 16);
+        ++s.nblocks;
+        s.seg += nops;
+        if (nops - skip > 0) {
+            s.last_op = sm.ops[skip];                  // first op after the trimmed ones (the walk's first op without a trim)
+            s.ncols += nops - skip;
+            s.qcons += skip ? ae - qcnt : ae;
+            s.tcons += skip ? be - tcnt : be;
+        }
+        if (stop) break;
+        s.qidx += ae - qcnt; // (:354-355)
+        s.tidx += be - tcnt;
+    }
+    __syncwarp(); // the segments were written by all lanes
+    if (lane == 0) {
+        const ChainResult out = {s.ncols, s.qcons, s.tcons, s.last_op, s.nblocks, 0, 0, 0};
+        g.res[s.chain] = out;
+        signal_direction_done(g.sig, s.chain);
+    }
+    return 0;
+}
 
 // One block of align_ex for the lane's chain.  Returns 0 = chain continues, 1 = chain finished,
 // 2 = hand the chain to the wide path.

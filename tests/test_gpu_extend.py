@@ -129,6 +129,28 @@ def test_repeats_and_wide_bands(dev, oracle):
     assert st["wide_chains"] > 0 or st["interior"] > 0
 
 
+def test_late_hand_overs_are_continued_at_their_block(dev, oracle):
+    """A tandem repeat deep inside the reads: the pair kernel runs ~8 blocks of a direction, then the band leaves its window
+    and the direction is handed over -- the consumer continues it from that block in the pair format (run_chain_resumed),
+    and records, strings and the cell count must still be the reference's."""
+    rng = np.random.default_rng(11)
+    unit = synth.make_reference(rng, 7)
+    ref = np.concatenate([synth.make_reference(rng, 9000), np.tile(unit, 500), synth.make_reference(rng, 9000)])
+    reads, cands = [], []
+    for i in range(16):
+        start = int(rng.integers(2000, 4000))
+        rd, _, _ = synth.make_read(rng, ref[start:start + 9001], 9000, False)
+        strand = i & 1
+        reads.append(np.frombuffer(rd.tobytes() if not strand else synth.orient(rd.tobytes(), 1), dtype=np.uint8))
+        cands.append((i, strand, start + 501, 500))
+    off = np.zeros(len(reads) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in reads], out=off[1:])
+    c = np.array(cands)
+    cand = dev.make_candidates(c[:, 0], c[:, 1], c[:, 2], c[:, 3])
+    st = _check_against_oracle(dev, oracle, ref, np.concatenate(reads), off, cand)
+    assert st["lane_chains"] > 0        # directions did leave the pair kernel
+
+
 def test_small_batches_take_the_row_parallel_path(dev, oracle, monkeypatch):
     """A handful of candidates (rescue extensions, second pass) runs one warp per direction with a 128-column window, and
     what leaves that window on the full-width form: same records, same strings, same cell count."""
