@@ -222,7 +222,12 @@ __global__ void __launch_bounds__(kLaneThreads) xdrop_lane_kernel(LaneArgs g)
 
 // Pair path (xdrop_pair.cuh): two directions per thread in packed 16-bit arithmetic, 64 directions in lock step
 // per warp.  The dominant kernel; the lane kernel above restarts the directions it hands over.
-__global__ void __launch_bounds__(kPairThreads, 8) xdrop_pair_kernel(LaneArgs g)
+__device__ __forceinline__ void pair_kernel_entry(const LaneArgs &g);
+__global__ void __launch_bounds__(kPairThreads, 8) xdrop_pair_kernel(LaneArgs g) { pair_kernel_entry(g); }
+// The same built for nine CTAs per SM: ptxas then takes 96 registers (16 bytes spilled).  An experiment of the streamed form
+// (AG2_STREAM_LEAN_KERNEL=1): eight CTAs that leave a quarter of the register file to the small kernels beside them.
+__global__ void __launch_bounds__(kPairThreads, 9) xdrop_pair_kernel_lean(LaneArgs g) { pair_kernel_entry(g); }
+__device__ __forceinline__ void pair_kernel_entry(const LaneArgs &g)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     PairSmem &sm = *reinterpret_cast<PairSmem *>(smem_raw);
@@ -1315,7 +1320,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
 
 // Which form ag2_xdrop_extend_batch takes when AG2_E2E_PATH does not say (see there).
 constexpr bool kStreamedByDefault = true;
-constexpr int kStreamPairCtasPerSm = 6;   // streamed form: pair CTAs per SM (7 fit), see extend_batch_streamed
+constexpr int kStreamPairCtasPerSm = 6;   // streamed form: pair CTAs per SM (8 fit), see extend_batch_streamed
 // extend_batch_streamed asks for the chunked form instead (positive: not an error of the call)
 constexpr int kStreamStalled = 1;         // in-kernel waits for the reads ran into their limit, results void
 constexpr int kStreamTooBig = 2;          // the whole batch's workspace does not fit beside what is resident; nothing ran
@@ -1349,17 +1354,28 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     RESERVE(ctx->chunk_count, (size_t)kMaxStreamChunks * 4);
 
     // The small kernels of this form (packing of the pieces still arriving, finalize / scan / assemble of the finished
-    // chunks) must run BESIDE the resident pair kernel.  At its full 7 CTAs per SM they did not get onto the SMs before pair
+    // chunks) must run BESIDE the resident pair kernel.  At its full occupancy they did not get onto the SMs before pair
     // CTAs retired (configs[1]: the first chunk's finalize waited 250 ms, in-kernel waits for the pack kernels ran into their
     // limit), so this launch asks for more dynamic shared memory than it uses until only kStreamPairCtasPerSm fit: every SM
-    // keeps a free slot (shared memory, 8 k registers, 64 threads) for them.
+    // keeps a free slot for them.  Registers are not what is missing: with the 96-register build of the kernel
+    // (AG2_STREAM_LEAN_KERNEL=1) all 8 CTAs fit beside 16 K free registers, and one run in eight still stalled.
+    // An SM has ONE shared-memory carve-out at a time: a kernel whose launch picks another one cannot join the pair CTAs on
+    // their SMs at all and waits for an idle SM -- which a persistent launch does not leave.  The small kernels ask for the
+    // pair kernel's carve-out, as the consumer kernel does.
+    CK(cudaFuncSetAttribute(pack_reads_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(pack_ops_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(extend_finalize_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(scan_chunk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int pocc = 0, want_occ = kStreamPairCtasPerSm;
     if (const char *e = getenv("AG2_STREAM_CTAS_PER_SM")) want_occ = std::max(1, atoi(e));   // tuning knob
+    static const bool lean_kernel = getenv("AG2_STREAM_LEAN_KERNEL") != nullptr;            // tuning knob: the 96-register build
+    auto pair_kernel = lean_kernel ? xdrop_pair_kernel_lean : xdrop_pair_kernel;
     size_t pair_smem = sizeof(PairSmem);
-    CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     for (;;) {
-        CK(cudaFuncSetAttribute(xdrop_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, xdrop_pair_kernel, kPairThreads, pair_smem));
+        CK(cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, pair_kernel, kPairThreads, pair_smem));
         if (pocc <= want_occ || pair_smem + 1024 > (size_t)200 * 1024) break;
         pair_smem += 1024;
     }
@@ -1518,7 +1534,7 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     }
     const double t_launch = now_ms();
     CK(cudaEventRecord(ctx->chain_events[0].first, st));
-    xdrop_pair_kernel<<<pair_grid, kPairThreads, pair_smem, st>>>(pa);
+    pair_kernel<<<pair_grid, kPairThreads, pair_smem, st>>>(pa);
     CK(cudaEventRecord(ctx->chain_events[0].second, st));
     CK(cudaGetLastError());
     CK(cudaStreamWaitEvent(st, ctx->side_done, 0));
