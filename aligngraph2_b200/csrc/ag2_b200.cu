@@ -1304,6 +1304,7 @@ static int extend_batch(ag2_ctx *ctx, const Candidate *d_cand, int64_t n, Record
     s.rows = (int64_t)hs.ctr.rows;
     s.blocks = (int64_t)hs.ctr.blocks;
     s.interior = (int64_t)hs.ctr.interior;
+    s.slots = (int64_t)hs.ctr.slots;
     s.wide_chains = (int64_t)hs.ctr.wide + ctx->stats_direct_wide;
     s.aligned = (int64_t)hs.aligned;
     s.columns = (int64_t)hs.columns;
@@ -1662,6 +1663,7 @@ static int extend_batch_streamed(ag2_ctx *ctx, const Candidate *d_cand, int64_t 
     s.rows = (int64_t)hs.ctr.rows;
     s.blocks = (int64_t)hs.ctr.blocks;
     s.interior = (int64_t)hs.ctr.interior;
+    s.slots = (int64_t)hs.ctr.slots;
     s.wide_chains = (int64_t)hs.ctr.wide + ctx->stats_direct_wide;
     s.aligned = (int64_t)hs.aligned;
     s.columns = (int64_t)hs.columns;

@@ -92,6 +92,7 @@ struct ChainResult {
 
 struct ChainCounters {
     unsigned long long cells, rows, blocks, interior, wide;
+    unsigned long long slots;   // pair kernel: window slots evaluated (8 per executed group for each of a warp's 64 directions); last: initialisers stay short
 };
 
 // ASCII of a code 0..3 (ACGT) or 4 ('-'), computed: an indexed read of a string literal is a global load

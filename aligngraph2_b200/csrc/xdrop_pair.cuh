@@ -54,6 +54,7 @@ constexpr int kPairMinN = 32;                      // shortest target block this
 struct PairSmem {
     uint32_t v[kPairSlots / 4][kPairThreads][4];   // slot j of both directions: v[j >> 2][tid][j & 3]
     uint32_t tg[kPairGroups][kPairThreads];        // 8 target codes of group g (2 bits each), per half
+    uint32_t wgroups[kPairThreads / 32];           // per warp: groups executed (statistics; a counter here costs no register)
 };
 // 27 KB: eight CTAs (16 warps) per SM.  The forced-mismatch bits of the columns from N - 1 on are not stored: they are
 // needed in the last rows of a block only, and computed there (pair_dp).
@@ -436,6 +437,7 @@ __device__ void pair_dp(PairSmem &sm, const int tid, const PairScratch &s0, cons
             pair_store16(row1 + (size_t)(g >> 2) * kPairQuadStride, t1);
         }
         if (more) bail |= (c.Ms | c.Mlp) & run; // the window is too narrow for this direction
+        if ((tid & 31) == 0) sm.wgroups[tid >> 5] += (unsigned)g;
         c.be = h2_add(c.be, Jg);                // back to window columns
         c.lastj = h2_add(c.lastj, Jg);
         PES({ const int l0 = h2_lo_int(c.lastj), l1 = h2_hi_int(c.lastj);
@@ -794,6 +796,7 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
     s[0].chain = s[1].chain = -1;
     const PairScratch ps[2] = {pair_scratch(scratch, tid, 0), pair_scratch(scratch, tid, 1)}; // scratch = the CTA's
     unsigned long long cells = 0, rows = 0, blocks = 0, handed = 0;
+    if ((tid & 31) == 0) sm.wgroups[tid >> 5] = 0;
     bool drained = false, warp_main_done = false;
     unsigned from_defer = 0;            // bit h: slot h runs a deferred direction
     unsigned done2 = g.defer_queue ? 0u : 3u;   // bit h: slot h will get nothing more from the deferred queue
@@ -931,6 +934,8 @@ __device__ void pair_kernel_body(const LaneArgs &g, PairSmem &sm, int tid, uint8
     atomicAdd(&g.counters->cells, cells);
     atomicAdd(&g.counters->rows, rows);
     atomicAdd(&g.counters->blocks, blocks);
+    // every group of a warp evaluates 8 slots of its 64 directions, running or not
+    if ((tid & 31) == 0) atomicAdd(&g.counters->slots, (unsigned long long)sm.wgroups[tid >> 5] * (8ull * 64ull));
     (void)handed;
 }
 

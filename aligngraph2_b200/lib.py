@@ -28,7 +28,7 @@ assert CANDIDATE_DTYPE.itemsize == 24 and RECORD_DTYPE.itemsize == 56 and SEED_C
 
 class ExtendStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("cells", "rows", "blocks", "aligned", "columns", "wide_chains",
-                                        "interior", "launches")] + [("kernel_ms", C.c_double), ("lane_chains", C.c_int64)]
+                                        "interior", "launches")] + [("kernel_ms", C.c_double), ("lane_chains", C.c_int64), ("slots", C.c_int64)]
 
 
 class MapStats(C.Structure):

@@ -916,6 +916,7 @@ def main():
                 "traffic": TRAFFIC_BYTES_PER_ALIGNED_BASE * st["aligned"], "traffic_note": TRAFFIC_NOTE,
                 "kernel": "xdrop_pair_kernel", "kernel_ms_per_launch": kernel_ms / args.steps,
                 "algorithmic_bytes_per_aligned_base": b_alg, "cells_per_aligned_base": cbar,
+                "cells_per_slot": st["cells"] / max(1, st.get("slots", 0)),   # how full the window slots the kernel evaluated were
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0}
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----

@@ -70,6 +70,7 @@ typedef struct ag2_extend_stats {
     int64_t launches;     /* kernel launches made by the call */
     double kernel_ms;     /* CUDA-event time of the dominant kernel (xdrop_pair_kernel) */
     int64_t lane_chains;  /* extension directions the pair kernel handed on (to the wide kernel when few, else to the lane kernel) */
+    int64_t slots;        /* window slots the pair kernel evaluated (8 per executed group for each of a warp's 64 directions, running or not); cells / slots = how full they were */
 } ag2_extend_stats;
 
 /* Number of CUDA devices this process sees.  The hosts shard reads over them, one ag2_ctx and one host thread per

@@ -57,7 +57,7 @@ def test_struct_layouts_match_header(lib):
     from aligngraph2_b200.lib import CANDIDATE_DTYPE, RECORD_DTYPE, ExtendStats
     assert CANDIDATE_DTYPE.itemsize == 24
     assert RECORD_DTYPE.itemsize == 56
-    assert C.sizeof(ExtendStats) == 80
+    assert C.sizeof(ExtendStats) == 88
     from aligngraph2_b200.lib import MapStats
     assert C.sizeof(MapStats) == 7 * 8 + 9 * 8      # ag2_map_stats: 7 doubles, 9 int64
 
