@@ -554,6 +554,7 @@ __device__ bool seed_cta_strand(const RefIndex &ix, const uint32_t *reads2, cons
             if (bid > 0 && r > 0 && ev_block(ev[sm.run_start[r - 1]]) == bid - 1) loc = sm.run_score[r - 1];
             int64_t start_loc = (int64_t)(loc > 0 ? bid - 1 : bid) * zv;
             const int n1 = loc > 0 ? min(loc, kSM) : 0, n2 = min(s_k, kSM), u_k = n1 + n2;
+            __syncwarp();   // lane 0 may still be reading the previous block's lists (find_location_choose); a shuffle orders no memory
             for (int x = lane; x < u_k; x += 32) {
                 int l, sd;
                 if (x < n1) run_entry(rv, r - 1, x, l, sd);
@@ -651,6 +652,7 @@ __device__ bool seed_cta_strand(const RefIndex &ix, const uint32_t *reads2, cons
             if (ncand < maxc) ncand++;
             __syncwarp();
         }
+        __syncwarp();       // every lane has read misc[2] (no block above the threshold: nothing in between)
         if (lane == 0) sm.misc[2] = ncand;
     }
     __syncthreads();
