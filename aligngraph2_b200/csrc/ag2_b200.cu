@@ -472,6 +472,7 @@ struct ag2_ctx {
     size_t seed_scratch_limit = 0;        // 0 = from the free memory (seed_limit); else a fixed limit in bytes
     DevBuf reads2, reads_irr, read_off, read_len, ascii_offs;
     int64_t n_reads = 0, read_bases = 0;
+    int32_t read_len_p90 = 0;          // 90th percentile of the read lengths (of a sample): what the seeding tables are sized for
 
     DevBuf cand, geom, caps, prefix, nmeta, meta_prefix, meta, res, rec, str_begin, ok_len, dense_off;
     int64_t n_cand = 0;
@@ -862,6 +863,14 @@ static int reads_load_impl(ag2_ctx *ctx, const char *bases, const int64_t *offs,
     ctx->reads_pending = true;
     ctx->n_reads = n;
     ctx->read_bases = total;
+    {   // 90th percentile of a sample of the lengths
+        std::vector<int32_t> sample;
+        const int64_t step = std::max<int64_t>(1, n / 32768);
+        for (int64_t r = 0; r < n; r += step) sample.push_back(lens[r]);
+        const size_t k = std::min(sample.size() - 1, sample.size() * 9 / 10);
+        std::nth_element(sample.begin(), sample.begin() + k, sample.end());
+        ctx->read_len_p90 = sample[k];
+    }
     {   // which reads enter the read index: the first <= 100 000 while the running length (+1 each) < 1e9 (:277)
         int64_t lenl = 0, kk = 0;
         while (kk < n && kk < 100000 && lenl < 1000000000ll) {
@@ -2004,8 +2013,9 @@ struct SeedCtl {
 
 constexpr int kSeedCapMax = 13824;   // index hits per strand that fit the 227 KB of shared memory of one CTA
 
-// Events per strand the first CTA launch is sized for: seeds x (index positions per bucket + share of exact seeds of a
-// 15 %-error read), with a margin; what exceeds it goes to the second launch (kSeedCapMax), then to the thread path.
+// Events per strand the standard CTA launch is sized for: seeds of a read at the 90th percentile of the lengths x (index
+// positions per bucket + share of exact seeds of a 15 %-error read), with a margin; what exceeds it goes to the launch with
+// kSeedCapMax, then to the thread path.
 static int seed_cap(const ag2_ctx *ctx, int pass, int tier)
 {
     if (tier == 0)
@@ -2014,10 +2024,10 @@ static int seed_cap(const ag2_ctx *ctx, int pass, int tier)
         if (const char *e = getenv("AG2_SEED_CAP2")) return std::max(64, std::min(kSeedCapMax, atoi(e) & ~63));
         return kSeedCapMax;
     }
-    const double mean_len = ctx->n_reads ? (double)ctx->read_bases / (double)ctx->n_reads : 10000.0;
-    const double bc = pass == 0 ? std::min(20.0, 5.0 + mean_len / 1000.0) : 5.0;
+    const double len = ctx->n_reads ? (double)ctx->read_len_p90 : 10000.0;   // nine reads of ten are not longer
+    const double bc = pass == 0 ? std::min(20.0, 5.0 + len / 1000.0) : 5.0;
     const double density = (double)ctx->ix_npos / (double)kNCodes;
-    const double ev = (mean_len / bc + 1.0) * (density + 0.2);
+    const double ev = (len / bc + 1.0) * (density + 0.2);
     const int cap = ((int)(ev * 1.25) + 128 + 127) & ~127;
     return std::max(256, std::min(kSeedCapMax, cap));
 }
@@ -2028,9 +2038,9 @@ static int seed_cap(const ag2_ctx *ctx, int pass, int tier)
 static int seed_cap_tight(const ag2_ctx *ctx, const void *kernel, int pass, int cap)
 {
     if (getenv("AG2_SEED_CAP")) return 0;
-    const double mean_len = ctx->n_reads ? (double)ctx->read_bases / (double)ctx->n_reads : 10000.0;
-    const double bc = pass == 0 ? std::min(20.0, 5.0 + mean_len / 1000.0) : 5.0;
-    const double ev = (mean_len / bc + 1.0) * ((double)ctx->ix_npos / (double)kNCodes + 0.2);
+    const double len = ctx->n_reads ? (double)ctx->read_len_p90 : 10000.0;
+    const double bc = pass == 0 ? std::min(20.0, 5.0 + len / 1000.0) : 5.0;
+    const double ev = (len / bc + 1.0) * ((double)ctx->ix_npos / (double)kNCodes + 0.2);
     const int floor_cap = std::max(256, ((int)(ev * 1.06) + 32 + 63) & ~63);
     int occ0 = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, kernel, kSeedCtaThreads, seed_cta_smem_bytes(cap)) != cudaSuccess) return 0;
