@@ -290,30 +290,6 @@ __global__ void pack_ops_kernel(const char *__restrict__ q, const char *__restri
     }
 }
 
-// Entry t of the hand-over queue: continued from the block the pair kernel stopped at (run_chain_resumed: 128 columns per
-// lane first, the kernel's K from the block that does not fit them).  false = not possible (no state, or a reservation of
-// the pair / lane format is exceeded): the caller restarts the direction on the plain form.
-template <int K>
-__device__ bool continue_handed_over(const ChainArgs &g, int64_t chain, unsigned long long t, WarpSmem &sm, uint8_t *tb, int lane,
-                                     ChainCounters &ctr)
-{
-    if (!g.resume) return false;
-    LaneChain s;
-    lane_start_chain(g, chain, s);
-    if (!s.ge.valid) return false;
-    lane_resume(s, g.resume[t]);
-    ChainCounters lc = {0, 0, 0, 0, 0};
-    int rc = 2;
-    if (K > kNarrowK && g.try_narrow) rc = run_chain_resumed<kNarrowK>(g, s, sm, tb, lane, lc);
-    if (rc == 2) rc = run_chain_resumed<K>(g, s, sm, tb, lane, lc);
-    if (rc != 0) return false;
-    ctr.cells += lc.cells + s.cells;      // s.cells / rows / blocks: what the pair kernel did before it handed over
-    ctr.rows += lc.rows + s.rows;
-    ctr.blocks += lc.blocks + s.blocks;
-    ctr.interior += lc.interior;
-    return true;
-}
-
 // Wide path (any band a block can have): the int32 row kernel with K columns per lane.
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) xdrop_chains_kernel(ChainArgs g)

@@ -153,6 +153,7 @@ int emu_extend(int K, const char *ref, long ref_len, const char *read, int read_
 // reads: concatenated ASCII with offs[n+1]; cand: n x (read, strand, loc1, loc2).  Outputs per candidate:
 // rec[8] = ok qb qe sb se aln_len mode_left mode_right; strings concatenated into qaln/taln at aoff[i].
 static int g_emu_defer = 0;
+static int g_emu_row_resume = 0;   // handed-over directions continued by the row-parallel form (as xdrop_stream_kernel does), not by the lane kernel
 static int batch_impl(bool pair, const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
                       int n, long *rec, long *aoff, char *qaln, char *taln, long *stats /* cells wide handed */)
 {
@@ -228,7 +229,31 @@ static int batch_impl(bool pair, const char *ref, long ref_len, const char *read
             const int lane = warp_emu::st().cur;
             pair_kernel_body(pa, psm, lane, pa.scratch);
         });
-        if (handed) {
+        if (handed && g_emu_row_resume) {
+            // the consumer's way: continue_handed_over (128 columns per lane, then 736), a restart on the plain form if that gives up
+            static WarpSmem sm;
+            std::vector<uint8_t> tb((size_t)(kMaxBlk + 2) * TbLayout<23>::kRowBytes);
+            ChainArgs w = {};
+            w.seqs = sq;
+            w.cand = cs.data();
+            w.geom = ge.data();
+            w.res = res.data();
+            w.ws_q = wq.data();
+            w.ws_t = wt.data();
+            w.try_narrow = 1;
+            w.resume = lane_resume.data();
+            w.meta = meta.data();
+            warp_emu::run_warp([&]() {
+                const int lane = warp_emu::st().cur;
+                ChainCounters lc = {0, 0, 0, 0, 0};
+                for (unsigned t = 0; t < handed; ++t) {
+                    bool ok = continue_handed_over<23>(w, lane_queue[t], t, sm, tb.data(), lane, lc);
+                    if (!ok) ok = run_chain<4>(w, lane_queue[t], sm, tb.data(), lane, lc);
+                    if (!ok) run_chain<23>(w, lane_queue[t], sm, tb.data(), lane, lc);
+                }
+                if (lane == 0) ctr.cells += lc.cells;
+            });
+        } else if (handed) {
             next = 0;
             a.queue = lane_queue.data();
             a.resume = lane_resume.data();
@@ -293,6 +318,7 @@ static int batch_impl(bool pair, const char *ref, long ref_len, const char *read
 }
 
 void emu_set_defer(int on) { g_emu_defer = on; }
+void emu_set_row_resume(int on) { g_emu_row_resume = on; }
 
 int emu_lane_batch(const char *ref, long ref_len, const char *reads, const long *offs, int n_reads, const long *cand,
                    int n, long *rec, long *aoff, char *qaln, char *taln, long *stats)

@@ -208,3 +208,36 @@ def test_emulated_pair_path_long_reads(emu, oracle, defer):
         emu.emu_set_defer(0)
     _check(exp, got)
     assert got_cells == cells
+
+
+def test_emulated_hand_overs_continued_by_the_row_parallel_form(emu, oracle):
+    """What the consumer kernel does with a direction the pair kernel hands over (xdrop_stream_kernel ->
+    continue_handed_over -> run_chain_resumed): continue it at the failing block on the row-parallel DP, writing the pair
+    path's per-block segments.  Two batches: the stress batch (short target blocks, unrelated extensions: hand-overs at the
+    first blocks) and reads with a tandem repeat deep inside (hand-overs after several blocks)."""
+    emu.emu_set_row_resume(1)
+    try:
+        ref, reads, cands, exp, cells = _stress_batch(oracle, 22, 80)
+        got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
+        _check(exp, got)
+        assert got_cells == cells and handed > 0
+
+        rng = np.random.default_rng(11)
+        unit = synth.make_reference(rng, 7)
+        ref = np.concatenate([synth.make_reference(rng, 5000), np.tile(unit, 400), synth.make_reference(rng, 5000)])
+        reads, cands, exp, cells = [], [], [], 0
+        for i in range(8):
+            start = int(rng.integers(500, 1500))
+            rd, _, _ = synth.make_read(rng, ref[start:start + 5001], 5000, False)
+            strand = i & 1
+            given = rd.tobytes() if not strand else synth.orient(rd.tobytes(), 1)
+            reads.append(given)
+            cands.append((i, strand, start + 301, 300))
+            a = oracle.extend(ref.tobytes(), synth.orient(given, strand), start + 301, 300)
+            exp.append(a)
+            cells += a["cells"]
+        got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
+        _check(exp, got)
+        assert got_cells == cells and handed > 0
+    finally:
+        emu.emu_set_row_resume(0)
