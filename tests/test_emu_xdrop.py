@@ -217,7 +217,7 @@ def test_emulated_hand_overs_continued_by_the_row_parallel_form(emu, oracle):
     first blocks) and reads with a tandem repeat deep inside (hand-overs after several blocks)."""
     emu.emu_set_row_resume(1)
     try:
-        ref, reads, cands, exp, cells = _stress_batch(oracle, 22, 80)
+        ref, reads, cands, exp, cells = _stress_batch(oracle, 22, 40)
         got, got_cells, (wide, handed) = emu_lane_batch(emu, ref.tobytes(), reads, cands, pair=True)
         _check(exp, got)
         assert got_cells == cells and handed > 0
@@ -226,7 +226,7 @@ def test_emulated_hand_overs_continued_by_the_row_parallel_form(emu, oracle):
         unit = synth.make_reference(rng, 7)
         ref = np.concatenate([synth.make_reference(rng, 5000), np.tile(unit, 400), synth.make_reference(rng, 5000)])
         reads, cands, exp, cells = [], [], [], 0
-        for i in range(8):
+        for i in range(4):
             start = int(rng.integers(500, 1500))
             rd, _, _ = synth.make_read(rng, ref[start:start + 5001], 5000, False)
             strand = i & 1
