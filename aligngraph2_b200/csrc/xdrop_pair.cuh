@@ -25,7 +25,8 @@
 //     the rows at which the base moved are logged for the walk.
 //
 // A direction this path cannot hold (window overflow, a target block shorter than 32, reservation exceeded) is handed
-// to the lane kernel (xdrop_lane.cuh), which continues it from that block; behind that stands the wide kernel.
+// over with its state at that block: the consumer kernel beside this one continues it there on the row-parallel DP
+// (continue_handed_over, xdrop_lane.cuh), the lane kernel does when there are many; behind both stands the wide kernel.
 #pragma once
 
 #include "h2ops.cuh"
