@@ -103,6 +103,13 @@ long orc_map_batch(const char *ref, long R, const char *reads, const long *offs,
 long orc_solid_kmers(const char *reads, const long *offs, long n_reads, int k, double threshold, uint64_t *codes_out, long cap,
                      long *min_abundance);
 
+/* ---- vanilla MECAT2 DiffAligner (row N2, "next"): ag2_diff.c ---- */
+/* one block the way dw_in_one_direction aligns it; out6 = q_s q_e t_s t_e dist n; strings are codes 0..4 (4 = gap) */
+int orc_diff_block(const uint8_t *Q, int q_len, const uint8_t *T, int t_len, int right_extend, int *out6, uint8_t *qstr, uint8_t *tstr);
+/* DiffAligner::go; out5 = qoff qend toff tend aln_size; ASCII strings */
+int orc_diff_go(const uint8_t *query, int qstart, int qsize, const uint8_t *target, int tstart, int tsize, int min_aln_size,
+                int large_block, int *out5, char *qaln, char *taln);
+
 #ifdef __cplusplus
 }
 #endif

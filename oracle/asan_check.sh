@@ -12,7 +12,8 @@ FLAGS="-O1 -g -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -ffp-co
 /usr/bin/gcc $FLAGS -std=gnu11 -c -o /tmp/asan_o2.o oracle/ag2_mapper.c
 /usr/bin/gcc $FLAGS -std=gnu11 -c -o /tmp/asan_o3.o oracle/ag2_kmer.c
 /usr/bin/g++ $FLAGS -std=c++14 -c -o /tmp/asan_o4.o oracle/ag2_pagraph.cpp
-/usr/bin/g++ -shared -fsanitize=address,undefined -o $SO /tmp/asan_o1.o /tmp/asan_o2.o /tmp/asan_o3.o /tmp/asan_o4.o -lm
+/usr/bin/gcc $FLAGS -std=gnu11 -c -o /tmp/asan_o5.o oracle/ag2_diff.c
+/usr/bin/g++ -shared -fsanitize=address,undefined -o $SO /tmp/asan_o1.o /tmp/asan_o2.o /tmp/asan_o3.o /tmp/asan_o4.o /tmp/asan_o5.o -lm
 {
   echo "# ASan + UBSan pass of the oracle (oracle/asan_check.sh), $(date -u +%Y-%m-%dT%H:%MZ)"
   echo "# tests: the oracle against the committed goldens of the reference (thread file of the stress fixture, X-drop blocks and"
@@ -20,7 +21,7 @@ FLAGS="-O1 -g -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -ffp-co
   echo "# binaries are left out (they would inherit the preloaded sanitizer runtime)"
   LD_PRELOAD="$(/usr/bin/gcc -print-file-name=libasan.so) $(/usr/bin/gcc -print-file-name=libubsan.so)" \
   ASAN_OPTIONS=detect_leaks=0:halt_on_error=0 UBSAN_OPTIONS=print_stacktrace=1 AG2_ORACLE_SO=$SO \
-    python -m pytest tests/test_oracle_mapper.py tests/test_oracle_pinned.py tests/test_oracle_pagraph.py tests/test_kmer_counter.py -q \
-      -k "golden or edge_cases or oracle_vs_reference or committed" 2>&1 | grep -v "^$" | tail -40
+    python -m pytest tests/test_oracle_mapper.py tests/test_oracle_pinned.py tests/test_oracle_pagraph.py tests/test_kmer_counter.py tests/test_oracle_diff.py -q \
+      -k "golden or edge_cases or oracle_vs_reference or committed or against_the_reference" 2>&1 | grep -v "^$" | tail -40
 } > "$OUT" 2>&1
 tail -5 "$OUT"

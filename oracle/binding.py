@@ -312,3 +312,89 @@ def parse_graph_dump(blob: bytes):
             edges = [tuple(int(x) for x in s.split(",")) for s in t[7 + npos:7 + npos + nedge]]
             cfgs[-1][int(t[1])] = (int(t[2]), pos, edges)
     return cfgs
+
+
+# ---- vanilla MECAT2 DiffAligner ("next"): oracle/ag2_diff.c against oracle/_ref/libref_mecat_vanilla.so ----
+REF_DIFF_SO = os.path.join(HERE, "_ref", "libref_mecat_vanilla.so")
+
+
+def have_diff_ref() -> bool:
+    return os.path.exists(REF_DIFF_SO)
+
+
+def _diff_block_args(Q, T, right_extend):
+    """The block as the aligner sees it: a pointer at its first base, running towards lower addresses when not right_extend.
+    Returns (buffers kept alive, q pointer, t pointer)."""
+    q, t = _u8(Q), _u8(T)
+    if right_extend:
+        return (q, t), q.ctypes.data, t.ctypes.data
+    qr, tr = np.ascontiguousarray(q[::-1]), np.ascontiguousarray(t[::-1])
+    return (qr, tr), qr.ctypes.data + max(len(qr) - 1, 0), tr.ctypes.data + max(len(tr) - 1, 0)
+
+
+class _DiffBase:
+    def _block(self, fn, handle, Q, T, right_extend):
+        keep, qp, tp = _diff_block_args(Q, T, right_extend)
+        out6 = (C.c_int * 6)()
+        cap = len(Q) + len(T) + 64
+        qs, ts = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+        args = [C.c_void_p(qp), len(Q), C.c_void_p(tp), len(T), int(bool(right_extend)), out6, qs.ctypes.data_as(C.c_void_p),
+                ts.ctypes.data_as(C.c_void_p)]
+        rc = fn(*([handle] + args if handle is not None else args))
+        del keep
+        n = out6[5]
+        return dict(rc=rc, q_s=out6[0], q_e=out6[1], t_s=out6[2], t_e=out6[3], dist=out6[4], n=n, qstr=qs[:n].tobytes(), tstr=ts[:n].tobytes())
+
+    def _go(self, fn, handle, q, qstart, t, tstart, min_aln, extra):
+        qq, tt = _u8(q), _u8(t)
+        out5 = (C.c_int * 5)()
+        cap = len(qq) + len(tt) + 64
+        qa, ta = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        args = [qq.ctypes.data_as(C.c_void_p), int(qstart), len(qq), tt.ctypes.data_as(C.c_void_p), int(tstart), len(tt), int(min_aln)] + extra + [out5, qa, ta]
+        ok = fn(*([handle] + args if handle is not None else args))
+        n = out5[4]
+        return dict(ok=int(ok), qoff=out5[0], qend=out5[1], toff=out5[2], tend=out5[3], aln_size=n, qaln=qa.raw[:n], taln=ta.raw[:n])
+
+
+class DiffOracle(_DiffBase):
+    """oracle/ag2_diff.c (codes 0..3 in)."""
+
+    def __init__(self) -> None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        self.lib = C.CDLL(ORACLE_SO)
+        self.lib.orc_diff_block.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        self.lib.orc_diff_go.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                         C.c_char_p, C.c_char_p]
+
+    def block(self, Q, T, right_extend=True):
+        return self._block(self.lib.orc_diff_block, None, Q, T, right_extend)
+
+    def go(self, q, qstart, t, tstart, min_aln=0, large_block=0):
+        return self._go(self.lib.orc_diff_go, None, q, qstart, t, tstart, min_aln, [int(large_block)])
+
+
+class DiffRef(_DiffBase):
+    """The unmodified vanilla-MECAT2 DiffAligner (oracle/ref_diff_shim.cpp)."""
+
+    def __init__(self, large_block: int = 0) -> None:
+        self.lib = C.CDLL(REF_DIFF_SO)
+        L = self.lib
+        L.ref_diff_new.restype = C.c_void_p
+        L.ref_diff_new.argtypes = [C.c_int]
+        L.ref_diff_free.argtypes = [C.c_void_p]
+        L.ref_diff_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p]
+        L.ref_diff_go.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                  C.c_char_p, C.c_char_p]
+        self.x = C.c_void_p(L.ref_diff_new(int(large_block)))
+
+    def close(self) -> None:
+        if self.x:
+            self.lib.ref_diff_free(self.x)
+            self.x = None
+
+    def block(self, Q, T, right_extend=True):
+        return self._block(self.lib.ref_diff_block, self.x, Q, T, right_extend)
+
+    def go(self, q, qstart, t, tstart, min_aln=0):
+        return self._go(self.lib.ref_diff_go, self.x, q, qstart, t, tstart, min_aln, [])
