@@ -7,7 +7,10 @@ is one pass of the extension over the whole read batch.
 
   value : whole-job aligned Gbp/s with reads, reference and candidates already resident in HBM
   e2e   : the same through the reference-facing C-ABI calls with HOST (pinned) buffers: ASCII reads
-          host->device + pack, candidates up, records and both alignment strings device->host
+          host->device + pack, candidates up, records and the alignments as 2-bit ops device->host
+          (e2e.e2e_ascii: with both ASCII alignment strings instead)
+  full_path : BASELINE configs[2] per GPU -- 250 k reads against a 250 Mb reference through the whole
+          per-read path (ag2_map_reads), resident and from host buffers, with its own roofline
   roofline / cpu_baseline : see DESIGN.md "Measurement"
 
 `--impl reference` times the reference's own CPU implementation of the same stage (the unmodified
